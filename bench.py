@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — retrieval queries/s of the motion-retrieval hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3q1|c3q4096|c4]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+    python bench.py --impl reference ...      # the reference's CPU call pattern (oracle port)
+
+A step = one pass of the hot path (scan -> top-k -> fp32 re-score -> filter [-> gather]) over
+one batch of synthetic queries. Default workload c1 = BASELINE.json configs[1]: 1 M-entry
+768-d table, ONE query per step, k = 12 (= ref_video_num + 3), `video != own` post-filter.
+With N > 1 the same table is row-sharded over the ranks (strong scaling) and a step also
+contains the all-gather of per-shard candidates and the merge. Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+DIM, TOPK, K_REF, L_TOK, C_FEAT = 768, 12, 9, 25, 1024
+WORKLOADS = {
+    # name: (rows, queries per step, data kind, description)
+    "c1": (1_000_000, 1, "clustered", "1M-entry DB, single-query top-12 (HBM-streaming scan)"),
+    "c2": (1_000_000, 4096, "clustered", "1M-entry DB, 4096-query batch top-12 (tcgen05 scan, fused epilogue top-k)"),
+    "c3q1": (10_000_000, 1, "clustered", "10M-entry DB row-sharded, single query"),
+    "c3q4096": (10_000_000, 4096, "clustered", "10M-entry DB row-sharded, 4096-query batch"),
+    "c4": (1_000_000, 16, "clustered", "1M-entry DB, 16-query batch + gather into CAMA context [16,250,1024] bf16"),
+}
+POOL = 16  # distinct query batches cycled through the steps
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        p = json.loads(f.read_text())
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.file = gpu_index, None, None
+
+    def start(self):
+        try:
+            self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [r.split(",") for r in Path(self.file.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.file.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
+
+
+# ================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import motionrag_b200 as m
+    from motionrag_b200 import synthetic
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pk = peaks()
+    stores = {}
+
+    def get_store(n_rows, kind):
+        key = (n_rows, kind)
+        if key not in stores:
+            for old in list(stores):          # one table resident at a time
+                stores.pop(old)[0].close()
+            torch.cuda.empty_cache()
+            rps = -(-n_rows // world)
+            rps = -(-rps // synthetic.CHUNK_ROWS) * synthetic.CHUNK_ROWS
+            lo, hi = min(n_rows, rank * rps), min(n_rows, (rank + 1) * rps)
+            st = m.EmbeddingStore(DIM, max(hi - lo, 1), dev)
+            synthetic.fill_store(st, hi - lo, kind, seed=0, first_row=lo)
+            st.set_groups(synthetic.groups(hi - lo, lo, dev))
+            stores[key] = (st, m.ShardedRetriever(st, rank, world, rps), rps, lo, hi)
+        return stores[key]
+
+    def make_queries(st, nq, seed):
+        """POOL batches of nq un-normalised queries near rows of rank 0's shard, same on all ranks."""
+        g = torch.Generator(device=dev).manual_seed(seed)
+        src = torch.randint(0, len(st), (POOL, nq), generator=g, device=dev)
+        q = synthetic.queries_from_rows(st.rows_f32()[src.flatten()], seed=seed + 1).view(POOL, nq, DIM)
+        ex = (src // 3).to(torch.int32)
+        if world > 1:
+            dist.broadcast(q, 0)
+            dist.broadcast(ex, 0)
+        return q.contiguous(), ex.contiguous()
+
+    def measure(name, steps, warmup, with_e2e=True, sample_clocks=False):
+        n_rows, nq, kind, desc = WORKLOADS[name]
+        st, retr, rps, lo, hi = get_store(n_rows, kind)
+        q, ex = make_queries(st, nq, seed=100 + nq)
+        gather = name == "c4"
+        ctx = None
+        if gather:
+            n_feat = 65_536                    # feature rows kept resident for the gather (3.4 GB bf16)
+            table = synthetic.features(n_feat, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev)
+            gg = torch.Generator(device=dev).manual_seed(4)
+            sos = (torch.randn(1, L_TOK, C_FEAT, generator=gg, device=dev) / 32).bfloat16()
+            un = torch.randn(L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
+            cond = torch.randn(nq, (K_REF + 1) * L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
+            ctx = m.MotionContext(m.FeatureTable(table), sos, un, pe_max_length=256)
+
+        def step(i, timings=None):
+            j = i % POOL
+            if timings is not None and world == 1:
+                r = st.search(q[j], TOPK, exclude_group=ex[j], filter_mode="post", timings=timings)
+            else:
+                r = retr.search(q[j], TOPK, exclude_group=ex[j], filter_mode="post")
+            if gather:
+                ref = torch.where(r.index[:, :K_REF] >= 0, r.index[:, :K_REF] % n_feat, r.index[:, :K_REF])
+                return ctx.build(ref.contiguous(), cond)
+            return r
+
+        for i in range(warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        launches0 = m.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        launches = m.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        ms_total = allmax(e0.elapsed_time(e1))
+        out = {"workload": name, "desc": desc, "db_rows": n_rows, "queries_per_step": nq, "steps": steps,
+               "ms_per_step": ms_total / steps, "value": steps * nq / (ms_total / 1e3), "gpu_launches": launches}
+        # per-step latency distribution (device time per step, max over ranks)
+        lat = []
+        for i in range(min(steps, 200)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            a.record()
+            step(i)
+            b.record()
+            b.synchronize()
+            lat.append(a.elapsed_time(b))
+        lat_t = torch.tensor(lat, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
+        lat = sorted(lat_t.tolist())
+        out["p50_ms"] = lat[len(lat) // 2]
+        out["p95_ms"] = lat[min(len(lat) - 1, int(len(lat) * 0.95))]
+        # roofline of the dominant (scan) kernel: event-bracketed launches on this rank's shard
+        tm = []
+        for i in range(min(steps, 50)):
+            st.search(q[i % POOL], TOPK, exclude_group=ex[i % POOL], filter_mode="post", timings=tm)
+        scan_ms = allmax(statistics.mean(t[0] for t in tm))
+        plan = st.plan(nq, k=TOPK, filter_mode="post")
+        if plan.path == 3:
+            ach = plan.scan_flops / (scan_ms / 1e3) / 1e12
+            peak = pk["bf16_tflops_sustained"] if steps * scan_ms > 2000 else pk["bf16_tflops"]
+            out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                               "frac": ach / peak, "traffic": None, "kernel": "k2_batch_kernel",
+                               "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / (ms_total / steps),
+                               "peak_source": pk["source"],
+                               "plan": {"grid": plan.grid, "m_tiles": plan.m_tiles, "n_tiles": plan.n_tiles,
+                                        "chunks": plan.chunks}}
+        else:
+            ach = plan.scan_bytes / (scan_ms / 1e3) / 1e9
+            out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                               "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel": "k1_stream_kernel<float>",
+                               "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / (ms_total / steps),
+                               "peak_source": pk["source"], "bytes_per_launch": plan.scan_bytes,
+                               "plan": {"grid": plan.grid, "cands_per_query": plan.cands_per_query}}
+        out["total_ms_single_rank_call"] = statistics.mean(t[1] for t in tm)
+        if clocks:
+            out["clocks"] = clocks
+
+        # end to end: HOST query buffers in, HOST results out, every step
+        if with_e2e:
+            q_host = q.cpu().pin_memory()
+            ex_host = ex.cpu().pin_memory()
+            if world == 1 and not gather and nq == 1:
+                # the reference-facing call itself: RAGDatabase.text_search(ndarray) -> list[dict]
+                videos = [f"video_{j // 3:07d}.mp4" for j in range(n_rows)]
+                import numpy as np
+                cols = {"video": np.array(videos), "start_sec": np.zeros(n_rows), "end_sec": np.ones(n_rows) * 2}
+                db = m.RAGDatabase.from_store(st, cols)
+                qn = q_host.numpy()
+                wh = [f'video != "video_{int(ex_host[j, 0]):07d}.mp4"' for j in range(POOL)]
+
+                def e2e_step(i):
+                    j = i % POOL
+                    return db.text_search(qn[j, 0], top_k=TOPK, where=wh[j], select=["video", "start_sec", "end_sec"])
+                api = "RAGDatabase.text_search(ndarray[768]) -> list[dict]"
+                d2h = TOPK * 12
+            else:
+                def e2e_step(i):
+                    j = i % POOL
+                    qd = q_host[j].to(dev, non_blocking=True)
+                    exd = ex_host[j].to(dev, non_blocking=True)
+                    r = retr.search(qd, TOPK, exclude_group=exd, filter_mode="post")
+                    if gather:
+                        ref = torch.where(r.index[:, :K_REF] >= 0, r.index[:, :K_REF] % n_feat, r.index[:, :K_REF])
+                        x = ctx.build(ref.contiguous(), cond)
+                        return x.float().sum().item(), r.index.cpu()
+                    return r.distance.cpu(), r.index.cpu()
+                api = "ShardedRetriever.search(pinned host queries) -> host (distance, index)" + (" + gather_context" if gather else "")
+                d2h = nq * TOPK * 12 + (4 if gather else 0)
+            for i in range(max(3, warmup // 2)):
+                e2e_step(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                e2e_step(i)
+            torch.cuda.synchronize()
+            dt = allmax(time.perf_counter() - t0)
+            out["e2e"] = {"value": steps * nq / dt, "unit": "queries/s", "ms_per_step": dt / steps * 1e3,
+                          "h2d_bytes_per_step": nq * (DIM * 4 + 4), "d2h_bytes_per_step": d2h, "api": api}
+        return out
+
+    main = measure(args.workload, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
+    extra = {}
+    if not args.no_extras:
+        todo = [w for w in ("c1", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
+        for w in todo:
+            try:
+                steps = 200 if WORKLOADS[w][1] == 1 else (30 if WORKLOADS[w][1] <= 16 else 8)
+                extra[w] = measure(w, steps, 3, with_e2e=(w in ("c2", "c4")))
+            except Exception as e:  # an extra must never take the headline line down
+                extra[w] = {"error": f"{type(e).__name__}: {e}"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.workload, budget_s=12.0)
+
+    if rank == 0:
+        n_rows, nq, kind, desc = WORKLOADS[args.workload]
+        line = {"metric": "retrieval queries/sec", "value": main["value"], "unit": "queries/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic (seeded clustered unit vectors, un-normalised queries; random-init features)",
+                "config": {"workload": f"{args.workload}: {desc}", "db_rows": n_rows, "dim": DIM,
+                           "queries_per_step": nq, "top_k": TOPK, "filter": 'post-filter video != own',
+                           "sharding": f"rows/{world}", "l2_flush": "none needed: table (>=3 GB) >> 126 MB L2",
+                           "query_pool": POOL},
+                "p50_latency_ms": main["p50_ms"], "p95_latency_ms": main["p95_ms"],
+                "e2e": main.get("e2e"), "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
+                "cpu_baseline": cpu, "clocks": main.get("clocks"), "extra": extra}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ================================================================================================
+def cpu_baseline(workload: str, budget_s: float = 12.0, steps: int | None = None, warmup: int = 1):
+    """The reference's call pattern (one fp32 flat scan per query) on this host's cores, on a
+    bounded sample of the same workload: full-size table (capped at 2 M rows for host RAM and
+    generation time), as many queries as fit the time budget."""
+    import torch
+
+    from oracle import cpu_port
+    n_rows, nq, kind, desc = WORKLOADS[workload]
+    n = min(n_rows, 2_000_000)
+    g = torch.Generator().manual_seed(0)
+    db = torch.empty(n, DIM)
+    for s in range(0, n, 1 << 17):
+        e = min(n, s + (1 << 17))
+        db[s:e] = torch.nn.functional.normalize(torch.randn(e - s, DIM, generator=g), dim=-1)
+    db_sq = (db * db).sum(-1)
+    groups = (torch.arange(n) // 3).to(torch.int32)
+    src = torch.randint(0, n, (4096,), generator=g)
+    q = db[src] * (5 + 10 * torch.rand(4096, 1, generator=g))
+    ex = groups[src]
+    cores = torch.get_num_threads()
+    for i in range(warmup):
+        cpu_port.search_loop(db, db_sq, q[i:i + 1], TOPK, groups, ex[i:i + 1])
+    done, t0 = 0, time.perf_counter()
+    if nq == 1 or workload == "c4":
+        # per-query loop: exactly the reference's behaviour
+        limit = steps if steps is not None else 10 ** 9
+        while done < min(limit, 4096) and (steps is not None or time.perf_counter() - t0 < budget_s):
+            cpu_port.search_loop(db, db_sq, q[done:done + 1], TOPK, groups, ex[done:done + 1])
+            done += 1
+        kind_s = "per-query loop (reference call pattern)"
+    else:
+        limit = (steps if steps is not None else 10 ** 9) * 64
+        while done < min(limit, 4096) and (steps is not None or time.perf_counter() - t0 < budget_s):
+            cpu_port.search_batched(db, db_sq, q[done:done + 64], TOPK)
+            done += 64
+        kind_s = "batched sgemm + topk, 64 queries per call (best-case CPU)"
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{done} queries against a {n}-row x {DIM} fp32 table, {kind_s}, torch {torch.__version__} fp32, "
+                      f"{dt:.1f} s; os.cpu_count()={os.cpu_count()}",
+            "ms_per_query": dt / max(done, 1) * 1e3, "rows": n}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path. LanceDB 0.14 is not
+    installable offline, so this is the oracle port (oracle/cpu_port.py) with every host thread
+    torch will use. Rank 0 only; other ranks exit 0."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    n_rows, nq, kind, desc = WORKLOADS[args.workload]
+    # a step = one query batch of the workload; bounded: at most `steps` steps of <= 64 queries
+    cpu = cpu_baseline(args.workload, steps=max(1, min(args.steps, 50)), warmup=max(1, min(args.warmup, 3)))
+    per_step = nq if nq <= 64 else 64
+    ms = cpu["ms_per_query"] * per_step
+    line = {"impl": "reference", "metric": "retrieval queries/sec", "value": cpu["value"], "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded unit vectors, un-normalised queries)",
+            "config": {"workload": f"{args.workload}: {desc}", "db_rows": n_rows, "dim": DIM,
+                       "queries_per_step": nq, "top_k": TOPK, "filter": 'post-filter video != own',
+                       "note": "LanceDB 0.14 (the reference's engine) is not installable offline; this arm is the "
+                               "fp32 CPU restatement of its flat scan, one scan per query like src/data/rag.py:54"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1", choices=list(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/*
+ * mrag.h — C ABI of the B200-native motion-retrieval hot path (libmrag.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * The reference (MCG-NJU/MotionRAG) is pure Python and has no FFI of its own;
+ * each entry point below names the reference call it replaces (file:line relative
+ * to the reference root) — the binding a maintainer adds is the ctypes stub shown
+ * in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative mrag_status on error;
+ *     mrag_last_error() returns a thread-local human-readable message.
+ *   - "dev" pointers are CUDA device pointers on the store's device; "host" pointers
+ *     are ordinary (ideally pinned) host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *     No call synchronises the device unless documented (the *_host variants do).
+ *   - nothing here ever falls back to a CPU implementation: without a CUDA device
+ *     of compute capability 10.x the compute calls fail with MRAG_ERR_DEVICE.
+ */
+#ifndef MRAG_H_
+#define MRAG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRAG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MRAG_API __attribute__((visibility("default")))
+#else
+#define MRAG_API
+#endif
+
+typedef enum mrag_status {
+  MRAG_OK = 0,
+  MRAG_ERR_ARG = -1,         /* bad argument (NULL, size, unsupported dim / k) */
+  MRAG_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  MRAG_ERR_DEVICE = -3,      /* no sm_100-class device: this library has no other path */
+  MRAG_ERR_CAPACITY = -4,    /* store or workspace too small */
+  MRAG_ERR_UNSUPPORTED = -5  /* valid request this build does not implement */
+} mrag_status;
+
+/* distance definitions of LanceDB 0.14 (reference: src/data/rag.py:54 — the
+ * reference never sets a metric, so MRAG_METRIC_L2 is what it runs). */
+typedef enum mrag_metric {
+  MRAG_METRIC_L2 = 0,      /* _distance = sum (q-d)^2            */
+  MRAG_METRIC_COSINE = 1,  /* _distance = 1 - q.d / (|q| |d|)    */
+  MRAG_METRIC_DOT = 2      /* _distance = 1 - q.d                */
+} mrag_metric;
+
+/* which scan kernel serves the query batch */
+typedef enum mrag_path {
+  MRAG_PATH_AUTO = 0,        /* nq <= 4: STREAM_F32, else TENSOR_BF16 */
+  MRAG_PATH_STREAM_F32 = 1,  /* K1 on the fp32 master rows (exact ranking, 4 B/elt streamed) */
+  MRAG_PATH_STREAM_BF16 = 2, /* K1 on the bf16 shadow rows + fp32 re-rank (2 B/elt streamed) */
+  MRAG_PATH_TENSOR_BF16 = 3  /* K2 tcgen05 GEMM with fused epilogue top-k + fp32 re-rank */
+} mrag_path;
+
+/* `where video != "<own video>"` (reference: src/data/datamodule.py:235) */
+typedef enum mrag_filter {
+  MRAG_FILTER_NONE = 0,
+  MRAG_FILTER_POST = 1, /* LanceDB 0.14 default: k nearest first, then drop excluded rows (<= k results) */
+  MRAG_FILTER_PRE = 2   /* drop excluded rows first, then k nearest */
+} mrag_filter;
+
+typedef struct mrag_store mrag_store; /* opaque: HBM-resident, row-major, immutable between appends */
+
+typedef struct mrag_store_info {
+  int32_t dim;
+  int32_t device;
+  int64_t n_rows;
+  int64_t capacity_rows;
+  int32_t has_groups;
+  int32_t sm_count;
+  const void* rows_f32_dev;  /* [n_rows, dim] float32, L2-normalised when appended with normalise=1 */
+  const void* rows_bf16_dev; /* [n_rows, dim] bfloat16 shadow of the same rows */
+  const void* groups_dev;    /* [n_rows] int32 group id per row (video identity) or NULL */
+} mrag_store_info;
+
+typedef struct mrag_search_params {
+  int32_t k;           /* results per query, 1..32 (reference: top_k, src/data/rag.py:36) */
+  int32_t metric;      /* mrag_metric */
+  int32_t path;        /* mrag_path */
+  int32_t refine;      /* candidates re-scored in fp32 per query (k..64); 0 = default max(32, k).
+                          Plays the role of the reference's refine_factor (src/data/rag.py:37). */
+  int32_t filter_mode; /* mrag_filter; needs store groups + exclude_group */
+  int32_t reserved;
+  int64_t index_base;  /* added to local row numbers in out_idx (row-sharded stores) */
+} mrag_search_params;
+
+MRAG_API int mrag_abi_version(void);
+MRAG_API const char* mrag_last_error(void);
+
+/* ---- store: replaces lancedb.connect/open_table (src/data/rag.py:13-14) and the vector
+ *      column written by tools/build_rag_database.py:35-50 ------------------------------ */
+MRAG_API int mrag_store_create(int32_t dim, int64_t capacity_rows, int32_t device, mrag_store** out);
+MRAG_API int mrag_store_destroy(mrag_store* s);
+/* append n fp32 rows (host or device memory); normalise != 0 L2-normalises each row first
+ * (tools/build_rag_database.py:31-37 stores normalised vectors); also refreshes the bf16 shadow */
+MRAG_API int mrag_store_append(mrag_store* s, const float* rows, int64_t n, int32_t rows_on_device,
+                      int32_t normalise, void* stream);
+/* int32 group id per row for the `video != x` filter; n must equal the current row count */
+MRAG_API int mrag_store_set_groups(mrag_store* s, const int32_t* groups, int64_t n, int32_t on_device,
+                          void* stream);
+MRAG_API int mrag_store_get_info(const mrag_store* s, mrag_store_info* out);
+
+/* ---- search: replaces table.search(vec, col).limit(k)[.where(..)] (src/data/rag.py:54-59) -- */
+typedef struct mrag_plan_info {
+  int32_t path;            /* resolved mrag_path (never AUTO) */
+  int32_t grid;            /* CTAs of the scan kernel (K1 or K2) */
+  int32_t cands_per_query; /* candidate keys the scan leaves per query for K3 */
+  int32_t rerank;          /* candidates K3 re-scores in fp32 */
+  int32_t m_tiles, n_tiles, chunks, tiles_per_chunk; /* K2 tiling (0 for K1) */
+  int64_t scan_bytes;      /* algorithmic bytes streamed by the scan kernel: n_rows*dim*elt */
+  int64_t scan_flops;      /* algorithmic flops: 2*nq*n_rows*dim */
+  size_t workspace_bytes;
+} mrag_plan_info;
+/* validates (store, nq, params) and reports how the call would run, including the workspace
+ * the caller must provide to mrag_search */
+MRAG_API int mrag_search_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p,
+                              mrag_plan_info* out);
+/* queries_dev [nq, dim] fp32 (not normalised, as in src/data/datamodule.py:300-302);
+ * exclude_group_dev [nq] int32 or NULL; outputs [nq, k]: ascending distance, ties by lowest
+ * row index, unused slots = (+inf, -1, -1). out_group_dev may be NULL. */
+MRAG_API int mrag_search(const mrag_store* s, const float* queries_dev, int32_t nq,
+                const mrag_search_params* p, const int32_t* exclude_group_dev,
+                float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream);
+/* mrag_search bracketed by CUDA events on `stream`: *scan_ms_out = duration of the scan kernel
+ * alone (K1 or K2), *total_ms_out = the whole call on the device. Synchronises the stream.
+ * Used by bench.py for the roofline of the dominant kernel. */
+MRAG_API int mrag_search_timed(const mrag_store* s, const float* queries_dev, int32_t nq,
+                const mrag_search_params* p, const int32_t* exclude_group_dev,
+                float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
+                void* workspace_dev, size_t workspace_bytes, void* stream,
+                float* scan_ms_out, float* total_ms_out);
+/* same call with HOST buffers: copies in, searches, copies out, synchronises the stream.
+ * Allocates its device scratch from the stream-ordered pool. */
+MRAG_API int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
+                     const mrag_search_params* p, const int32_t* exclude_group_host,
+                     float* out_dist_host, int64_t* out_idx_host, int32_t* out_group_host,
+                     void* stream);
+
+/* ---- cross-shard merge of per-shard results (after the all-gather of [nshards, nq, k]) ----
+ * Shard g's [nq, k_in] block of every field starts shard_stride_bytes * g after the field's
+ * base pointer (0 = dense [nshards, nq, k_in] arrays); this lets one packed per-rank record
+ * {dist, idx, group} travel in a single all-gather. Each shard's list must be sorted by
+ * (distance, index) and shards ordered by ascending row range. */
+MRAG_API int mrag_merge_topk(const float* cand_dist_dev, const int64_t* cand_idx_dev,
+                    const int32_t* cand_group_dev /* may be NULL */, int64_t shard_stride_bytes,
+                    int32_t nshards, int32_t nq,
+                    int32_t k_in, int32_t k_out, const int32_t* exclude_group_dev,
+                    int32_t filter_mode, float* out_dist_dev, int64_t* out_idx_dev,
+                    int32_t* out_group_dev /* may be NULL */, void* stream);
+
+/* ---- context gather: replaces get_ref_videos + encode_vision for the K references and the
+ *      context assembly x = cat([sos, feats[:, :-1]]) (+pe) (+cond)
+ *      (src/data/dataset.py:285-312, src/projects/condition/module.py:264-268, 298-301) ------
+ * shard_ptrs_dev: device array of nshards pointers to [rows_per_shard, L, C] feature blocks
+ *                 (local or peer-mapped); global row r lives in shard r / rows_per_shard.
+ * ref_idx_dev [b, K] int64 in similarity order (0 = most similar), -1 = missing/dropped.
+ * out [b, (K+1)*L, C]; group 0 = sos, group g>=1 = feature of reference rank K-g.
+ * dtype: 0 = bfloat16, 1 = float32 (all feature-like tensors share it).
+ * pe_dev [(K+1)*L, C] and cond_dev [b, (K+1)*L, C] may be NULL; when given the adds happen in
+ * the reference's order and rounding (x + pe, then += cond, each rounded to dtype). */
+MRAG_API int mrag_gather_context(const void* const* shard_ptrs_dev, int32_t nshards,
+                        int64_t rows_per_shard, const int64_t* ref_idx_dev, const void* sos_dev,
+                        const void* uncond_row_dev, const void* pe_dev, const void* cond_dev,
+                        void* out_dev, int32_t b, int32_t K, int32_t L, int32_t C, int32_t dtype,
+                        void* stream);
+
+/* plain cudaMalloc / cudaFree on `device` (IPC-exportable blocks for sharded feature tables) */
+MRAG_API int mrag_device_alloc(int32_t device, size_t bytes, void** dev_ptr_out);
+MRAG_API int mrag_device_free(int32_t device, void* dev_ptr);
+
+/* ---- peer memory plumbing for row-sharded feature tables (one process per GPU) ------------ */
+MRAG_API int mrag_ipc_export(const void* dev_ptr, void* handle_out_64B);
+MRAG_API int mrag_ipc_open(const void* handle_64B, void** dev_ptr_out);
+MRAG_API int mrag_ipc_close(void* dev_ptr);
+
+/* ---- introspection used by bench.py / tests -------------------------------------------- */
+/* name and duration hooks: number of kernels launched by this library on this thread so far */
+MRAG_API int64_t mrag_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRAG_H_ */

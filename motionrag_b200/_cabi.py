@@ -1,0 +1,114 @@
+"""ctypes binding of libmrag.so — the only way Python reaches the CUDA kernels.
+
+There is deliberately no fallback: if the shared library is missing or a call fails the
+caller gets an exception (`MragError`), never a CPU substitute.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "_lib" / "libmrag.so"
+
+ABI_VERSION = 1
+
+# enums of include/mrag.h
+METRIC = {"l2": 0, "cosine": 1, "dot": 2}
+PATH = {"auto": 0, "stream_f32": 1, "stream_bf16": 2, "tensor_bf16": 3}
+FILTER = {"none": 0, "post": 1, "pre": 2}
+STATUS = {0: "MRAG_OK", -1: "MRAG_ERR_ARG", -2: "MRAG_ERR_CUDA", -3: "MRAG_ERR_DEVICE",
+          -4: "MRAG_ERR_CAPACITY", -5: "MRAG_ERR_UNSUPPORTED"}
+
+
+class MragError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class StoreInfo(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("device", C.c_int32), ("n_rows", C.c_int64),
+                ("capacity_rows", C.c_int64), ("has_groups", C.c_int32), ("sm_count", C.c_int32),
+                ("rows_f32_dev", C.c_void_p), ("rows_bf16_dev", C.c_void_p),
+                ("groups_dev", C.c_void_p)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("metric", C.c_int32), ("path", C.c_int32),
+                ("refine", C.c_int32), ("filter_mode", C.c_int32), ("reserved", C.c_int32),
+                ("index_base", C.c_int64)]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [("path", C.c_int32), ("grid", C.c_int32), ("cands_per_query", C.c_int32),
+                ("rerank", C.c_int32), ("m_tiles", C.c_int32), ("n_tiles", C.c_int32),
+                ("chunks", C.c_int32), ("tiles_per_chunk", C.c_int32), ("scan_bytes", C.c_int64),
+                ("scan_flops", C.c_int64), ("workspace_bytes", C.c_size_t)]
+
+
+# name -> (restype, argtypes); mirrors include/mrag.h one to one (tests check the list)
+SIGNATURES = {
+    "mrag_abi_version": (C.c_int, []),
+    "mrag_last_error": (C.c_char_p, []),
+    "mrag_launch_count": (C.c_int64, []),
+    "mrag_store_create": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mrag_store_destroy": (C.c_int, [C.c_void_p]),
+    "mrag_store_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "mrag_store_set_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "mrag_store_get_info": (C.c_int, [C.c_void_p, C.POINTER(StoreInfo)]),
+    "mrag_search_plan": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.POINTER(PlanInfo)]),
+    "mrag_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mrag_search_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "mrag_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrag_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "mrag_gather_context": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p]),
+    "mrag_device_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "mrag_device_free": (C.c_int, [C.c_int32, C.c_void_p]),
+    "mrag_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mrag_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mrag_ipc_close": (C.c_int, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load(path: os.PathLike | str | None = None) -> C.CDLL:
+    """Load libmrag.so (once). Raises if it has not been built — there is no other path."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = Path(path) if path is not None else LIB_PATH
+    if not p.exists():
+        raise MragError(-3, f"{p} not found: build it with `python -m motionrag_b200.build` "
+                            "(the CUDA extension is mandatory, there is no CPU fallback)")
+    lib = C.CDLL(str(p))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.mrag_abi_version()
+    if got != ABI_VERSION:
+        raise MragError(-5, f"libmrag ABI {got} != binding ABI {ABI_VERSION}")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().mrag_last_error()
+        raise MragError(rc, msg.decode() if msg else "")
+
+
+def launch_count() -> int:
+    return int(load().mrag_launch_count())

@@ -1,0 +1,141 @@
+"""Context assembly for the CAMA causal motion transformer — face 2 of the drop-in boundary.
+
+`gather_context` produces, with ONE kernel launch (K4, mrag_gather_context), the tensor `x` that
+the reference's ActionTransformer.forward builds at src/projects/condition/module.py:298-301
+from the K retrieved clips, without decoding or re-encoding them: rows of a precomputed
+feature table are packed straight into the `[b, (K+1)*L, C]` layout, optionally with the
+sinusoid position table and the condition embedding added in the reference's order/rounding.
+
+`MotionContext` mirrors the pieces of ActionTransformer a caller touches (get_mask, the flipped
+similarity order of batch_forward :318-319, the CFG "uncond" row of predict :326-330) and
+`attach` lets a real ActionTransformer accept `batch['ref_index']` in place of
+`batch['ref_videos']`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check
+from .store import FeatureTable, _stream_ptr
+
+
+def sinusoid_table(n_position: int, d_hid: int) -> torch.Tensor:
+    """Same table as SinusoidPositionalEmbeddings (position_embeddings.py:159-170): float64
+    angles, sin on even / cos on odd columns, stored float32. Shape [n_position, d_hid]."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)
+    t = pos / np.power(10000, 2 * (j // 2) / d_hid)[None, :]
+    t[:, 0::2] = np.sin(t[:, 0::2])
+    t[:, 1::2] = np.cos(t[:, 1::2])
+    return torch.from_numpy(t.astype(np.float32))
+
+
+def block_causal_mask(num_groups: int, group_tokens: int, device=None) -> torch.Tensor:
+    """ActionTransformer.get_mask (module.py:131-135): bool, True = blocked."""
+    g = torch.arange(num_groups * group_tokens, device=device) // group_tokens
+    return g[None, :] > g[:, None]
+
+
+def _ptr(t: torch.Tensor | None):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def gather_context(table: FeatureTable, ref_index: torch.Tensor, sos: torch.Tensor,
+                   uncond_row: torch.Tensor, pos_table: torch.Tensor | None = None,
+                   cond: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """ref_index [b, K] int64 (similarity order, 0 = most similar, -1 = dropped/missing) ->
+    x [b, (K+1)*L, C] in the table's dtype. sos [L, C] / [1, L, C]; uncond_row [L, C];
+    pos_table [>= (K+1)*L, C] already in the table's dtype (the reference casts its fp32 table
+    with .type_as(x) before adding); cond [b, (K+1)*L, C]."""
+    lib = _cabi.load()
+    dev, dt = table.device, table.local.dtype
+    if ref_index.device != dev or ref_index.dtype != torch.int64 or ref_index.ndim != 2:
+        raise ValueError("ref_index must be an int64 [b, K] tensor on the table's device")
+    ref_index = ref_index.contiguous()
+    b, K = ref_index.shape
+    L, Cd = table.L, table.Cdim
+    n_tok = (K + 1) * L
+
+    def chk(name, t, shape):
+        if t is None:
+            return None
+        if t.device != dev or t.dtype != dt:
+            raise ValueError(f"{name} must be {dt} on {dev}")
+        t = t.reshape(shape) if t.numel() == int(np.prod(shape)) else t
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+        return t.contiguous()
+
+    sos = chk("sos", sos, (L, Cd))
+    uncond_row = chk("uncond_row", uncond_row, (L, Cd))
+    cond = chk("cond", cond, (b, n_tok, Cd))
+    if pos_table is not None:
+        if pos_table.device != dev or pos_table.dtype != dt or pos_table.ndim != 2 or pos_table.shape[0] < n_tok:
+            raise ValueError(f"pos_table must be {dt} [>={n_tok}, {Cd}] on {dev}")
+        pos_table = pos_table[:n_tok].contiguous()
+    if out is None:
+        out = torch.empty((b, n_tok, Cd), dtype=dt, device=dev)
+    elif tuple(out.shape) != (b, n_tok, Cd) or out.dtype != dt or not out.is_contiguous():
+        raise ValueError("bad out tensor")
+    if not table.complete:
+        raise RuntimeError("feature table has unmapped peer shards; call parallel.open_peer_tables first")
+    check(lib.mrag_gather_context(
+        _ptr(table.shard_ptrs), table.n_shards, table.rows_per_shard, _ptr(ref_index), _ptr(sos),
+        _ptr(uncond_row), _ptr(pos_table), _ptr(cond), _ptr(out), b, K, L, Cd,
+        0 if dt == torch.bfloat16 else 1, _stream_ptr(dev)))
+    return out
+
+
+class MotionContext:
+    """Holds what the gather needs besides the table: SOS block, uncond row, position table."""
+
+    def __init__(self, table: FeatureTable, sos_token: torch.Tensor, uncond_row: torch.Tensor,
+                 pe_max_length: int | None = 256):
+        dt, dev = table.local.dtype, table.device
+        self.table = table
+        self.sos = sos_token.detach().to(dev, dt).reshape(table.L, table.Cdim).contiguous()
+        self.uncond_row = uncond_row.detach().to(dev, dt).reshape(table.L, table.Cdim).contiguous()
+        # the reference keeps an fp32 table and casts per call (.type_as(x)); cast once here
+        self.pos_table = (sinusoid_table(pe_max_length, table.Cdim).to(dev).to(dt)
+                          if pe_max_length else None)
+
+    def get_mask(self, num_frames: int, frame_tokens: int) -> torch.Tensor:
+        return block_causal_mask(num_frames, frame_tokens, self.table.device)
+
+    def build(self, ref_index: torch.Tensor, condition_emb: torch.Tensor | None = None,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+        return gather_context(self.table, ref_index, self.sos, self.uncond_row, self.pos_table,
+                              condition_emb, out)
+
+    def uncond_action_emb(self, b: int) -> torch.Tensor:
+        """predict()'s CFG branch (module.py:327-329): encode_vision(zeros)[:, 0] per sample."""
+        return self.uncond_row[None].expand(b, -1, -1)
+
+
+def attach(model, ctx: MotionContext):
+    """Teach a reference ActionTransformer to take `batch['ref_index']` ([b, K] int64 row ids
+    from retrieval) instead of `batch['ref_videos']` for inference (`return_loss=False`),
+    producing the same prediction tensor as module.py:292-315 with encode_vision of the K
+    references replaced by the table gather. The condition embedding is still computed by the
+    model's own encode_condition from `batch['ref_images']` ([b, K+1, C, H, W], refs flipped +
+    target first frame, as batch_forward builds them at :321)."""
+    orig = model.batch_forward
+
+    def batch_forward(batch, return_loss: bool = True, ignore_ref_loss: bool = False):
+        if 'ref_index' not in batch:
+            return orig(batch, return_loss, ignore_ref_loss)
+        if return_loss:
+            raise NotImplementedError("the table-backed path serves inference (predict); "
+                                      "training losses need the target clip's own features")
+        cond = model.encode_condition(batch['ref_images']) if 'ref_images' in batch else batch.get('condition_emb')
+        x = ctx.build(batch['ref_index'], cond)
+        K = batch['ref_index'].shape[1]
+        pred = model.transformer(x, ctx.get_mask(K + 1, ctx.table.L))
+        return pred.reshape(pred.shape[0], K + 1, ctx.table.L, -1)
+
+    model.batch_forward = batch_forward
+    return model

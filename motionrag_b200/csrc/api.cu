@@ -1,0 +1,478 @@
+// C ABI of libmrag (see include/mrag.h). Host-side orchestration only: argument checks,
+// workspace carving and kernel launches on the caller's stream. No CPU compute path exists.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/mrag.h"
+#include "kernels.h"
+
+namespace mrag {
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+void note_launch(int n) { g_launches += n; }
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(MRAG_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CK(call)                                          \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace mrag
+
+using namespace mrag;
+
+struct mrag_store {
+  int32_t dim = 0;
+  int32_t device = 0;
+  int32_t sm_count = 0;
+  int64_t n_rows = 0;
+  int64_t capacity = 0;  // rows, multiple of 256
+  float* rows_f32 = nullptr;
+  void* rows_bf16 = nullptr;
+  int32_t* groups = nullptr;
+  bool has_groups = false;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// resolved execution plan of one search call
+struct Plan {
+  int path;       // MRAG_PATH_* (never AUTO)
+  int kc;         // candidates per CTA (K1) / per chunk (K2)
+  int rerank;     // entries re-scored by K3
+  int k1_grid = 0;
+  K2Plan k2{};
+  int cands_per_query = 0;
+  size_t off_cand = 0, off_qbf16 = 0, total = 0;
+};
+
+int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan* out) {
+  if (!s || !p) return fail(MRAG_ERR_ARG, "null store or params");
+  if (nq < 1) return fail(MRAG_ERR_ARG, "nq must be >= 1 (got %d)", nq);
+  if (p->k < 1 || p->k > 32) return fail(MRAG_ERR_ARG, "k must be in 1..32 (got %d)", p->k);
+  if (p->metric < 0 || p->metric > 2) return fail(MRAG_ERR_ARG, "unknown metric %d", p->metric);
+  if (p->filter_mode < 0 || p->filter_mode > 2)
+    return fail(MRAG_ERR_ARG, "unknown filter_mode %d", p->filter_mode);
+  if (s->n_rows < 1) return fail(MRAG_ERR_ARG, "store is empty");
+  int path = p->path;
+  if (path == MRAG_PATH_AUTO) path = (nq <= 4) ? MRAG_PATH_STREAM_F32 : MRAG_PATH_TENSOR_BF16;
+  int refine = p->refine > 0 ? p->refine : 32;
+  if (refine < p->k) refine = p->k;
+  if (refine > 64) refine = 64;
+  Plan pl;
+  pl.path = path;
+  if (path == MRAG_PATH_STREAM_F32 || path == MRAG_PATH_STREAM_BF16) {
+    if (!k1_supported(s->dim, nq))
+      return fail(MRAG_ERR_UNSUPPORTED,
+                  "streaming path needs nq <= 4 and dim in {256,512,768,1024} (nq=%d dim=%d)", nq,
+                  s->dim);
+    const bool f32 = (path == MRAG_PATH_STREAM_F32);
+    if (f32 && p->filter_mode != MRAG_FILTER_PRE) {
+      pl.kc = (p->k <= 12) ? 16 : 32;
+      pl.rerank = pl.kc;
+    } else {
+      pl.kc = 32;
+      pl.rerank = f32 ? (refine > 32 ? 32 : refine) : refine;
+    }
+    pl.k1_grid = k1_grid(s->n_rows, f32 ? 4 : 2, s->dim, nq, s->sm_count);
+    pl.cands_per_query = pl.k1_grid * pl.kc;
+  } else if (path == MRAG_PATH_TENSOR_BF16) {
+    if (!k2_supported(s->dim))
+      return fail(MRAG_ERR_UNSUPPORTED, "tensor path needs dim %% 64 == 0 (dim=%d)", s->dim);
+    pl.kc = kK2Cand;
+    pl.rerank = refine;
+    pl.k2 = k2_plan(s->n_rows, nq, s->sm_count);
+    pl.cands_per_query = pl.k2.chunks * kK2Cand;
+  } else {
+    return fail(MRAG_ERR_ARG, "unknown path %d", p->path);
+  }
+  if (pl.cands_per_query > 16384)
+    return fail(MRAG_ERR_UNSUPPORTED, "too many candidates per query (%d)", pl.cands_per_query);
+  size_t off = 0;
+  pl.off_cand = off;
+  off += align_up(size_t(nq) * pl.cands_per_query * sizeof(uint64_t), 256);
+  pl.off_qbf16 = off;
+  if (path == MRAG_PATH_TENSOR_BF16)
+    off += align_up(size_t(pl.k2.m_tiles) * 128 * s->dim * 2, 256);
+  pl.total = off;
+  *out = pl;
+  return MRAG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrag_abi_version(void) { return MRAG_ABI_VERSION; }
+const char* mrag_last_error(void) { return g_err; }
+int64_t mrag_launch_count(void) { return g_launches; }
+
+int mrag_store_create(int32_t dim, int64_t capacity_rows, int32_t device, mrag_store** out) {
+  if (!out) return fail(MRAG_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (dim < 64 || dim % 64 != 0 || dim > 4096)
+    return fail(MRAG_ERR_ARG, "dim must be a multiple of 64 in 64..4096 (got %d)", dim);
+  if (capacity_rows < 1 || capacity_rows >= 0x7fffff00ll)
+    return fail(MRAG_ERR_ARG, "capacity_rows out of range (%lld)", (long long)capacity_rows);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(MRAG_ERR_DEVICE, "no CUDA device visible: libmrag has no CPU path");
+  }
+  if (device < 0 || device >= ndev) return fail(MRAG_ERR_ARG, "device %d out of range", device);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(MRAG_ERR_DEVICE, "device %d is sm_%d%d; libmrag is built for sm_100a only", device,
+                prop.major, prop.minor);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MRAG_ERR_CUDA, "cannot select device %d", device);
+  mrag_store* s = new (std::nothrow) mrag_store();
+  if (!s) return fail(MRAG_ERR_CAPACITY, "host allocation failed");
+  s->dim = dim;
+  s->device = device;
+  s->sm_count = prop.multiProcessorCount;
+  s->capacity = (capacity_rows + 255) / 256 * 256;
+  const size_t elems = size_t(s->capacity) * dim;
+  cudaError_t e = cudaMalloc(&s->rows_f32, elems * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&s->rows_bf16, elems * 2);
+  if (e == cudaSuccess) e = cudaMalloc(&s->groups, size_t(s->capacity) * 4);
+  if (e == cudaSuccess) e = cudaMemset(s->rows_f32, 0, elems * 4);
+  if (e == cudaSuccess) e = cudaMemset(s->rows_bf16, 0, elems * 2);
+  if (e == cudaSuccess) e = cudaMemset(s->groups, 0xff, size_t(s->capacity) * 4);
+  if (e != cudaSuccess) {
+    cudaFree(s->rows_f32);
+    cudaFree(s->rows_bf16);
+    cudaFree(s->groups);
+    delete s;
+    return cuda_fail(e, "store allocation");
+  }
+  *out = s;
+  return MRAG_OK;
+}
+
+int mrag_store_destroy(mrag_store* s) {
+  if (!s) return MRAG_OK;
+  DeviceGuard g(s->device);
+  cudaFree(s->rows_f32);
+  cudaFree(s->rows_bf16);
+  cudaFree(s->groups);
+  delete s;
+  return MRAG_OK;
+}
+
+int mrag_store_append(mrag_store* s, const float* rows, int64_t n, int32_t rows_on_device,
+                      int32_t normalise, void* stream) {
+  if (!s || (!rows && n > 0)) return fail(MRAG_ERR_ARG, "null store or rows");
+  if (n < 0) return fail(MRAG_ERR_ARG, "negative row count");
+  if (s->n_rows + n > s->capacity)
+    return fail(MRAG_ERR_CAPACITY, "append of %lld rows exceeds capacity %lld (have %lld)",
+                (long long)n, (long long)s->capacity, (long long)s->n_rows);
+  if (n == 0) return MRAG_OK;
+  DeviceGuard g(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dst = s->rows_f32 + size_t(s->n_rows) * s->dim;
+  CK(cudaMemcpyAsync(dst, rows, size_t(n) * s->dim * 4,
+                     rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  CK(launch_prepare_rows(dst, static_cast<char*>(s->rows_bf16) + size_t(s->n_rows) * s->dim * 2, n,
+                         s->dim, normalise != 0, st));
+  s->n_rows += n;
+  return MRAG_OK;
+}
+
+int mrag_store_set_groups(mrag_store* s, const int32_t* groups, int64_t n, int32_t on_device,
+                          void* stream) {
+  if (!s || !groups) return fail(MRAG_ERR_ARG, "null store or groups");
+  if (n != s->n_rows)
+    return fail(MRAG_ERR_ARG, "groups length %lld != row count %lld", (long long)n,
+                (long long)s->n_rows);
+  DeviceGuard g(s->device);
+  CK(cudaMemcpyAsync(s->groups, groups, size_t(n) * 4,
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                     static_cast<cudaStream_t>(stream)));
+  s->has_groups = true;
+  return MRAG_OK;
+}
+
+int mrag_store_get_info(const mrag_store* s, mrag_store_info* out) {
+  if (!s || !out) return fail(MRAG_ERR_ARG, "null argument");
+  out->dim = s->dim;
+  out->device = s->device;
+  out->n_rows = s->n_rows;
+  out->capacity_rows = s->capacity;
+  out->has_groups = s->has_groups ? 1 : 0;
+  out->sm_count = s->sm_count;
+  out->rows_f32_dev = s->rows_f32;
+  out->rows_bf16_dev = s->rows_bf16;
+  out->groups_dev = s->has_groups ? s->groups : nullptr;
+  return MRAG_OK;
+}
+
+int mrag_search_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p,
+                     mrag_plan_info* out) {
+  if (!out) return fail(MRAG_ERR_ARG, "out is null");
+  Plan pl;
+  int rc = make_plan(s, nq, p, &pl);
+  if (rc != MRAG_OK) return rc;
+  memset(out, 0, sizeof(*out));
+  out->path = pl.path;
+  out->cands_per_query = pl.cands_per_query;
+  out->rerank = pl.rerank;
+  const bool tensor = (pl.path == MRAG_PATH_TENSOR_BF16);
+  out->grid = tensor ? pl.k2.grid : pl.k1_grid;
+  if (tensor) {
+    out->m_tiles = pl.k2.m_tiles;
+    out->n_tiles = pl.k2.n_tiles;
+    out->chunks = pl.k2.chunks;
+    out->tiles_per_chunk = pl.k2.tiles_per_chunk;
+  }
+  out->scan_bytes = s->n_rows * int64_t(s->dim) * (pl.path == MRAG_PATH_STREAM_F32 ? 4 : 2);
+  out->scan_flops = 2ll * nq * s->n_rows * s->dim;
+  out->workspace_bytes = pl.total;
+  return MRAG_OK;
+}
+
+static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq,
+                       const mrag_search_params* p, const int32_t* exclude_group_dev,
+                       float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream,
+                       cudaEvent_t before_scan, cudaEvent_t after_scan) {
+  Plan pl;
+  int rc = make_plan(s, nq, p, &pl);
+  if (rc != MRAG_OK) return rc;
+  if (!queries_dev || !out_dist_dev || !out_idx_dev || !workspace_dev)
+    return fail(MRAG_ERR_ARG, "null device buffer");
+  if (workspace_bytes < pl.total)
+    return fail(MRAG_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes, pl.total);
+  if (p->filter_mode != MRAG_FILTER_NONE && exclude_group_dev && !s->has_groups)
+    return fail(MRAG_ERR_ARG, "filter requested but the store has no group ids");
+  DeviceGuard g(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace_dev);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
+
+  if (pl.path != MRAG_PATH_TENSOR_BF16 && before_scan) CK(cudaEventRecord(before_scan, st));
+  if (pl.path == MRAG_PATH_STREAM_F32) {
+    CK(launch_k1_stream(s->rows_f32, 4, s->n_rows, s->dim, queries_dev, nq, cand, pl.kc,
+                        pl.k1_grid, st));
+  } else if (pl.path == MRAG_PATH_STREAM_BF16) {
+    CK(launch_k1_stream(s->rows_bf16, 2, s->n_rows, s->dim, queries_dev, nq, cand, pl.kc,
+                        pl.k1_grid, st));
+  } else {
+    void* qb = ws + pl.off_qbf16;
+    const size_t qb_bytes = size_t(pl.k2.m_tiles) * 128 * s->dim * 2;
+    if (nq % 128 != 0) CK(cudaMemsetAsync(qb, 0, qb_bytes, st));
+    CK(launch_cast_queries_bf16(queries_dev, qb, nq, s->dim, st));
+    // rows beyond n_rows up to the 256-row tile edge are zero (store capacity is padded)
+    const int64_t rows_padded = (s->n_rows + 255) / 256 * 256;
+    if (before_scan) CK(cudaEventRecord(before_scan, st));
+    cudaError_t e = launch_k2_batch(qb, pl.k2.m_tiles * 128, s->rows_bf16, rows_padded, s->n_rows,
+                                    s->dim, nq, pl.k2, cand, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch_k2_batch");
+  }
+  if (after_scan) CK(cudaEventRecord(after_scan, st));
+  const int32_t* groups = s->has_groups ? s->groups : nullptr;
+  const int fm = (exclude_group_dev && groups) ? p->filter_mode : MRAG_FILTER_NONE;
+  CK(launch_k3_merge_rerank(cand, pl.cands_per_query, s->rows_f32, s->dim, queries_dev, nq, groups,
+                            exclude_group_dev, fm, p->metric, pl.rerank, p->k, p->index_base,
+                            out_dist_dev, out_idx_dev, out_group_dev, st));
+  return MRAG_OK;
+}
+
+int mrag_search(const mrag_store* s, const float* queries_dev, int32_t nq,
+                const mrag_search_params* p, const int32_t* exclude_group_dev, float* out_dist_dev,
+                int64_t* out_idx_dev, int32_t* out_group_dev, void* workspace_dev,
+                size_t workspace_bytes, void* stream) {
+  return search_impl(s, queries_dev, nq, p, exclude_group_dev, out_dist_dev, out_idx_dev,
+                     out_group_dev, workspace_dev, workspace_bytes, stream, nullptr, nullptr);
+}
+
+int mrag_search_timed(const mrag_store* s, const float* queries_dev, int32_t nq,
+                      const mrag_search_params* p, const int32_t* exclude_group_dev,
+                      float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
+                      void* workspace_dev, size_t workspace_bytes, void* stream,
+                      float* scan_ms_out, float* total_ms_out) {
+  if (!s) return fail(MRAG_ERR_ARG, "null store");
+  DeviceGuard g(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0, e1, e2, e3;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventCreate(&e2));
+  CK(cudaEventCreate(&e3));
+  cudaEventRecord(e0, st);
+  int rc = search_impl(s, queries_dev, nq, p, exclude_group_dev, out_dist_dev, out_idx_dev,
+                       out_group_dev, workspace_dev, workspace_bytes, stream, e1, e2);
+  cudaEventRecord(e3, st);
+  cudaError_t e = cudaEventSynchronize(e3);
+  if (rc == MRAG_OK && e != cudaSuccess) rc = cuda_fail(e, "event synchronize");
+  if (rc == MRAG_OK) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, e1, e2);
+    cudaEventElapsedTime(&b, e0, e3);
+    if (scan_ms_out) *scan_ms_out = a;
+    if (total_ms_out) *total_ms_out = b;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  cudaEventDestroy(e3);
+  return rc;
+}
+
+int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
+                     const mrag_search_params* p, const int32_t* exclude_group_host,
+                     float* out_dist_host, int64_t* out_idx_host, int32_t* out_group_host,
+                     void* stream) {
+  Plan pl;
+  int rc = make_plan(s, nq, p, &pl);
+  if (rc != MRAG_OK) return rc;
+  if (!queries_host || !out_dist_host || !out_idx_host)
+    return fail(MRAG_ERR_ARG, "null host buffer");
+  DeviceGuard g(s->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t q_bytes = align_up(size_t(nq) * s->dim * 4, 256);
+  const size_t ex_bytes = align_up(size_t(nq) * 4, 256);
+  const size_t od_bytes = align_up(size_t(nq) * p->k * 4, 256);
+  const size_t oi_bytes = align_up(size_t(nq) * p->k * 8, 256);
+  const size_t og_bytes = od_bytes;
+  const size_t total = q_bytes + ex_bytes + od_bytes + oi_bytes + og_bytes + pl.total;
+  char* buf = nullptr;
+  CK(cudaMallocAsync(reinterpret_cast<void**>(&buf), total, st));
+  char* c = buf;
+  float* q_d = reinterpret_cast<float*>(c); c += q_bytes;
+  int32_t* ex_d = reinterpret_cast<int32_t*>(c); c += ex_bytes;
+  float* od_d = reinterpret_cast<float*>(c); c += od_bytes;
+  int64_t* oi_d = reinterpret_cast<int64_t*>(c); c += oi_bytes;
+  int32_t* og_d = reinterpret_cast<int32_t*>(c); c += og_bytes;
+  void* ws = c;
+  cudaError_t e = cudaMemcpyAsync(q_d, queries_host, size_t(nq) * s->dim * 4, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && exclude_group_host)
+    e = cudaMemcpyAsync(ex_d, exclude_group_host, size_t(nq) * 4, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    cudaFreeAsync(buf, st);
+    return cuda_fail(e, "host->device copy");
+  }
+  rc = mrag_search(s, q_d, nq, p, exclude_group_host ? ex_d : nullptr, od_d, oi_d,
+                   out_group_host ? og_d : nullptr, ws, pl.total, stream);
+  if (rc == MRAG_OK) {
+    e = cudaMemcpyAsync(out_dist_host, od_d, size_t(nq) * p->k * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(out_idx_host, oi_d, size_t(nq) * p->k * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_group_host)
+      e = cudaMemcpyAsync(out_group_host, og_d, size_t(nq) * p->k * 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "device->host copy");
+  }
+  cudaFreeAsync(buf, st);
+  e = cudaStreamSynchronize(st);
+  if (rc == MRAG_OK && e != cudaSuccess) rc = cuda_fail(e, "stream synchronize");
+  return rc;
+}
+
+int mrag_merge_topk(const float* cand_dist_dev, const int64_t* cand_idx_dev,
+                    const int32_t* cand_group_dev, int64_t shard_stride_bytes, int32_t nshards,
+                    int32_t nq, int32_t k_in,
+                    int32_t k_out, const int32_t* exclude_group_dev, int32_t filter_mode,
+                    float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
+                    void* stream) {
+  if (!cand_dist_dev || !cand_idx_dev || !out_dist_dev || !out_idx_dev)
+    return fail(MRAG_ERR_ARG, "null device buffer");
+  if (nshards < 1 || nq < 1 || k_in < 1 || k_out < 1 || k_out > 32 || nshards * k_in > 256)
+    return fail(MRAG_ERR_ARG, "need 1 <= k_out <= 32 and nshards*k_in <= 256 (got %d x %d -> %d)",
+                nshards, k_in, k_out);
+  if (filter_mode != MRAG_FILTER_NONE && exclude_group_dev && !cand_group_dev)
+    return fail(MRAG_ERR_ARG, "filter requested without candidate group ids");
+  if (shard_stride_bytes < 0 || shard_stride_bytes % 8 != 0)
+    return fail(MRAG_ERR_ARG, "shard_stride_bytes must be a non-negative multiple of 8");
+  const int fm = exclude_group_dev ? filter_mode : MRAG_FILTER_NONE;
+  CK(launch_k3_merge_shards(cand_dist_dev, cand_idx_dev, cand_group_dev, shard_stride_bytes,
+                            nshards, nq, k_in, k_out,
+                            exclude_group_dev, fm, out_dist_dev, out_idx_dev, out_group_dev,
+                            static_cast<cudaStream_t>(stream)));
+  return MRAG_OK;
+}
+
+int mrag_gather_context(const void* const* shard_ptrs_dev, int32_t nshards, int64_t rows_per_shard,
+                        const int64_t* ref_idx_dev, const void* sos_dev, const void* uncond_row_dev,
+                        const void* pe_dev, const void* cond_dev, void* out_dev, int32_t b,
+                        int32_t K, int32_t L, int32_t C, int32_t dtype, void* stream) {
+  if (!shard_ptrs_dev || !ref_idx_dev || !sos_dev || !uncond_row_dev || !out_dev)
+    return fail(MRAG_ERR_ARG, "null device buffer");
+  if (nshards < 1 || rows_per_shard < 1 || b < 1 || K < 1 || L < 1 || C < 1)
+    return fail(MRAG_ERR_ARG, "bad gather shape");
+  if (dtype != 0 && dtype != 1) return fail(MRAG_ERR_ARG, "dtype must be 0 (bf16) or 1 (f32)");
+  if ((int64_t(L) * C * (dtype == 0 ? 2 : 4)) % 16 != 0)
+    return fail(MRAG_ERR_ARG, "L*C*sizeof(elt) must be a multiple of 16 bytes");
+  CK(launch_k4_gather(shard_ptrs_dev, nshards, rows_per_shard, ref_idx_dev, sos_dev, uncond_row_dev,
+                      pe_dev, cond_dev, out_dev, b, K, L, C, dtype,
+                      static_cast<cudaStream_t>(stream)));
+  return MRAG_OK;
+}
+
+int mrag_device_alloc(int32_t device, size_t bytes, void** dev_ptr_out) {
+  if (!dev_ptr_out || bytes == 0) return fail(MRAG_ERR_ARG, "bad alloc request");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(MRAG_ERR_DEVICE, "cannot select device %d", device);
+  CK(cudaMalloc(dev_ptr_out, bytes));
+  return MRAG_OK;
+}
+
+int mrag_device_free(int32_t device, void* dev_ptr) {
+  if (!dev_ptr) return MRAG_OK;
+  DeviceGuard g(device);
+  CK(cudaFree(dev_ptr));
+  return MRAG_OK;
+}
+
+int mrag_ipc_export(const void* dev_ptr, void* handle_out_64B) {
+  if (!dev_ptr || !handle_out_64B) return fail(MRAG_ERR_ARG, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+  memcpy(handle_out_64B, &h, 64);
+  return MRAG_OK;
+}
+
+int mrag_ipc_open(const void* handle_64B, void** dev_ptr_out) {
+  if (!handle_64B || !dev_ptr_out) return fail(MRAG_ERR_ARG, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64B, 64);
+  CK(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return MRAG_OK;
+}
+
+int mrag_ipc_close(void* dev_ptr) {
+  if (!dev_ptr) return MRAG_OK;
+  CK(cudaIpcCloseMemHandle(dev_ptr));
+  return MRAG_OK;
+}
+
+}  // extern "C"

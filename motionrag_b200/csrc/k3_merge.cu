@@ -1,0 +1,323 @@
+// K0 (store preparation), K3 (candidate merge + exact fp32 re-score + filter) and the
+// cross-shard merge.
+//
+// K3 turns the per-CTA / per-chunk candidate keys written by K1 / K2 into the record list the
+// reference returns from RAGDatabase.vector_search (src/data/rag.py:54-61): at most k rows,
+// ascending `_distance`, computed in fp32 from the master rows with LanceDB's own formulas
+// (l2 = sum (q-d)^2, cosine = 1 - cos, dot = 1 - q.d), ties broken by lowest row index, and
+// the `video != "<own>"` filter of src/data/datamodule.py:235 applied as a post-filter
+// (LanceDB 0.14 default) or pre-filter.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mrag {
+
+// ---- K0 -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k0_prepare_rows_kernel(float* __restrict__ rows, __nv_bfloat16* __restrict__ shadow, int64_t n,
+                           int dim, int normalise) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  float4* p = reinterpret_cast<float4*>(rows + row * dim);
+  const int nv = dim >> 2;
+  float scale = 1.f;
+  if (normalise) {
+    float ss = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+      float4 v = p[i];
+      ss = fmaf(v.x, v.x, ss);
+      ss = fmaf(v.y, v.y, ss);
+      ss = fmaf(v.z, v.z, ss);
+      ss = fmaf(v.w, v.w, ss);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    // x / max(|x|, eps), the torch.nn.functional.normalize convention
+    scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  uint2* o = reinterpret_cast<uint2*>(shadow + row * dim);
+  for (int i = lane; i < nv; i += 32) {
+    float4 v = p[i];
+    if (normalise) {
+      v.x *= scale;
+      v.y *= scale;
+      v.z *= scale;
+      v.w *= scale;
+      p[i] = v;
+    }
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    o[i] = pk;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k0_cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n4) {
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(in)[i];
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&a);
+  pk.y = *reinterpret_cast<uint32_t*>(&b);
+  reinterpret_cast<uint2*>(out)[i] = pk;
+}
+
+cudaError_t launch_prepare_rows(float* rows_f32, void* rows_bf16, int64_t n, int dim,
+                                bool normalise, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const int64_t threads = n * 32;
+  const int64_t blocks = (threads + 255) / 256;
+  k0_prepare_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(
+      rows_f32, static_cast<__nv_bfloat16*>(rows_bf16), n, dim, normalise ? 1 : 0);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cast_queries_bf16(const float* q, void* q_bf16, int nq, int dim,
+                                     cudaStream_t st) {
+  const int64_t n4 = int64_t(nq) * dim / 4;
+  k0_cast_bf16_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(
+      q, static_cast<__nv_bfloat16*>(q_bf16), n4);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// ---- shared tail: filter + emit the first entries of a sorted list (executed by warp 0) ----
+// entry(j) -> valid?, distance, global index, group; list length <= 64, sorted ascending.
+struct Emit {
+  float dist;
+  int64_t idx;
+  int32_t group;
+  bool valid;
+};
+
+template <typename EntryFn>
+__device__ __forceinline__ void emit_filtered(EntryFn entry, int n_sorted, int k, int filter_mode,
+                                              int exclude, float* out_dist, int64_t* out_idx,
+                                              int32_t* out_group, int lane) {
+  // two entries per lane: j0 = lane, j1 = lane + 32
+  Emit e0 = entry(lane, lane < n_sorted);
+  Emit e1 = entry(lane + 32, lane + 32 < n_sorted);
+  const bool excl0 = (filter_mode != 0) && (exclude >= 0) && e0.valid && (e0.group == exclude);
+  const bool excl1 = (filter_mode != 0) && (exclude >= 0) && e1.valid && (e1.group == exclude);
+  bool keep0, keep1;
+  if (filter_mode == 1) {  // post-filter: only the k nearest are eligible at all
+    keep0 = e0.valid && (lane < k) && !excl0;
+    keep1 = e1.valid && (lane + 32 < k) && !excl1;
+  } else {
+    keep0 = e0.valid && !excl0;
+    keep1 = e1.valid && !excl1;
+  }
+  const uint32_t b0 = __ballot_sync(0xffffffffu, keep0);
+  const uint32_t b1 = __ballot_sync(0xffffffffu, keep1);
+  const uint32_t lt = (1u << lane) - 1u;
+  const int pos0 = __popc(b0 & lt);
+  const int pos1 = __popc(b0) + __popc(b1 & lt);
+  if (keep0 && pos0 < k) {
+    out_dist[pos0] = e0.dist;
+    out_idx[pos0] = e0.idx;
+    if (out_group) out_group[pos0] = e0.group;
+  }
+  if (keep1 && pos1 < k) {
+    out_dist[pos1] = e1.dist;
+    out_idx[pos1] = e1.idx;
+    if (out_group) out_group[pos1] = e1.group;
+  }
+  const int total = min(k, __popc(b0) + __popc(b1));
+  for (int j = total + lane; j < k; j += 32) {
+    out_dist[j] = INFINITY;
+    out_idx[j] = -1;
+    if (out_group) out_group[j] = -1;
+  }
+}
+
+// ---- K3 -------------------------------------------------------------------------------------
+constexpr int kMaxRerank = 64;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    k3_merge_rerank_kernel(const uint64_t* __restrict__ cand, int cands_per_query, int padded,
+                           const float* __restrict__ db, int dim, const float* __restrict__ queries,
+                           const int32_t* __restrict__ row_group,
+                           const int32_t* __restrict__ exclude_group, int filter_mode, int metric,
+                           int rerank, int k, int64_t index_base, float* __restrict__ out_dist,
+                           int64_t* __restrict__ out_idx, int32_t* __restrict__ out_group) {
+  extern __shared__ __align__(16) uint64_t keys[];  // [padded]
+  __shared__ uint64_t rr_keys[kMaxRerank];          // (ordered distance << 32) | local row
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.x;
+
+  const uint64_t* src = cand + int64_t(q) * cands_per_query;
+  for (int i = tid; i < padded; i += THREADS) keys[i] = (i < cands_per_query) ? src[i] : kEmptyKey;
+  bitonic_sort_smem(keys, padded, tid, THREADS);
+
+  // exact fp32 distances for the best `rerank` candidates: one warp per candidate
+  const float4* qv = reinterpret_cast<const float4*>(queries + int64_t(q) * dim);
+  const int nv = dim >> 2;
+  if (tid < kMaxRerank) rr_keys[tid] = kEmptyKey;
+  __syncthreads();
+  const int n_rr = min(rerank, min(padded, kMaxRerank));
+  for (int c = warp; c < n_rr; c += THREADS / 32) {
+    const uint64_t key = keys[c];
+    const uint32_t idx = uint32_t(key);
+    if (idx >= uint32_t(kInvalidIdx)) continue;  // empty slot (warp-uniform)
+    const float4* dv = reinterpret_cast<const float4*>(db + int64_t(idx) * dim);
+    float l2 = 0.f, dot = 0.f, qq = 0.f, dd = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+      const float4 a = qv[i];
+      const float4 b = dv[i];
+      float t;
+      t = a.x - b.x; l2 = fmaf(t, t, l2);
+      t = a.y - b.y; l2 = fmaf(t, t, l2);
+      t = a.z - b.z; l2 = fmaf(t, t, l2);
+      t = a.w - b.w; l2 = fmaf(t, t, l2);
+      dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot);
+      dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+      qq = fmaf(a.x, a.x, qq); qq = fmaf(a.y, a.y, qq);
+      qq = fmaf(a.z, a.z, qq); qq = fmaf(a.w, a.w, qq);
+      dd = fmaf(b.x, b.x, dd); dd = fmaf(b.y, b.y, dd);
+      dd = fmaf(b.z, b.z, dd); dd = fmaf(b.w, b.w, dd);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      l2 += __shfl_xor_sync(0xffffffffu, l2, off);
+      dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      qq += __shfl_xor_sync(0xffffffffu, qq, off);
+      dd += __shfl_xor_sync(0xffffffffu, dd, off);
+    }
+    float dist;
+    if (metric == 0) dist = l2;
+    else if (metric == 1) dist = 1.f - dot / fmaxf(sqrtf(qq) * sqrtf(dd), 1e-30f);
+    else dist = 1.f - dot;
+    if (lane == 0) rr_keys[c] = (uint64_t(f32_to_ordered(dist)) << 32) | idx;
+  }
+  bitonic_sort_smem(rr_keys, kMaxRerank, tid, THREADS);
+
+  if (warp == 0) {
+    const int exclude = (exclude_group != nullptr) ? exclude_group[q] : -1;
+    auto entry = [&](int j, bool in_range) {
+      Emit e;
+      e.valid = false;
+      e.dist = INFINITY;
+      e.idx = -1;
+      e.group = -1;
+      if (in_range && j < kMaxRerank) {
+        const uint64_t key = rr_keys[j];
+        const uint32_t idx = uint32_t(key);
+        if (key != kEmptyKey && idx < uint32_t(kInvalidIdx)) {
+          e.valid = true;
+          e.dist = ordered_to_f32(uint32_t(key >> 32));
+          e.idx = index_base + int64_t(idx);
+          e.group = (row_group != nullptr) ? row_group[idx] : -1;
+        }
+      }
+      return e;
+    };
+    emit_filtered(entry, n_rr, k, filter_mode, exclude, out_dist + int64_t(q) * k,
+                  out_idx + int64_t(q) * k, out_group ? out_group + int64_t(q) * k : nullptr, lane);
+  }
+}
+
+cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int cands_per_query, const float* db_f32,
+                                   int dim, const float* queries, int nq,
+                                   const int32_t* row_group, const int32_t* exclude_group,
+                                   int filter_mode, int metric, int rerank, int k,
+                                   int64_t index_base, float* out_dist, int64_t* out_idx,
+                                   int32_t* out_group, cudaStream_t st) {
+  int padded = 64;
+  while (padded < cands_per_query) padded <<= 1;
+  if (padded > 16384) return cudaErrorInvalidValue;
+  const size_t smem = size_t(padded) * sizeof(uint64_t);
+  if (padded > 2048) {
+    auto kern = k3_merge_rerank_kernel<1024>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+    if (e != cudaSuccess) return e;
+    kern<<<nq, 1024, smem, st>>>(cand, cands_per_query, padded, db_f32, dim, queries, row_group,
+                                 exclude_group, filter_mode, metric, rerank, k, index_base,
+                                 out_dist, out_idx, out_group);
+  } else {
+    k3_merge_rerank_kernel<256><<<nq, 256, smem, st>>>(
+        cand, cands_per_query, padded, db_f32, dim, queries, row_group, exclude_group, filter_mode,
+        metric, rerank, k, index_base, out_dist, out_idx, out_group);
+  }
+  note_launch();
+  return cudaGetLastError();
+}
+
+// ---- cross-shard merge ----------------------------------------------------------------------
+// Shard g's [nq][k_in] block of each field sits `stride` elements (of that field's type) after
+// the base pointer; each shard's list is already sorted by (distance, index) and shards are
+// ordered by ascending row range, so "lower slot" == "lower global index" among equal distances.
+__global__ void __launch_bounds__(256)
+    k3_merge_shards_kernel(const float* __restrict__ cand_dist, const int64_t* __restrict__ cand_idx,
+                           const int32_t* __restrict__ cand_group, int64_t stride4, int64_t stride8,
+                           int nshards, int nq, int k_in,
+                           int k_out, const int32_t* __restrict__ exclude_group, int filter_mode,
+                           float* __restrict__ out_dist, int64_t* __restrict__ out_idx,
+                           int32_t* __restrict__ out_group) {
+  __shared__ uint64_t keys[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.x;
+  const int total = nshards * k_in;  // <= 256
+  uint64_t key = kEmptyKey;
+  if (tid < total) {
+    const int g = tid / k_in, j = tid % k_in;
+    const int64_t off = int64_t(q) * k_in + j;
+    if (cand_idx[g * stride8 + off] >= 0)
+      key = (uint64_t(f32_to_ordered(cand_dist[g * stride4 + off])) << 32) | uint32_t(tid);
+  }
+  keys[tid] = key;
+  bitonic_sort_smem(keys, 256, tid, 256);
+  if (warp == 0) {
+    const int exclude = (exclude_group != nullptr) ? exclude_group[q] : -1;
+    auto entry = [&](int j, bool in_range) {
+      Emit e;
+      e.valid = false;
+      e.dist = INFINITY;
+      e.idx = -1;
+      e.group = -1;
+      if (in_range) {
+        const uint64_t kk = keys[j];
+        if (kk != kEmptyKey) {
+          const int slot = int(uint32_t(kk));
+          const int g = slot / k_in, jj = slot % k_in;
+          const int64_t off = int64_t(q) * k_in + jj;
+          e.valid = true;
+          e.dist = cand_dist[g * stride4 + off];
+          e.idx = cand_idx[g * stride8 + off];
+          e.group = cand_group ? cand_group[g * stride4 + off] : -1;
+        }
+      }
+      return e;
+    };
+    emit_filtered(entry, min(total, 64), k_out, filter_mode, exclude, out_dist + int64_t(q) * k_out,
+                  out_idx + int64_t(q) * k_out,
+                  out_group ? out_group + int64_t(q) * k_out : nullptr, lane);
+  }
+}
+
+cudaError_t launch_k3_merge_shards(const float* cand_dist, const int64_t* cand_idx,
+                                   const int32_t* cand_group, int64_t shard_stride_bytes,
+                                   int nshards, int nq, int k_in,
+                                   int k_out, const int32_t* exclude_group, int filter_mode,
+                                   float* out_dist, int64_t* out_idx, int32_t* out_group,
+                                   cudaStream_t st) {
+  if (nshards * k_in > 256) return cudaErrorInvalidValue;
+  const int64_t dense = int64_t(nq) * k_in;
+  const int64_t stride4 = shard_stride_bytes ? shard_stride_bytes / 4 : dense;
+  const int64_t stride8 = shard_stride_bytes ? shard_stride_bytes / 8 : dense;
+  k3_merge_shards_kernel<<<nq, 256, 0, st>>>(cand_dist, cand_idx, cand_group, stride4, stride8,
+                                             nshards, nq, k_in,
+                                             k_out, exclude_group, filter_mode, out_dist, out_idx,
+                                             out_group);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace mrag

@@ -1,0 +1,127 @@
+// K4 — gather of retrieved motion-feature rows into the CAMA context tensor.
+//
+// Replaces, for the K retrieved references, the per-sample mp4 decode of
+// VideoDataset.get_ref_videos (reference src/data/dataset.py:285-312) and the frozen
+// VideoMAE + Resampler pass of ActionTransformer.encode_vision
+// (src/projects/condition/module.py:264-268) by a lookup into a precomputed
+// [rows, L, C] feature table, and writes the result directly in the layout
+// ActionTransformer.forward builds at module.py:298-301:
+//     x = cat([sos, feats[:, :-1]], 1);  x = x + pe[: (K+1) L];  x += cond
+// Group 0 is the SOS block, group g >= 1 is the reference of similarity rank K-g (the
+// reference flips the list so the most similar clip sits next to the target,
+// module.py:318-319); index -1 stands for a dropped / unreadable reference and selects the
+// "uncond" row (the encoding of an all-zero clip, dataset.py:292,305-310, module.py:328).
+// The table may be row-sharded over several GPUs: shard_ptrs holds one (local or
+// peer-mapped, NVLink) base pointer per shard and rows are read where they live.
+//
+// Pure bandwidth: per query K*L*C*s bytes read + (K+1)*L*C*s written (s = element size).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mrag {
+
+constexpr int kK4Threads = 256;
+constexpr int kK4Unroll = 4;  // 16-byte vectors in flight per thread
+
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  // torch semantics for bf16 + bf16: widen, add in fp32, round to nearest even
+  float lo = bf16lo_to_f32(a) + bf16lo_to_f32(b);
+  float hi = bf16hi_to_f32(a) + bf16hi_to_f32(b);
+  __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+template <bool BF16>
+__device__ __forceinline__ uint4 add_vec(const uint4& a, const uint4& b) {
+  uint4 r;
+  if constexpr (BF16) {
+    r.x = add_bf16x2(a.x, b.x);
+    r.y = add_bf16x2(a.y, b.y);
+    r.z = add_bf16x2(a.z, b.z);
+    r.w = add_bf16x2(a.w, b.w);
+  } else {
+    r.x = __float_as_uint(__uint_as_float(a.x) + __uint_as_float(b.x));
+    r.y = __float_as_uint(__uint_as_float(a.y) + __uint_as_float(b.y));
+    r.z = __float_as_uint(__uint_as_float(a.z) + __uint_as_float(b.z));
+    r.w = __float_as_uint(__uint_as_float(a.w) + __uint_as_float(b.w));
+  }
+  return r;
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kK4Threads)
+    k4_gather_kernel(const void* const* __restrict__ shard_ptrs, int nshards,
+                     int64_t rows_per_shard, const int64_t* __restrict__ ref_idx,
+                     const uint4* __restrict__ sos, const uint4* __restrict__ uncond,
+                     const uint4* __restrict__ pe, const uint4* __restrict__ cond,
+                     uint4* __restrict__ out, int K, int vec_per_group) {
+  const int g = blockIdx.x % (K + 1);  // context group
+  const int bi = blockIdx.x / (K + 1); // sample
+  const uint4* src;
+  if (g == 0) {
+    src = sos;
+  } else {
+    const int64_t r = ref_idx[int64_t(bi) * K + (K - g)];
+    const int64_t shard = (r >= 0) ? r / rows_per_shard : 0;
+    if (r < 0 || shard >= nshards) {
+      src = uncond;
+    } else {
+      src = reinterpret_cast<const uint4*>(shard_ptrs[shard]) +
+            (r - shard * rows_per_shard) * int64_t(vec_per_group);
+    }
+  }
+  const int64_t grp_off = int64_t(g) * vec_per_group;                       // into pe
+  const int64_t out_off = (int64_t(bi) * (K + 1) + g) * vec_per_group;      // into out / cond
+  const int v0 = blockIdx.y * (kK4Threads * kK4Unroll) + threadIdx.x;
+  uint4 x[kK4Unroll];
+#pragma unroll
+  for (int u = 0; u < kK4Unroll; ++u) {
+    const int v = v0 + u * kK4Threads;
+    if (v < vec_per_group) x[u] = ld_stream_v4(src + v);
+  }
+  if (pe != nullptr) {
+#pragma unroll
+    for (int u = 0; u < kK4Unroll; ++u) {
+      const int v = v0 + u * kK4Threads;
+      if (v < vec_per_group) x[u] = add_vec<BF16>(x[u], __ldg(pe + grp_off + v));
+    }
+  }
+  if (cond != nullptr) {
+#pragma unroll
+    for (int u = 0; u < kK4Unroll; ++u) {
+      const int v = v0 + u * kK4Threads;
+      if (v < vec_per_group) x[u] = add_vec<BF16>(x[u], ld_stream_v4(cond + out_off + v));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kK4Unroll; ++u) {
+    const int v = v0 + u * kK4Threads;
+    if (v < vec_per_group) st_stream_v4(out + out_off + v, x[u]);
+  }
+}
+
+cudaError_t launch_k4_gather(const void* const* shard_ptrs, int nshards, int64_t rows_per_shard,
+                             const int64_t* ref_idx, const void* sos, const void* uncond,
+                             const void* pe, const void* cond, void* out, int b, int K, int L,
+                             int C, int dtype, cudaStream_t st) {
+  const int elt = (dtype == 0) ? 2 : 4;
+  const int64_t bytes = int64_t(L) * C * elt;
+  if (bytes % 16 != 0) return cudaErrorInvalidValue;
+  const int vec_per_group = int(bytes / 16);
+  dim3 grid(unsigned(b * (K + 1)),
+            unsigned((vec_per_group + kK4Threads * kK4Unroll - 1) / (kK4Threads * kK4Unroll)));
+  auto a = [](const void* p) { return reinterpret_cast<const uint4*>(p); };
+  if (dtype == 0)
+    k4_gather_kernel<true><<<grid, kK4Threads, 0, st>>>(shard_ptrs, nshards, rows_per_shard,
+                                                        ref_idx, a(sos), a(uncond), a(pe), a(cond),
+                                                        reinterpret_cast<uint4*>(out), K,
+                                                        vec_per_group);
+  else
+    k4_gather_kernel<false><<<grid, kK4Threads, 0, st>>>(shard_ptrs, nshards, rows_per_shard,
+                                                         ref_idx, a(sos), a(uncond), a(pe), a(cond),
+                                                         reinterpret_cast<uint4*>(out), K,
+                                                         vec_per_group);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace mrag

@@ -1,0 +1,64 @@
+// Internal launcher interface between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mrag {
+
+// thread-local count of kernels this library launched (mrag_launch_count)
+void note_launch(int n = 1);
+
+// K0: store preparation -------------------------------------------------------------------
+// rows (fp32, in place when normalise) -> bf16 shadow; one warp per row
+cudaError_t launch_prepare_rows(float* rows_f32, void* rows_bf16, int64_t n, int dim,
+                                bool normalise, cudaStream_t st);
+cudaError_t launch_cast_queries_bf16(const float* q, void* q_bf16, int nq, int dim,
+                                     cudaStream_t st);
+
+// K1: HBM-streaming scan + per-CTA top-KC -----------------------------------------------------
+// db: fp32 (elt_bytes 4) or bf16 (elt_bytes 2) rows; queries fp32 [nq<=4][dim]
+// cand: [nq][grid][kc] u64 similarity keys. Returns the grid it will use via k1_grid().
+int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count);
+bool k1_supported(int dim, int nq);
+cudaError_t launch_k1_stream(const void* db, int elt_bytes, int64_t n_rows, int dim,
+                             const float* queries, int nq, uint64_t* cand, int kc, int grid,
+                             cudaStream_t st);
+
+// K2: tcgen05 batched scan + fused epilogue top-32 ------------------------------------------
+struct K2Plan {
+  int m_tiles;          // ceil(nq / 128)
+  int n_tiles;          // ceil(n_rows / 256)
+  int chunks;           // database split into this many contiguous tile ranges
+  int tiles_per_chunk;  // ceil(n_tiles / chunks)
+  int grid;             // persistent CTAs
+};
+constexpr int kK2Cand = 32;  // candidates kept per (query, chunk)
+bool k2_supported(int dim);
+K2Plan k2_plan(int64_t n_rows, int nq, int sm_count);
+// q_bf16 [q_rows_padded][dim] (rows >= nq zero), db_bf16 [db_rows_padded][dim] (rows >= n_rows
+// zero), both padded to whole tiles; cand [nq][chunks][32] u64 keys
+cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* db_bf16,
+                            int64_t db_rows_padded, int64_t n_rows, int dim, int nq,
+                            const K2Plan& plan, uint64_t* cand, cudaStream_t st);
+
+// K3: candidate merge + exact fp32 re-score + filter --------------------------------------
+cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int cands_per_query,
+                                   const float* db_f32, int dim, const float* queries, int nq,
+                                   const int32_t* row_group, const int32_t* exclude_group,
+                                   int filter_mode, int metric, int rerank, int k,
+                                   int64_t index_base, float* out_dist, int64_t* out_idx,
+                                   int32_t* out_group, cudaStream_t st);
+cudaError_t launch_k3_merge_shards(const float* cand_dist, const int64_t* cand_idx,
+                                   const int32_t* cand_group, int64_t shard_stride_bytes,
+                                   int nshards, int nq, int k_in,
+                                   int k_out, const int32_t* exclude_group, int filter_mode,
+                                   float* out_dist, int64_t* out_idx, int32_t* out_group,
+                                   cudaStream_t st);
+
+// K4: feature gather into the CAMA context layout -------------------------------------------
+cudaError_t launch_k4_gather(const void* const* shard_ptrs, int nshards, int64_t rows_per_shard,
+                             const int64_t* ref_idx, const void* sos, const void* uncond,
+                             const void* pe, const void* cond, void* out, int b, int K, int L,
+                             int C, int dtype, cudaStream_t st);
+
+}  // namespace mrag

@@ -1,0 +1,164 @@
+"""Row-sharded retrieval over the GPUs of one NVSwitch box: one process per GPU.
+
+Partition: shard g owns the contiguous global rows
+[g * rows_per_shard, (g+1) * rows_per_shard); embedding store and feature table use the same
+split. A search is: every rank scans its shard for the (replicated) query batch -> ONE
+all-gather of the packed per-rank record {distance f32, group i32, index i64}[nq, k] over
+NCCL/NVLink -> every rank merges G*k -> k (mrag_merge_topk; ties by lowest global index; the
+`video != x` post-filter is applied after the global top-k, exactly where a single table
+would apply it). Retrieved feature rows are then read where they live through peer-mapped
+pointers (CUDA IPC) by the gather kernel itself — no second collective.
+
+The search / merge callables are injectable so the exchange and layout logic can run under
+`gloo` on CPU in tests (with the oracle standing in for the kernels); the defaults are the
+CUDA paths.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from ._cabi import check
+from .store import EmbeddingStore, FeatureTable, SearchResult, merge_topk
+
+
+def shard_range(n_rows: int, n_shards: int, rank: int) -> tuple[int, int, int]:
+    """(rows_per_shard, first_row, last_row_exclusive) of `rank` for an n_rows table."""
+    rps = (n_rows + n_shards - 1) // n_shards
+    lo = min(n_rows, rank * rps)
+    hi = min(n_rows, lo + rps)
+    return rps, lo, hi
+
+
+@dataclass
+class PackedLayout:
+    """Byte layout of one rank's record block: dist f32 | group i32 | idx i64, each [nq, k]."""
+    nq: int
+    k: int
+
+    @property
+    def n(self) -> int:
+        return self.nq * self.k
+
+    @property
+    def off_dist(self) -> int:
+        return 0
+
+    @property
+    def off_group(self) -> int:
+        return 4 * self.n
+
+    @property
+    def off_idx(self) -> int:
+        return 8 * self.n
+
+    @property
+    def nbytes(self) -> int:
+        return 16 * self.n
+
+    def views(self, buf: torch.Tensor, n_blocks: int):
+        """Typed strided views [n_blocks, nq, k] into a uint8 buffer of n_blocks records."""
+        assert buf.dtype == torch.uint8 and buf.numel() == n_blocks * self.nbytes
+        b = buf.view(n_blocks, self.nbytes)
+        d = b[:, self.off_dist:self.off_group].view(torch.float32).view(n_blocks, self.nq, self.k)
+        g = b[:, self.off_group:self.off_idx].view(torch.int32).view(n_blocks, self.nq, self.k)
+        i = b[:, self.off_idx:].view(torch.int64).view(n_blocks, self.nq, self.k)
+        return d, g, i
+
+
+class ShardedRetriever:
+    def __init__(self, store: EmbeddingStore | None, rank: int, world: int, rows_per_shard: int,
+                 group: dist.ProcessGroup | None = None, local_search=None, merge=None,
+                 device: torch.device | None = None):
+        self.store, self.rank, self.world = store, rank, world
+        self.rows_per_shard = int(rows_per_shard)
+        self.group = group
+        self.device = device if device is not None else store.device
+        self._local_search = local_search or self._cuda_search
+        self._merge = merge or self._cuda_merge
+        self._bufs: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor]] = {}
+
+    # default (product) implementations ------------------------------------------------------
+    def _cuda_search(self, queries, k, metric, path, refine, exclude_group, filter_mode, index_base, out):
+        return self.store.search(queries, k, metric=metric, path=path, refine=refine,
+                                 exclude_group=exclude_group, filter_mode=filter_mode,
+                                 index_base=index_base, out=out)
+
+    @staticmethod
+    def _cuda_merge(dist_v, idx_v, grp_v, k_out, exclude_group, filter_mode, stride):
+        return merge_topk(dist_v, idx_v, grp_v, k_out, exclude_group, filter_mode, stride)
+
+    def search(self, queries: torch.Tensor, k: int, *, metric: str = "l2", path: str = "auto",
+               refine: int = 0, exclude_group: torch.Tensor | None = None,
+               filter_mode: str = "post") -> SearchResult:
+        """Same contract as EmbeddingStore.search, over the union of all shards. Every rank
+        passes the same queries and gets the same (global-index) result."""
+        nq = queries.shape[0]
+        lay = PackedLayout(nq, k)
+        key = (nq, k)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.empty(lay.nbytes, dtype=torch.uint8, device=self.device),
+                               torch.empty(self.world * lay.nbytes, dtype=torch.uint8, device=self.device))
+        send, recv = self._bufs[key]
+        d, g, i = lay.views(send, 1)
+        local = SearchResult(d[0], i[0], g[0])
+        # post-filter happens after the GLOBAL top-k; pre-filter can be applied per shard
+        local_filter = "pre" if (filter_mode == "pre" and exclude_group is not None) else "none"
+        self._local_search(queries, k, metric, path, refine,
+                           exclude_group if local_filter == "pre" else None, local_filter,
+                           self.rank * self.rows_per_shard, local)
+        if self.world == 1:
+            recv = send
+        else:
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+        dv, gv, iv = lay.views(recv, self.world)
+        return self._merge(dv, iv, gv, k, exclude_group,
+                           filter_mode if exclude_group is not None else "none", lay.nbytes)
+
+
+# --- peer-mapped feature tables ------------------------------------------------------------------
+def alloc_feature_block(rows: int, L: int, Cdim: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    """cudaMalloc'ed (IPC-exportable) [rows, L, C] block wrapped as a torch tensor."""
+    from .store import _view
+    lib = _cabi.load()
+    esz = 2 if dtype == torch.bfloat16 else 4
+    ptr = C.c_void_p()
+    check(lib.mrag_device_alloc(device.index, rows * L * Cdim * esz, C.byref(ptr)))
+
+    class _Owner:
+        def __init__(self, p, dev):
+            self.p, self.dev = p, dev
+
+        def __del__(self):
+            try:
+                lib.mrag_device_free(self.dev, self.p)
+            except Exception:
+                pass
+
+    return _view(ptr.value, (rows, L, Cdim), dtype, device, _Owner(ptr, device.index))
+
+
+def open_peer_tables(table: FeatureTable, group: dist.ProcessGroup | None = None) -> FeatureTable:
+    """Exchange CUDA IPC handles of the local feature blocks and map every peer block, so the
+    gather kernel can read any global row over NVLink. The local block must come from
+    alloc_feature_block (IPC handles name whole cudaMalloc allocations)."""
+    if table.n_shards == 1:
+        return table
+    lib = _cabi.load()
+    handle = (C.c_ubyte * 64)()
+    check(lib.mrag_ipc_export(C.c_void_p(table.local.data_ptr()), handle))
+    mine = bytes(handle)
+    handles: list = [None] * table.n_shards
+    dist.all_gather_object(handles, mine, group=group)
+    for r, h in enumerate(handles):
+        if r == table.shard_rank:
+            continue
+        buf = (C.c_ubyte * 64).from_buffer_copy(h)
+        ptr = C.c_void_p()
+        check(lib.mrag_ipc_open(buf, C.byref(ptr)))
+        table.set_peer_ptr(r, ptr.value)
+    return table

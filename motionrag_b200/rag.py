@@ -1,0 +1,386 @@
+"""`RAGDatabase` — drop-in for the reference's src/data/rag.py:11-130, served from HBM.
+
+Same constructor, same method names, same defaults and the same return schema
+(`list[dict]`, ascending `_distance`, at most `top_k` rows, keys = `select` + `_distance`), so
+`VideoDataModule.prepare_data / prepare_annotations` (src/data/datamodule.py:102, 231-265)
+runs unchanged. What differs is what executes: the LanceDB flat scan becomes the libmrag CUDA
+kernels (K1 streaming / K2 tcgen05 scan, K3 merge + fp32 re-score + filter). There is no CPU
+path — constructing the object without a B200-class GPU raises.
+
+On-disk layout read by `RAGDatabase(db_path, table_name)` (written by `save_table`, or by
+tools/export_lancedb.py from a real LanceDB directory on a machine that has lancedb):
+    <db_path>/<table_name>/text_embedding.npy     float32 [N, dim]   (np.load mmap-able)
+    <db_path>/<table_name>/image_embedding.npy    optional
+    <db_path>/<table_name>/columns.parquet        every scalar column of the reference schema
+                                                  (tools/build_rag_database.py:35-45)
+"""
+from __future__ import annotations
+
+import re
+from pathlib import Path
+from typing import Callable, Literal, Sequence
+
+import numpy as np
+import torch
+
+from .store import EmbeddingStore
+
+VECTOR_COLUMNS = ("text_embedding", "image_embedding")
+_WHERE = re.compile(r'^\s*(\w+)\s*!=\s*(["\'])((?:(?!\2).)*)\2\s*$')
+
+
+def save_table(db_path: str | Path, table_name: str, columns: dict) -> Path:
+    """Write a table in the layout above. `columns` maps names to equal-length sequences;
+    vector columns are float32 [N, dim] arrays."""
+    import pandas as pd
+    root = Path(db_path) / table_name
+    root.mkdir(parents=True, exist_ok=True)
+    scalars = {}
+    for name, col in columns.items():
+        if name in VECTOR_COLUMNS:
+            np.save(root / f"{name}.npy", np.ascontiguousarray(col, dtype=np.float32))
+        else:
+            scalars[name] = list(col) if not isinstance(col, np.ndarray) else col
+    pd.DataFrame(scalars).to_parquet(root / "columns.parquet")
+    return root
+
+
+class _DeviceColumn:
+    """Stand-in for a vector column that only exists in HBM (RAGDatabase.from_store)."""
+
+    def __init__(self, store: EmbeddingStore):
+        self._store = store
+
+    @property
+    def shape(self):
+        return (len(self._store), self._store.dim)
+
+    def __getitem__(self, i):
+        return self._store.rows_f32()[i].cpu().numpy()
+
+
+class RAGDatabase:
+    def __init__(self, db_path: str | None, table_name: str | None,
+                 device: Literal['cpu', 'cuda'] | str | torch.device = 'cpu', *,
+                 columns: dict | None = None, embed_fn: Callable | None = None,
+                 metric: str = "l2", prefilter: bool = False, normalise: bool = False,
+                 path: str = "auto"):
+        """db_path / table_name / device as in the reference (src/data/rag.py:12-15). In the
+        reference `device` only places the query-text embedding model; the store itself always
+        lives on the current CUDA device (or on `device` when it names a cuda:N).
+
+        Keyword-only extensions: `columns` (in-memory table instead of a path), `embed_fn`
+        (text -> vector, for str queries; the reference delegates that to LanceDB's registered
+        gte-base-en-v1.5 function), `metric` / `prefilter` (LanceDB 0.14 defaults: "l2", post-
+        filter), `normalise` (L2-normalise rows on upload; the reference's tables already are),
+        `path` (force a scan kernel: auto | stream_f32 | stream_bf16 | tensor_bf16).
+        """
+        self.db_path, self.table_name = db_path, table_name
+        self._ctor = dict(device=str(device), metric=metric, prefilter=prefilter, normalise=normalise,
+                          path=path)
+        self.embed_fn = embed_fn
+        self.metric, self.prefilter, self.path = metric, prefilter, path
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type == "cuda" and dev.index is not None:
+            self.device = dev
+        else:
+            if not torch.cuda.is_available():
+                from ._cabi import MragError
+                raise MragError(-3, "RAGDatabase needs a CUDA device: the B200 path has no CPU fallback")
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._from_memory = columns is not None
+        if columns is None:
+            columns = self._load(Path(db_path) / table_name)
+        self._columns = {k: v for k, v in columns.items() if k not in VECTOR_COLUMNS}
+        self._vectors = {k: columns[k] for k in VECTOR_COLUMNS if k in columns}
+        if not self._vectors:
+            raise ValueError("table has no vector column (text_embedding / image_embedding)")
+        self._stores: dict[str, EmbeddingStore] = {}
+        self._normalise = normalise
+        self._group_col: str | None = None
+        self._group_ids: dict[str, dict] = {}
+        self.table = self  # reference attribute name (rag.py:14); `table=` arguments accept it
+
+    @classmethod
+    def from_store(cls, store: EmbeddingStore, columns: dict, vector_column: str = "text_embedding",
+                   **kw) -> "RAGDatabase":
+        """Wrap an already HBM-resident store (e.g. generated on device) with its scalar
+        columns; the vector column is then not available to `select` on the host side."""
+        self = object.__new__(cls)
+        self.db_path = self.table_name = None
+        self._ctor, self.embed_fn = {}, kw.get("embed_fn")
+        self.metric, self.prefilter = kw.get("metric", "l2"), kw.get("prefilter", False)
+        self.path = kw.get("path", "auto")
+        self.device = store.device
+        self._from_memory = True
+        self._columns = {k: v for k, v in columns.items() if k not in VECTOR_COLUMNS}
+        self._vectors = {vector_column: _DeviceColumn(store)}
+        self._stores = {vector_column: store}
+        self._normalise = False
+        self._group_col, self._group_ids = None, {}
+        self.table = self
+        return self
+
+    # -- loading ------------------------------------------------------------------------------
+    @staticmethod
+    def _load(root: Path) -> dict:
+        import pandas as pd
+        if not root.is_dir():
+            raise FileNotFoundError(f"no table directory {root}")
+        cols = {c: v.to_numpy() for c, v in pd.read_parquet(root / "columns.parquet").items()}
+        for name in VECTOR_COLUMNS:
+            f = root / f"{name}.npy"
+            if f.exists():
+                cols[name] = np.load(f, mmap_mode="r")
+        return cols
+
+    def __len__(self) -> int:
+        return int(next(iter(self._vectors.values())).shape[0])
+
+    def _store(self, column: str) -> EmbeddingStore:
+        if column not in self._vectors:
+            raise ValueError(f"table has no vector column {column!r}")
+        st = self._stores.get(column)
+        if st is None:
+            vec = self._vectors[column]
+            n, dim = vec.shape
+            st = EmbeddingStore(dim, n, self.device)
+            step = max(1, (256 << 20) // (dim * 4))          # 256 MB host chunks
+            for s in range(0, n, step):
+                st.append(np.ascontiguousarray(vec[s:s + step], dtype=np.float32), normalise=self._normalise)
+            self._stores[column] = st
+            self._group_col = None
+        return st
+
+    def _groups_for(self, column: str):
+        """Dense int ids for a scalar column (the `video != x` predicate); cached per column."""
+        g = self._group_ids.get(column)
+        if g is None:
+            values = np.asarray(self._columns[column])
+            uniq, inv = np.unique(values, return_inverse=True)
+            g = {"ids": inv.astype(np.int32), "lookup": {v: i for i, v in enumerate(uniq.tolist())}}
+            self._group_ids[column] = g
+        return g
+
+    def _bind_groups(self, column: str) -> dict:
+        g = self._groups_for(column)
+        if self._group_col != column:
+            for st in self._stores.values():
+                st.set_groups(g["ids"])
+            self._group_col = column
+        return g
+
+    # -- pickling: the reference ships the bound method into spawn workers (datamodule.py:257) --
+    def __getstate__(self):
+        if self._from_memory:
+            raise TypeError("an in-memory RAGDatabase cannot be pickled; use a db_path, or call "
+                            "search_batch() instead of a process pool")
+        return {"db_path": self.db_path, "table_name": self.table_name, "ctor": self._ctor,
+                "embed_fn": self.embed_fn}
+
+    def __setstate__(self, st):
+        c = st["ctor"]
+        self.__init__(st["db_path"], st["table_name"], c["device"], embed_fn=st["embed_fn"],
+                      metric=c["metric"], prefilter=c["prefilter"], normalise=c["normalise"], path=c["path"])
+
+    # -- reference API ------------------------------------------------------------------------
+    @staticmethod
+    def format_result(result, format: Literal["pandas", "pyarrow", "dict", "list"] = 'dict'):
+        """src/data/rag.py:17-34. `result` is the list of record dicts of one query."""
+        if format == 'pandas':
+            import pandas as pd
+            return pd.DataFrame.from_records(result)
+        elif format == 'pyarrow':
+            import pyarrow as pa
+            return pa.Table.from_pylist(result)
+        elif format == 'dict':
+            return result
+        elif format == 'list':
+            return result
+        else:
+            raise ValueError(f'Invalid format: {format}')
+
+    def _as_queries(self, vector) -> tuple[torch.Tensor, bool]:
+        if isinstance(vector, str) or (isinstance(vector, (list, tuple)) and vector and isinstance(vector[0], str)):
+            if self.embed_fn is None:
+                raise NotImplementedError(
+                    "text queries need an embed_fn (the reference lets LanceDB run gte-base-en-v1.5; "
+                    "src/data/datamodule.py:296-304 always passes precomputed vectors)")
+            vector = self.embed_fn(vector)
+        if isinstance(vector, torch.Tensor):
+            q = vector.detach()
+        else:
+            q = torch.from_numpy(np.ascontiguousarray(np.asarray(vector), dtype=np.float32))
+        single = q.ndim == 1
+        if single:
+            q = q[None]
+        if q.ndim != 2:
+            raise ValueError(f"query must be [dim] or [nq, dim], got {tuple(q.shape)}")
+        q = q.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        return q, single
+
+    def _exclusions(self, where, nq: int):
+        """`where` is one SQL string (reference form) or one per query (batched form)."""
+        if where is None:
+            return None
+        wheres = [where] * nq if isinstance(where, str) else list(where)
+        if len(wheres) != nq:
+            raise ValueError("need one where clause per query")
+        col, ids = None, np.full(nq, -1, dtype=np.int32)
+        for i, w in enumerate(wheres):
+            if w is None:
+                continue
+            m = _WHERE.match(w)
+            if not m:
+                raise ValueError(f"unsupported where clause {w!r}: only `<column> != \"<value>\"` "
+                                 "(src/data/datamodule.py:235) is implemented")
+            if col is None:
+                col = m.group(1)
+                if col not in self._columns:
+                    raise ValueError(f"where clause names unknown column {col!r}")
+            elif col != m.group(1):
+                raise ValueError("all where clauses of a batch must name the same column")
+            ids[i] = self._group_ids_lookup(col, m.group(3))
+        if col is None:
+            return None
+        self._bind_groups(col)
+        return torch.from_numpy(ids).to(self.device, non_blocking=True)
+
+    def _group_ids_lookup(self, col: str, value) -> int:
+        g = self._groups_for(col)
+        v = g["lookup"].get(value)
+        if v is None:  # numeric columns arrive as strings inside the SQL literal
+            for cast in (int, float):
+                try:
+                    v = g["lookup"].get(cast(value))
+                except ValueError:
+                    v = None
+                if v is not None:
+                    break
+        return -1 if v is None else int(v)
+
+    def _records(self, dist: np.ndarray, idx: np.ndarray, select: Sequence[str] | None) -> list[list[dict]]:
+        names = list(select) if select is not None else list(self._columns) + list(self._vectors)
+        cols = []
+        for c in names:
+            if c in self._columns:
+                cols.append((c, self._columns[c], False))
+            elif c in self._vectors:
+                cols.append((c, self._vectors[c], True))
+            else:
+                raise ValueError(f"unknown column {c!r} in select")
+        out = []
+        for q in range(idx.shape[0]):
+            recs = []
+            for d, i in zip(dist[q].tolist(), idx[q].tolist()):
+                if i < 0:
+                    continue
+                r = {}
+                for c, col, is_vec in cols:
+                    v = col[i]
+                    r[c] = np.array(v, dtype=np.float32) if is_vec else (v.item() if isinstance(v, np.generic) else v)
+                r["_distance"] = d
+                recs.append(r)
+            out.append(recs)
+        return out
+
+    def _search(self, vector, vector_column_name, top_k, where, refine_factor):
+        column = vector_column_name or "text_embedding"
+        store = self._store(column)
+        q, single = self._as_queries(vector)
+        excl = self._exclusions(where, q.shape[0])
+        refine = int(min(64, max(top_k, top_k * max(1, int(refine_factor)))))
+        res = store.search(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
+                           exclude_group=excl, filter_mode="pre" if self.prefilter else "post")
+        return res, single
+
+    def vector_search(self, vector, vector_column_name: str = None, top_k: int = 10, table=None,
+                      where: str = None, select: list[str] = None, nprobes: int = 50, refine_factor: int = 30,
+                      output_format: Literal["pandas", "pyarrow", "dict"] = 'dict'):
+        """src/data/rag.py:36-61. `nprobes` is accepted and ignored (the scan is exact);
+        `refine_factor` sizes the fp32 re-rank of the bf16 scan paths. A [nq, dim] batch returns
+        one result per query."""
+        if output_format not in ("pandas", "pyarrow", "dict", "list"):
+            raise ValueError(f'Invalid format: {output_format}')
+        db = self if table is None else table
+        res, single = db._search(vector, vector_column_name, top_k, where, refine_factor)
+        dist = res.distance.cpu().numpy()
+        idx = res.index.cpu().numpy()
+        recs = db._records(dist, idx, select)
+        if single:
+            return self.format_result(recs[0], output_format)
+        return [self.format_result(r, output_format) for r in recs]
+
+    def text_search(self, text, top_k: int = 10, table=None, where: str = None, select: list[str] = None,
+                    nprobes: int = 50, refine_factor: int = 30,
+                    output_format: Literal["pandas", "pyarrow", "dict"] = 'dict'):
+        """src/data/rag.py:63-80."""
+        return self.vector_search(text, vector_column_name="text_embedding", top_k=top_k, table=table,
+                                  where=where, select=select, nprobes=nprobes, refine_factor=refine_factor,
+                                  output_format=output_format)
+
+    def image_search(self, image_embedding, top_k: int = 10, table=None, where: str = None,
+                     select: list[str] = None, nprobes: int = 50, refine_factor: int = 30,
+                     output_format: Literal["pandas", "pyarrow", "dict"] = 'dict'):
+        """src/data/rag.py:82-99."""
+        return self.vector_search(image_embedding, vector_column_name="image_embedding", top_k=top_k,
+                                  table=table, where=where, select=select, nprobes=nprobes,
+                                  refine_factor=refine_factor, output_format=output_format)
+
+    def text_image_search(self, text, image_embedding, top_k: tuple[int, int] = (20, 10), table=None,
+                          where: str = None, select: list[str] = None, nprobes: int = 50,
+                          refine_factor: int = 30,
+                          output_format: Literal["pandas", "pyarrow", "dict"] = 'dict'):
+        """src/data/rag.py:101-130: text top-k0, then image-embedding top-k1 inside that
+        candidate set (the reference materialises a temporary table; here the k0 candidate rows
+        become a temporary HBM store searched by the same kernels)."""
+        db = self if table is None else table
+        res, single = db._search(text, "text_embedding", top_k[0], where, refine_factor)
+        if not single:
+            raise ValueError("text_image_search takes one query at a time, like the reference")
+        idx0 = res.index[0]
+        idx0 = idx0[idx0 >= 0]
+        if idx0.numel() == 0:
+            return self.format_result([], output_format)
+        rows = idx0.cpu().numpy()
+        img = np.ascontiguousarray(np.asarray(db._vectors["image_embedding"])[rows], dtype=np.float32)
+        tmp = EmbeddingStore(img.shape[1], img.shape[0], self.device)
+        try:
+            tmp.append(img, normalise=False)
+            q, _ = self._as_queries(image_embedding)
+            r2 = tmp.search(q, int(min(top_k[1], 32)), metric=self.metric, path="stream_f32")
+            d2 = r2.distance.cpu().numpy()
+            i2 = r2.index.cpu().numpy()
+        finally:
+            tmp.close()
+        i2g = np.where(i2 >= 0, rows[np.clip(i2, 0, len(rows) - 1)], -1)
+        return self.format_result(db._records(d2, i2g, select)[0], output_format)
+
+    # -- batched fast path (replaces the spawn pool of datamodule.py:257-262) -----------------------
+    def search_batch(self, vectors, top_k: int = 10, where: Sequence[str | None] | str | None = None,
+                     select: list[str] | None = None, refine_factor: int = 30,
+                     vector_column_name: str = "text_embedding", batch: int = 4096) -> list[list[dict]]:
+        """One scan per `batch` queries instead of one LanceDB call per annotation; returns the
+        same per-query record lists the reference stores in `anno['ref_videos']`
+        (src/data/datamodule.py:264-265)."""
+        q_all, _ = self._as_queries(vectors)
+        wheres = None if where is None else ([where] * q_all.shape[0] if isinstance(where, str) else list(where))
+        out: list[list[dict]] = []
+        for s in range(0, q_all.shape[0], batch):
+            w = None if wheres is None else wheres[s:s + batch]
+            res, _ = self._search(q_all[s:s + batch], vector_column_name, top_k, w, refine_factor)
+            out.extend(self._records(res.distance.cpu().numpy(), res.index.cpu().numpy(), select))
+        return out
+
+    def retrieve_for_annotations(self, annotations: list[dict], ref_video_num: int,
+                                 batch: int = 4096) -> list[dict]:
+        """The `rag_text` branch of VideoDataModule.prepare_annotations
+        (src/data/datamodule.py:231-236, 264-265) as one batched call: k = ref_video_num + 3,
+        `where video != "<own video>"`, select video/start_sec/end_sec; attaches `ref_videos`."""
+        vec = np.stack([np.asarray(a['text_embedding'], dtype=np.float32) for a in annotations])
+        wheres = [f'video != "{a["video"]}"' for a in annotations]
+        results = self.search_batch(vec, top_k=ref_video_num + 3, where=wheres,
+                                    select=['video', 'start_sec', 'end_sec'], batch=batch)
+        for anno, r in zip(annotations, results):
+            anno['ref_videos'] = r
+        return annotations

@@ -1,0 +1,261 @@
+"""HBM-resident stores of the retrieval hot path.
+
+`EmbeddingStore`  — the text-embedding column of the RAG table written by the reference's
+                    tools/build_rag_database.py:35-50 (fp32[dim], L2-normalised), held as an
+                    fp32 master + bf16 shadow in device memory owned by libmrag.
+`FeatureTable`    — the precomputed motion-feature rows [N, L, C] that stand in for the
+                    reference's per-sample decode + VideoMAE + Resampler
+                    (src/data/dataset.py:285-312, src/projects/condition/module.py:264-268).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import FILTER, METRIC, PATH, PlanInfo, SearchParams, StoreInfo, check
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class SearchResult:
+    """Device tensors [nq, k]; unused slots hold (+inf, -1, -1)."""
+    distance: torch.Tensor  # float32, ascending
+    index: torch.Tensor     # int64 global row ids
+    group: torch.Tensor     # int32 group id of each hit
+
+
+class EmbeddingStore:
+    def __init__(self, dim: int, capacity_rows: int, device: int | str | torch.device = 0):
+        self._lib = _cabi.load()
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise _cabi.MragError(-3, f"EmbeddingStore lives in HBM; got device {dev}")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
+        self.dim = int(dim)
+        h = C.c_void_p()
+        check(self._lib.mrag_store_create(self.dim, int(capacity_rows), self.device.index, C.byref(h)))
+        self._h = h
+        self._ws: torch.Tensor | None = None
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.mrag_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- contents ---------------------------------------------------------------------------
+    def info(self) -> StoreInfo:
+        inf = StoreInfo()
+        check(self._lib.mrag_store_get_info(self._h, C.byref(inf)))
+        return inf
+
+    def __len__(self) -> int:
+        return int(self.info().n_rows)
+
+    def append(self, rows: torch.Tensor | np.ndarray, normalise: bool = True) -> None:
+        """Append fp32 rows [n, dim] from host (numpy / CPU tensor) or device memory."""
+        if isinstance(rows, np.ndarray):
+            rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32))
+        rows = rows.to(torch.float32).contiguous()
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"rows must be [n, {self.dim}], got {tuple(rows.shape)}")
+        on_dev = rows.is_cuda
+        if on_dev and rows.device != self.device:
+            rows = rows.to(self.device)
+        check(self._lib.mrag_store_append(self._h, C.c_void_p(rows.data_ptr()), rows.shape[0],
+                                          1 if on_dev else 0, 1 if normalise else 0,
+                                          _stream_ptr(self.device)))
+        if not on_dev:
+            torch.cuda.current_stream(self.device).synchronize()  # pageable source must stay alive
+
+    def set_groups(self, groups: torch.Tensor | np.ndarray) -> None:
+        """int32 group id per row (rows of the same source video share an id)."""
+        if isinstance(groups, np.ndarray):
+            groups = torch.from_numpy(np.ascontiguousarray(groups, dtype=np.int32))
+        groups = groups.to(torch.int32).contiguous()
+        on_dev = groups.is_cuda
+        check(self._lib.mrag_store_set_groups(self._h, C.c_void_p(groups.data_ptr()), groups.numel(),
+                                              1 if on_dev else 0, _stream_ptr(self.device)))
+        if not on_dev:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def rows_f32(self) -> torch.Tensor:
+        """Zero-copy view of the fp32 master rows (for tests / re-use by torch code)."""
+        inf = self.info()
+        return _view(inf.rows_f32_dev, (int(inf.n_rows), self.dim), torch.float32, self.device, self)
+
+    def rows_bf16(self) -> torch.Tensor:
+        inf = self.info()
+        return _view(inf.rows_bf16_dev, (int(inf.n_rows), self.dim), torch.bfloat16, self.device, self)
+
+    # -- search -----------------------------------------------------------------------------
+    def _params(self, k, metric, path, refine, filter_mode, index_base) -> SearchParams:
+        return SearchParams(k=int(k), metric=METRIC[metric], path=PATH[path], refine=int(refine),
+                            filter_mode=FILTER[filter_mode], reserved=0, index_base=int(index_base))
+
+    def plan(self, nq: int, params: SearchParams | None = None, **kw) -> PlanInfo:
+        """How a search of nq queries would run (path, grid, candidates, workspace, work)."""
+        if params is None:
+            params = self._params(kw.get("k", 12), kw.get("metric", "l2"), kw.get("path", "auto"),
+                                  kw.get("refine", 0), kw.get("filter_mode", "none"),
+                                  kw.get("index_base", 0))
+        info = PlanInfo()
+        check(self._lib.mrag_search_plan(self._h, int(nq), C.byref(params), C.byref(info)))
+        return info
+
+    def search(self, queries: torch.Tensor, k: int, *, metric: str = "l2", path: str = "auto",
+               refine: int = 0, exclude_group: torch.Tensor | None = None,
+               filter_mode: str = "post", index_base: int = 0,
+               out: SearchResult | None = None, timings: list | None = None) -> SearchResult:
+        """Device-resident search: queries [nq, dim] fp32 on this store's GPU -> SearchResult.
+
+        Asynchronous on the current stream; nothing is copied to the host.
+        """
+        if queries.device != self.device or queries.dtype != torch.float32 or not queries.is_contiguous():
+            raise ValueError("queries must be a contiguous float32 tensor on the store's device")
+        nq = queries.shape[0]
+        if exclude_group is None:
+            filter_mode = "none"
+        elif exclude_group.device != self.device or exclude_group.dtype != torch.int32:
+            raise ValueError("exclude_group must be int32 on the store's device")
+        p = self._params(k, metric, path, refine, filter_mode, index_base)
+        need = int(self.plan(nq, p).workspace_bytes)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if out is None:
+            out = SearchResult(torch.empty((nq, k), dtype=torch.float32, device=self.device),
+                               torch.empty((nq, k), dtype=torch.int64, device=self.device),
+                               torch.empty((nq, k), dtype=torch.int32, device=self.device))
+        args = (self._h, C.c_void_p(queries.data_ptr()), nq, C.byref(p),
+                C.c_void_p(exclude_group.data_ptr()) if exclude_group is not None else None,
+                C.c_void_p(out.distance.data_ptr()), C.c_void_p(out.index.data_ptr()),
+                C.c_void_p(out.group.data_ptr()), C.c_void_p(self._ws.data_ptr()), self._ws.numel(),
+                _stream_ptr(self.device))
+        if timings is None:
+            check(self._lib.mrag_search(*args))
+        else:  # synchronous, event-bracketed variant: appends (scan_ms, total_ms)
+            a, b = C.c_float(), C.c_float()
+            check(self._lib.mrag_search_timed(*args, C.byref(a), C.byref(b)))
+            timings.append((a.value, b.value))
+        return out
+
+    def search_host(self, queries: np.ndarray, k: int, *, metric: str = "l2", path: str = "auto",
+                    refine: int = 0, exclude_group: np.ndarray | None = None,
+                    filter_mode: str = "post", index_base: int = 0):
+        """Host-buffer search through `mrag_search_host` (copies inside, synchronous).
+
+        Returns (distance f32 [nq,k], index i64 [nq,k], group i32 [nq,k]) numpy arrays.
+        """
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [nq, {self.dim}]")
+        nq = q.shape[0]
+        ex = None
+        if exclude_group is None:
+            filter_mode = "none"
+        else:
+            ex = np.ascontiguousarray(exclude_group, dtype=np.int32)
+        p = self._params(k, metric, path, refine, filter_mode, index_base)
+        dist = np.empty((nq, k), dtype=np.float32)
+        idx = np.empty((nq, k), dtype=np.int64)
+        grp = np.empty((nq, k), dtype=np.int32)
+        check(self._lib.mrag_search_host(
+            self._h, q.ctypes.data_as(C.c_void_p), nq, C.byref(p),
+            ex.ctypes.data_as(C.c_void_p) if ex is not None else None,
+            dist.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p),
+            grp.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)))
+        return dist, idx, grp
+
+
+def merge_topk(cand_dist: torch.Tensor, cand_idx: torch.Tensor, cand_group: torch.Tensor | None,
+               k_out: int, exclude_group: torch.Tensor | None = None,
+               filter_mode: str = "post", shard_stride_bytes: int = 0) -> SearchResult:
+    """Merge per-shard results laid out [nshards, nq, k_in] (the all-gather layout); with
+    shard_stride_bytes the three fields may be views into one packed per-rank record."""
+    lib = _cabi.load()
+    nshards, nq, k_in = cand_dist.shape
+    dev = cand_dist.device
+    out = SearchResult(torch.empty((nq, k_out), dtype=torch.float32, device=dev),
+                       torch.empty((nq, k_out), dtype=torch.int64, device=dev),
+                       torch.empty((nq, k_out), dtype=torch.int32, device=dev))
+    if exclude_group is None:
+        filter_mode = "none"
+    check(lib.mrag_merge_topk(
+        C.c_void_p(cand_dist.data_ptr()), C.c_void_p(cand_idx.data_ptr()),
+        C.c_void_p(cand_group.data_ptr()) if cand_group is not None else None,
+        int(shard_stride_bytes), nshards, nq, k_in, k_out,
+        C.c_void_p(exclude_group.data_ptr()) if exclude_group is not None else None,
+        FILTER[filter_mode], C.c_void_p(out.distance.data_ptr()), C.c_void_p(out.index.data_ptr()),
+        C.c_void_p(out.group.data_ptr()), _stream_ptr(dev)))
+    return out
+
+
+def _view(ptr: int, shape, dtype, device, owner) -> torch.Tensor:
+    """Wrap raw device memory owned by libmrag as a torch tensor (no copy)."""
+    n = int(np.prod(shape))
+    if n == 0 or not ptr:
+        return torch.empty(shape, dtype=dtype, device=device)
+    itemsize = torch.empty((), dtype=dtype).element_size()
+    typestr = {torch.float32: "<f4", torch.bfloat16: "<u2", torch.int32: "<i4"}[dtype]
+
+    class _Holder:
+        pass
+
+    holder = _Holder()
+    holder.owner = owner
+    holder.__cuda_array_interface__ = {
+        "shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+        "strides": None,
+    }
+    with torch.cuda.device(device):
+        t = torch.as_tensor(holder, device=device)
+    if dtype == torch.bfloat16:
+        t = t.view(torch.bfloat16)
+    assert t.element_size() == itemsize
+    return t
+
+
+class FeatureTable:
+    """Motion-feature rows [n_rows, L, C] in HBM, optionally row-sharded over ranks.
+
+    Global row r lives in shard r // rows_per_shard. `shard_ptrs` is the device array of
+    base pointers handed to the gather kernel: the local block plus, after
+    `parallel.open_peer_tables`, the peer-mapped blocks of the other ranks (read over NVLink).
+    """
+
+    def __init__(self, local: torch.Tensor, rows_per_shard: int | None = None, shard_rank: int = 0,
+                 n_shards: int = 1):
+        if local.ndim != 3 or not local.is_cuda or not local.is_contiguous():
+            raise ValueError("local feature block must be a contiguous CUDA tensor [rows, L, C]")
+        if local.dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("feature dtype must be bfloat16 or float32")
+        self.local = local
+        self.device = local.device
+        self.L, self.Cdim = int(local.shape[1]), int(local.shape[2])
+        self.rows_per_shard = int(rows_per_shard if rows_per_shard is not None else local.shape[0])
+        self.shard_rank, self.n_shards = int(shard_rank), int(n_shards)
+        ptrs = [0] * self.n_shards
+        ptrs[self.shard_rank] = local.data_ptr()
+        self._peer_ptrs: list[int] = ptrs
+        self.shard_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+
+    def set_peer_ptr(self, shard: int, ptr: int) -> None:
+        self._peer_ptrs[shard] = int(ptr)
+        self.shard_ptrs = torch.tensor(self._peer_ptrs, dtype=torch.int64, device=self.device)
+
+    @property
+    def complete(self) -> bool:
+        return all(p != 0 for p in self._peer_ptrs)

@@ -1,0 +1,72 @@
+"""ORACLE (test infrastructure) — the parity rule of BASELINE.md §5 as code.
+
+Scores within `rtol` relative of the fp32 oracle; indices identical except positions whose
+ORACLE scores differ by less than that tolerance (documented near-ties: the count is
+returned so every run can state it).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def pair_distances(db: np.ndarray, queries: np.ndarray, idx: np.ndarray, metric: str) -> np.ndarray:
+    """float64 `_distance` of (query q, row idx[q, j]) pairs; nan where idx < 0."""
+    db = np.asarray(db, dtype=np.float32)
+    queries = np.asarray(queries, dtype=np.float32)
+    out = np.full(idx.shape, np.nan, dtype=np.float64)
+    for q in range(idx.shape[0]):
+        valid = idx[q] >= 0
+        if not valid.any():
+            continue
+        rows = db[idx[q][valid]].astype(np.float64)
+        qv = queries[q].astype(np.float64)
+        if metric == "l2":
+            d = ((rows - qv[None]) ** 2).sum(-1)
+        elif metric == "dot":
+            d = 1.0 - rows @ qv
+        elif metric == "cosine":
+            d = 1.0 - (rows @ qv) / np.maximum(np.linalg.norm(rows, axis=-1) * np.linalg.norm(qv), 1e-30)
+        else:
+            raise ValueError(metric)
+        out[q, valid] = d
+    return out
+
+
+def check_retrieval(got_dist: np.ndarray, got_idx: np.ndarray, ref_dist: np.ndarray,
+                    ref_idx: np.ndarray, db: np.ndarray, queries: np.ndarray, metric: str = "l2",
+                    rtol: float = 1e-3, atol: float = 1e-6) -> dict:
+    """Raises AssertionError on a parity violation; returns a report otherwise.
+
+    atol guards relative comparisons of distances that are ~0 (a query equal to a row).
+    """
+    got_dist = np.asarray(got_dist, dtype=np.float64)
+    ref_dist = np.asarray(ref_dist, dtype=np.float64)
+    got_idx = np.asarray(got_idx, dtype=np.int64)
+    ref_idx = np.asarray(ref_idx, dtype=np.int64)
+    assert got_idx.shape == ref_idx.shape, (got_idx.shape, ref_idx.shape)
+    # 1. same number of rows per query
+    n_got = (got_idx >= 0).sum(-1)
+    n_ref = (ref_idx >= 0).sum(-1)
+    bad = np.nonzero(n_got != n_ref)[0]
+    assert bad.size == 0, f"row-count mismatch for queries {bad[:8]}: got {n_got[bad[:8]]} ref {n_ref[bad[:8]]}"
+    # 2. returned scores match the exact distance of the rows actually returned
+    exact = pair_distances(db, queries, got_idx, metric)
+    valid = got_idx >= 0
+    err = np.abs(got_dist[valid] - exact[valid]) / np.maximum(np.abs(exact[valid]), atol / rtol)
+    max_rel = float(err.max()) if err.size else 0.0
+    assert max_rel <= rtol, f"score error {max_rel:.3e} exceeds rtol {rtol:g}"
+    # 3. ascending order, ties by index
+    for q in range(got_idx.shape[0]):
+        d = got_dist[q][valid[q]]
+        assert np.all(np.diff(d) >= 0), f"query {q}: distances not ascending"
+    # 4. indices identical up to near-ties of the ORACLE scores
+    diff = (got_idx != ref_idx) & valid
+    near = 0
+    for q, j in zip(*np.nonzero(diff)):
+        gap = abs(exact[q, j] - ref_dist[q, j])
+        lim = rtol * max(abs(ref_dist[q, j]), atol / rtol)
+        assert gap <= lim, (f"query {q} rank {j}: row {got_idx[q, j]} (d={exact[q, j]:.9g}) returned, "
+                            f"oracle has row {ref_idx[q, j]} (d={ref_dist[q, j]:.9g}); gap {gap:.3e} > {lim:.3e}")
+        near += 1
+    return {"queries": int(got_idx.shape[0]), "positions": int(valid.sum()), "index_mismatches": int(diff.sum()),
+            "near_tie_positions": int(near), "max_rel_score_err": max_rel}

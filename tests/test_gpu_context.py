@@ -1,0 +1,85 @@
+"""Gather kernel (K4) against the reference-captured golden context and the restatement."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cama_context as cc
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(a):
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+
+
+@pytest.mark.parametrize("name,dt", [("bf16", torch.bfloat16), ("f32", torch.float32)])
+def test_gather_reproduces_reference_context_bit_for_bit(libmrag, golden_dir, name, dt):
+    """Fixture x was captured from the reference's real ActionTransformer.batch_forward."""
+    from motionrag_b200 import FeatureTable, gather_context
+    z = np.load(golden_dir / f"cama_context_{name}.npz")
+    t = (lambda k: _bf16(z[k])) if dt == torch.bfloat16 else (lambda k: torch.from_numpy(z[k]))
+    ref = t("ref_feats")
+    b, K, L, C = ref.shape
+    # put the retrieved rows at scattered positions of a bigger table
+    g = torch.Generator().manual_seed(0)
+    rows = torch.randperm(500, generator=g)[:b * K].view(b, K)
+    table = torch.randn(500, L, C, generator=g).to(dt)
+    table[rows.flatten()] = ref.reshape(b * K, L, C)
+    ft = FeatureTable(table.cuda())
+    pos = torch.from_numpy(z["pos_table"])[0].to(dt).cuda()
+    x = gather_context(ft, rows.cuda(), t("sos").cuda(), torch.zeros(L, C, dtype=dt).cuda(), pos, t("cond").cuda())
+    assert torch.equal(x.cpu(), t("x"))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("b,K,with_pe,with_cond", [(1, 9, True, True), (16, 9, True, False), (5, 3, False, True),
+                                                   (2, 1, False, False)])
+def test_gather_matches_restatement_cogvideox_shapes(libmrag, dt, b, K, with_pe, with_cond):
+    """L=25, C=1024 (configs/cogvideox/MotionRAG_open.yml:228-238), missing refs -> uncond row."""
+    from motionrag_b200 import FeatureTable, MotionContext
+    L, C, n = 25, 1024, 300
+    g = torch.Generator().manual_seed(b * 100 + K)
+    table = torch.randn(n, L, C, generator=g).to(dt)
+    idx = torch.randint(0, n, (b, K), generator=g)
+    idx[0, K // 2] = -1
+    idx[-1, 0] = -1
+    sos = (torch.randn(1, L, C, generator=g) / 32).to(dt)
+    un = torch.randn(L, C, generator=g).to(dt)
+    cond = torch.randn(b, (K + 1) * L, C, generator=g).to(dt) if with_cond else None
+    ctx = MotionContext(FeatureTable(table.cuda()), sos, un, pe_max_length=256 if with_pe else None)
+    x = ctx.build(idx.cuda(), cond.cuda() if with_cond else None)
+    feats = cc.gather_restatement(table, idx, un)
+    want = cc.context_restatement(feats, sos, cc.sinusoid_table(256, C) if with_pe else None,
+                                  cond.clone() if with_cond else None)
+    assert torch.equal(x.cpu(), want)
+    assert torch.equal(ctx.get_mask(K + 1, L).cpu(), cc.block_causal_mask(K + 1, L))
+    assert torch.equal(ctx.uncond_action_emb(b).cpu(), un[None].expand(b, -1, -1))
+
+
+def test_gather_reads_row_sharded_tables_through_pointer_table(libmrag):
+    """Two shard blocks (same GPU here; peer-mapped over NVLink in the multi-process case)."""
+    from motionrag_b200 import FeatureTable, gather_context
+    L, C, rps = 25, 1024, 64
+    g = torch.Generator().manual_seed(3)
+    full = torch.randn(2 * rps, L, C, generator=g).to(torch.bfloat16)
+    s0, s1 = full[:rps].contiguous().cuda(), full[rps:].contiguous().cuda()
+    ft = FeatureTable(s0, rows_per_shard=rps, shard_rank=0, n_shards=2)
+    assert not ft.complete
+    with pytest.raises(RuntimeError):
+        gather_context(ft, torch.zeros(1, 2, dtype=torch.int64).cuda(), full[0].cuda(), full[0].cuda())
+    ft.set_peer_ptr(1, s1.data_ptr())
+    idx = torch.tensor([[3, 100, 64, 63], [127, 0, -1, 65]])
+    un = torch.zeros(L, C, dtype=torch.bfloat16)
+    x = gather_context(ft, idx.cuda(), full[5].cuda(), un.cuda())
+    want = cc.context_restatement(cc.gather_restatement(full, idx, un), full[5][None], None, None)
+    assert torch.equal(x.cpu(), want)
+
+
+def test_gather_argument_checks(libmrag):
+    from motionrag_b200 import FeatureTable, gather_context
+    ft = FeatureTable(torch.zeros(4, 25, 1024, dtype=torch.bfloat16).cuda())
+    z = torch.zeros(25, 1024, dtype=torch.bfloat16).cuda()
+    with pytest.raises(ValueError):
+        gather_context(ft, torch.zeros(1, 2, dtype=torch.int32).cuda(), z, z)
+    with pytest.raises(ValueError):
+        gather_context(ft, torch.zeros(1, 2, dtype=torch.int64).cuda(), z.float(), z)

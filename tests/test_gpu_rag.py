@@ -1,0 +1,106 @@
+"""`RAGDatabase` drop-in against the oracle's restatement of the reference class."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flat_search as fs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def table():
+    rng = np.random.default_rng(0)
+    n, dim = 6000, 768
+    emb = fs.normalise_rows(rng.standard_normal((n, dim)).astype(np.float32))
+    return {"text": np.array([f"caption {j}" for j in range(n)]), "text_embedding": emb,
+            "image_embedding": fs.normalise_rows(rng.standard_normal((n, 768)).astype(np.float32)),
+            "id": np.arange(n), "uid": np.array([f"u{j}" for j in range(n)]),
+            "dataset": np.array(["openvid"] * n), "video": np.array([f"clip_{j // 3:05d}.mp4" for j in range(n)]),
+            "start_sec": (np.arange(n) % 3) * 2.0, "end_sec": (np.arange(n) % 3) * 2.0 + 2.0}
+
+
+def _same(a, b):
+    assert len(a) == len(b)
+    for ra, rb in zip(a, b):
+        assert set(ra) == set(rb)
+        for key in ra:
+            if key == "_distance":
+                assert ra[key] == pytest.approx(rb[key], rel=1e-3, abs=1e-6)
+            elif isinstance(ra[key], np.ndarray):
+                np.testing.assert_array_equal(ra[key], rb[key])
+            else:
+                assert ra[key] == rb[key]
+
+
+def test_text_search_matches_reference_call_pattern(libmrag, table):
+    """The exact kwargs prepare_annotations builds (src/data/datamodule.py:231-236)."""
+    from motionrag_b200 import RAGDatabase
+    db = RAGDatabase(None, None, 'cuda', columns=table)
+    ora = fs.OracleRAGDatabase(table)
+    rng = np.random.default_rng(1)
+    for j in rng.integers(0, 6000, 6):
+        q = (table["text_embedding"][j] + 0.01 * rng.standard_normal(768)).astype(np.float32) * 8
+        kw = dict(text=q, top_k=9 + 3, where=f'video != "{table["video"][j]}"', select=['video', 'start_sec', 'end_sec'])
+        got, want = db.text_search(**kw), ora.text_search(**kw)
+        _same(got, want)
+        assert 9 <= len(got) <= 12 and all(r["video"] != table["video"][j] for r in got)
+    # defaults: top_k=10, all columns + vector + _distance, torch / CUDA tensors accepted
+    full = db.text_search(torch.from_numpy(table["text_embedding"][5]))
+    assert len(full) == 10 and full[0]["id"] == 5 and set(full[0]) == set(table) | {"_distance"}
+    assert db.text_search(torch.from_numpy(table["text_embedding"][5]).cuda().half(), top_k=3)[0]["id"] == 5
+    assert db.vector_search(table["text_embedding"][5], "text_embedding", output_format="pandas").shape[0] == 10
+    assert db.image_search(table["image_embedding"][77], top_k=4)[0]["id"] == 77
+    with pytest.raises(ValueError, match="Invalid format"):
+        db.text_search(q, output_format="csv")
+    with pytest.raises(ValueError, match="unsupported where"):
+        db.text_search(q, where="start_sec > 1")
+    with pytest.raises(NotImplementedError):
+        db.text_search("a person pours water")
+    db2 = RAGDatabase(None, None, columns=table, embed_fn=lambda s: table["text_embedding"][42])
+    assert db2.text_search("anything", top_k=1)[0]["id"] == 42
+
+
+def test_batched_fast_path_equals_per_query_calls(libmrag, table):
+    from motionrag_b200 import RAGDatabase
+    db = RAGDatabase(None, None, 'cuda', columns=table)
+    rng = np.random.default_rng(2)
+    src = rng.integers(0, 6000, 300)
+    annos = [{"video": table["video"][j], "text_embedding": (table["text_embedding"][j] * 6).astype(np.float32)}
+             for j in src]
+    out = db.retrieve_for_annotations([dict(a) for a in annos], ref_video_num=9, batch=128)
+    ora = fs.OracleRAGDatabase(table)
+    for a, o in list(zip(annos, out))[::25]:
+        want = ora.text_search(a["text_embedding"], top_k=12, where=f'video != "{a["video"]}"',
+                               select=['video', 'start_sec', 'end_sec'])
+        _same(o["ref_videos"], want)
+        single = db.text_search(a["text_embedding"], top_k=12, where=f'video != "{a["video"]}"',
+                                select=['video', 'start_sec', 'end_sec'])
+        _same(o["ref_videos"], single)
+
+
+def test_text_image_two_stage(libmrag, table):
+    """src/data/rag.py:101-130 / datamodule.py:239-245: text top-(2K+3), then image top-K."""
+    from motionrag_b200 import RAGDatabase
+    db = RAGDatabase(None, None, 'cuda', columns=table)
+    q_t = table["text_embedding"][100] * 3
+    q_i = table["image_embedding"][100] * 2
+    got = db.text_image_search(q_t, q_i, top_k=(21, 9), select=['video', 'id'])
+    _, i0 = fs.flat_search(table["text_embedding"], q_t[None], 21)
+    cand = i0[0]
+    d1, i1 = fs.flat_search(table["image_embedding"][cand], q_i[None], 9)
+    assert [r["id"] for r in got] == cand[i1[0]].tolist()
+    np.testing.assert_allclose([r["_distance"] for r in got], d1[0], rtol=1e-3)
+
+
+def test_on_disk_table_and_pickle_roundtrip(libmrag, table, tmp_path):
+    import pickle
+    from motionrag_b200 import RAGDatabase, save_table
+    small = {k: v[:900] for k, v in table.items()}
+    save_table(tmp_path / "rag.db", "motion_caption", small)
+    db = RAGDatabase(str(tmp_path / "rag.db"), "motion_caption", 'cuda')
+    r = db.text_search(small["text_embedding"][10], top_k=3, select=["id"])
+    db2 = pickle.loads(pickle.dumps(db.text_search)).__self__      # what the spawn pool does
+    assert [x["id"] for x in db2.text_search(small["text_embedding"][10], top_k=3, select=["id"])] == [x["id"] for x in r]
+    with pytest.raises(TypeError):
+        pickle.dumps(RAGDatabase(None, None, columns=small))

@@ -1,0 +1,95 @@
+"""Host-side logic that needs no GPU: where-clause parsing, record formatting, layouts, plans."""
+import numpy as np
+import pytest
+import torch
+
+from motionrag_b200 import parallel, rag
+from motionrag_b200.context import block_causal_mask, sinusoid_table
+from oracle import cama_context as cc
+
+
+def _db_no_gpu(n=30, dim=8):
+    """A RAGDatabase shell with host columns only (bypasses __init__, which requires CUDA)."""
+    db = object.__new__(rag.RAGDatabase)
+    rng = np.random.default_rng(0)
+    db._columns = {"video": np.array([f"v{j // 3}" for j in range(n)]), "id": np.arange(n),
+                   "start_sec": np.arange(n, dtype=np.float64)}
+    db._vectors = {"text_embedding": rng.standard_normal((n, dim)).astype(np.float32)}
+    db._group_ids, db._group_col, db._stores = {}, None, {}
+    return db
+
+
+def test_where_regex_accepts_only_the_reference_form():
+    assert rag._WHERE.match('video != "a b/c.mp4"').group(3) == "a b/c.mp4"
+    assert rag._WHERE.match("video != 'x'").group(1) == "video"
+    for bad in ('video = "a"', 'start_sec > 3', 'video != a', 'video != "a" AND id != "3"'):
+        assert rag._WHERE.match(bad) is None
+
+
+def test_group_ids_and_lookup():
+    db = _db_no_gpu()
+    g = db._groups_for("video")
+    assert g["ids"].dtype == np.int32 and len(set(g["ids"].tolist())) == 10
+    assert db._group_ids_lookup("video", "v3") == g["ids"][9]
+    assert db._group_ids_lookup("video", "missing") == -1
+    assert db._group_ids_lookup("id", "7") == 7          # numeric literal inside the SQL string
+
+
+def test_records_schema_and_padding_rows_are_dropped():
+    db = _db_no_gpu()
+    dist = np.array([[0.1, 0.2, np.inf]], dtype=np.float32)
+    idx = np.array([[4, 9, -1]])
+    recs = db._records(dist, idx, ["video", "start_sec"])
+    assert recs == [[{"video": "v1", "start_sec": 4.0, "_distance": pytest.approx(0.1)},
+                     {"video": "v3", "start_sec": 9.0, "_distance": pytest.approx(0.2)}]]
+    full = db._records(dist, idx, None)[0][0]
+    assert set(full) == {"video", "id", "start_sec", "text_embedding", "_distance"}
+    with pytest.raises(ValueError):
+        db._records(dist, idx, ["nope"])
+
+
+def test_format_result_formats_and_error():
+    recs = [{"video": "a", "_distance": 0.5}]
+    assert rag.RAGDatabase.format_result(recs, "dict") == recs
+    assert rag.RAGDatabase.format_result(recs, "list") == recs
+    assert list(rag.RAGDatabase.format_result(recs, "pandas").columns) == ["video", "_distance"]
+    assert rag.RAGDatabase.format_result(recs, "pyarrow").num_rows == 1
+    with pytest.raises(ValueError, match="Invalid format"):
+        rag.RAGDatabase.format_result(recs, "csv")
+
+
+def test_save_table_roundtrip(tmp_path):
+    n = 12
+    cols = {"text_embedding": np.random.default_rng(1).standard_normal((n, 8)).astype(np.float32),
+            "video": [f"v{j}" for j in range(n)], "start_sec": np.arange(n, dtype=np.float64),
+            "end_sec": np.arange(n, dtype=np.float64) + 1, "id": np.arange(n)}
+    rag.save_table(tmp_path, "motion_caption", cols)
+    back = rag.RAGDatabase._load(tmp_path / "motion_caption")
+    np.testing.assert_array_equal(back["text_embedding"], cols["text_embedding"])
+    assert list(back["video"]) == cols["video"] and back["start_sec"].dtype == np.float64
+
+
+def test_shard_range_covers_table_exactly():
+    for n, g in [(10, 3), (1_000_000, 8), (7, 8), (256, 2)]:
+        spans = [parallel.shard_range(n, g, r) for r in range(g)]
+        assert spans[0][1] == 0 and spans[-1][2] == n
+        assert all(a[2] == b[1] for a, b in zip(spans, spans[1:]))
+        assert all(lo == min(n, r * rps) for r, (rps, lo, hi) in enumerate(spans))
+
+
+def test_packed_layout_views_alias_one_buffer():
+    lay = parallel.PackedLayout(nq=3, k=4)
+    buf = torch.zeros(2 * lay.nbytes, dtype=torch.uint8)
+    d, g, i = lay.views(buf, 2)
+    assert d.shape == g.shape == i.shape == (2, 3, 4)
+    d[1, 2, 3] = 1.5
+    g[0, 0, 0] = 7
+    i[1, 0, 0] = 1 << 40
+    d2, g2, i2 = lay.views(buf, 2)
+    assert d2[1, 2, 3] == 1.5 and g2[0, 0, 0] == 7 and i2[1, 0, 0] == 1 << 40
+    assert d[1].data_ptr() - d[0].data_ptr() == lay.nbytes and i[0].data_ptr() % 8 == 0
+
+
+def test_mask_and_sinusoid_match_oracle():
+    assert torch.equal(block_causal_mask(10, 25), cc.block_causal_mask(10, 25))
+    assert torch.equal(sinusoid_table(256, 1024), cc.sinusoid_table(256, 1024)[0])

@@ -23,3 +23,11 @@ if [ "${1:-}" != "quick" ]; then
       --log-file $OUT/launches.csv python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
   echo "ncu launches rc=$?" | tee -a $OUT/summary.txt
 fi
+if [ "${1:-}" == "prof" ] || [ "${2:-}" == "prof" ]; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_stream -s 4 -c 2 -f -o $OUT/prof_k1 \
+      python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_k1.log 2>&1
+  echo "ncu k1 rc=$?" | tee -a $OUT/summary.txt
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k2_batch -s 2 -c 1 -f -o $OUT/prof_k2 \
+      python bench.py --workload c2 --steps 3 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_k2.log 2>&1
+  echo "ncu k2 rc=$?" | tee -a $OUT/summary.txt
+fi

@@ -20,8 +20,8 @@ OUT_DIR = PKG / "_lib"
 LIB = OUT_DIR / "libmrag.so"
 STAMP = OUT_DIR / "libmrag.stamp"
 
-SOURCES = ["api.cu", "k1_stream.cu", "k2_batch.cu", "k3_merge.cu", "k4_gather.cu"]
-HEADERS = ["common.cuh", "kernels.h"]
+SOURCES = ["api.cu", "k1_stream.cu", "k2_batch.cu", "k2_batch2.cu", "k3_merge.cu", "k4_gather.cu"]
+HEADERS = ["common.cuh", "kernels.h", "k2_common.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -70,8 +71,10 @@ struct Plan {
   int rerank;     // entries re-scored by K3
   int k1_grid = 0;
   K2Plan k2{};
+  bool k2_pair = false;  // cta_group::2 kernel
+  int q_rows_padded = 0;
   int cands_per_query = 0;
-  size_t off_cand = 0, off_qbf16 = 0, total = 0;
+  size_t off_cand = 0, off_qbf16 = 0, off_gthr = 0, total = 0;
 };
 
 int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan* out) {
@@ -108,20 +111,29 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
     if (!k2_supported(s->dim))
       return fail(MRAG_ERR_UNSUPPORTED, "tensor path needs dim %% 64 == 0 (dim=%d)", s->dim);
     pl.kc = kK2Cand;
-    pl.rerank = refine;
-    pl.k2 = k2_plan(s->n_rows, nq, s->sm_count);
+    // the shared per-query bound guarantees the global top-32 by bf16 score, not more
+    pl.rerank = refine > kK2Cand ? kK2Cand : refine;
+    // more than one query tile: the CTA-pair kernel (M = 256 per cluster); MRAG_K2_SINGLE=1
+    // forces the single-CTA kernel for A/B measurements
+    const char* force = getenv("MRAG_K2_SINGLE");
+    pl.k2_pair = nq > 128 && !(force && force[0] == '1');
+    pl.k2 = pl.k2_pair ? k2_plan_pair(s->n_rows, nq, s->sm_count) : k2_plan(s->n_rows, nq, s->sm_count);
+    pl.q_rows_padded = pl.k2_pair ? ((pl.k2.m_tiles + 1) / 2) * 256 : pl.k2.m_tiles * 128;
     pl.cands_per_query = pl.k2.chunks * kK2Cand;
   } else {
     return fail(MRAG_ERR_ARG, "unknown path %d", p->path);
   }
-  if (pl.cands_per_query > 16384)
-    return fail(MRAG_ERR_UNSUPPORTED, "too many candidates per query (%d)", pl.cands_per_query);
+  if (pl.cands_per_query / pl.kc > 512)
+    return fail(MRAG_ERR_UNSUPPORTED, "too many candidate runs per query (%d)",
+                pl.cands_per_query / pl.kc);
   size_t off = 0;
   pl.off_cand = off;
   off += align_up(size_t(nq) * pl.cands_per_query * sizeof(uint64_t), 256);
   pl.off_qbf16 = off;
   if (path == MRAG_PATH_TENSOR_BF16)
-    off += align_up(size_t(pl.k2.m_tiles) * 128 * s->dim * 2, 256);
+    off += align_up(size_t(pl.q_rows_padded) * s->dim * 2, 256);
+  pl.off_gthr = off;
+  if (path == MRAG_PATH_TENSOR_BF16) off += align_up(size_t(nq) * 4, 256);
   pl.total = off;
   *out = pl;
   return MRAG_OK;
@@ -288,20 +300,25 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
                         pl.k1_grid, st));
   } else {
     void* qb = ws + pl.off_qbf16;
-    const size_t qb_bytes = size_t(pl.k2.m_tiles) * 128 * s->dim * 2;
-    if (nq % 128 != 0) CK(cudaMemsetAsync(qb, 0, qb_bytes, st));
+    const size_t qb_bytes = size_t(pl.q_rows_padded) * s->dim * 2;
+    if (nq != pl.q_rows_padded) CK(cudaMemsetAsync(qb, 0, qb_bytes, st));
     CK(launch_cast_queries_bf16(queries_dev, qb, nq, s->dim, st));
     // rows beyond n_rows up to the 256-row tile edge are zero (store capacity is padded)
     const int64_t rows_padded = (s->n_rows + 255) / 256 * 256;
+    uint32_t* gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
+    CK(cudaMemsetAsync(gthr, 0, size_t(nq) * 4, st));
     if (before_scan) CK(cudaEventRecord(before_scan, st));
-    cudaError_t e = launch_k2_batch(qb, pl.k2.m_tiles * 128, s->rows_bf16, rows_padded, s->n_rows,
-                                    s->dim, nq, pl.k2, cand, st);
+    cudaError_t e = pl.k2_pair
+                        ? launch_k2_batch_pair(qb, pl.q_rows_padded, s->rows_bf16, rows_padded,
+                                               s->n_rows, s->dim, nq, pl.k2, cand, gthr, st)
+                        : launch_k2_batch(qb, pl.q_rows_padded, s->rows_bf16, rows_padded,
+                                          s->n_rows, s->dim, nq, pl.k2, cand, gthr, st);
     if (e != cudaSuccess) return cuda_fail(e, "launch_k2_batch");
   }
   if (after_scan) CK(cudaEventRecord(after_scan, st));
   const int32_t* groups = s->has_groups ? s->groups : nullptr;
   const int fm = (exclude_group_dev && groups) ? p->filter_mode : MRAG_FILTER_NONE;
-  CK(launch_k3_merge_rerank(cand, pl.cands_per_query, s->rows_f32, s->dim, queries_dev, nq, groups,
+  CK(launch_k3_merge_rerank(cand, pl.cands_per_query / pl.kc, pl.kc, s->rows_f32, s->dim, queries_dev, nq, groups,
                             exclude_group_dev, fm, p->metric, pl.rerank, p->k, p->index_base,
                             out_dist_dev, out_idx_dev, out_group_dev, st));
   return MRAG_OK;

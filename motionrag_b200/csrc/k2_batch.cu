@@ -19,24 +19,14 @@
 // fp32 from the master rows.
 //
 // Algorithmic flops: 2 * nq * n_rows * dim per launch.
-#include <cuda.h>
-
-#include "common.cuh"
-#include "kernels.h"
+#include "k2_common.cuh"
 
 namespace mrag {
 
-constexpr int kBM = 128;             // queries per tile (UMMA M)
-constexpr int kBN = 256;             // database rows per tile (UMMA N)
-constexpr int kBK = 64;              // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kUmmaK = 16;           // K per tcgen05.mma for 16-bit inputs
 constexpr int kStages = 4;
-constexpr int kK2Threads = 192;      // 6 warps
-constexpr int kEpiWarps = 4;
 constexpr uint32_t kABytes = kBM * kBK * 2;  // 16 KB
 constexpr uint32_t kBBytes = kBN * kBK * 2;  // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr uint32_t kTmemCols = 512;
 
 struct K2Smem {
   // offsets into the 1024-byte aligned dynamic shared memory window
@@ -44,14 +34,6 @@ struct K2Smem {
   static constexpr uint32_t kEpiStage = kStages * kStageBytes;               // 4 x 32 x 32 floats
   static constexpr uint32_t kBars = kEpiStage + kEpiWarps * 32 * 32 * 4;
   static constexpr uint32_t kTotal = kBars + 256;
-};
-
-struct K2Args {
-  int nq;
-  int dim;
-  int64_t n_rows;
-  int m_tiles, n_tiles, chunks, tiles_per_chunk;
-  uint64_t* cand;  // [nq][chunks][32]
 };
 
 __global__ void __launch_bounds__(kK2Threads, 1)
@@ -170,63 +152,18 @@ __global__ void __launch_bounds__(kK2Threads, 1)
       const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
       const int q_row = m * kBM + quarter * 32 + lane;
 
-      float ls[kK2Cand];
-      int li[kK2Cand];
-#pragma unroll
-      for (int i = 0; i < kK2Cand; ++i) {
-        ls[i] = -INFINITY;
-        li[i] = kInvalidIdx;
-      }
-      float thr = -INFINITY;
+      TopList top;
+      top.reset();
+      const bool live = q_row < a.nq;  // padding rows of the last query tile keep no state
+      uint32_t* gthr_q = a.gthr + (live ? q_row : 0);
 
       for (int t = t0; t < t1; ++t) {
+        if (live) top.refresh(gthr_q);
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
-        const int64_t row_base = int64_t(t) * kBN;
-        const bool ragged = row_base + kBN > a.n_rows;  // last tile: TMA zero-filled rows
         const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc) * kBN;
-#pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_addr + c * 32, v);
-          tmem_ld_wait();
-          const int col0 = int(row_base) + c * 32;
-          if (ragged) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (int64_t(col0) + j >= a.n_rows) v[j] = 0xff800000u;  // -inf
-          }
-          uint32_t hits = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) hits |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
-          if (__any_sync(0xffffffffu, hits != 0)) {
-            // rare path: park the 32 scores (column-major per lane, conflict-free) and let
-            // each thread walk its own hit mask
-#pragma unroll
-            for (int j = 0; j < 32; ++j) stg[j * 32 + lane] = __uint_as_float(v[j]);
-            while (hits) {
-              const int j = __ffs(hits) - 1;
-              hits &= hits - 1;
-              float cv = stg[j * 32 + lane];
-              if (cv > thr) {
-                int ci = col0 + j;
-                // bubble the new entry down a descending list; strict '>' keeps the earlier
-                // (lower) row index ahead on equal scores
-#pragma unroll
-                for (int i = 0; i < kK2Cand; ++i) {
-                  const bool sw = cv > ls[i];
-                  const float ts = ls[i];
-                  const int ti = li[i];
-                  ls[i] = sw ? cv : ts;
-                  li[i] = sw ? ci : ti;
-                  cv = sw ? ts : cv;
-                  ci = sw ? ti : ci;
-                }
-                thr = ls[kK2Cand - 1];
-              }
-            }
-          }
-        }
+        epilogue_tile(top, t_addr, int64_t(t) * kBN, a.n_rows, stg, lane, a.debug);
+        if (live) top.publish(gthr_q);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -234,11 +171,7 @@ __global__ void __launch_bounds__(kK2Threads, 1)
         if (acc == 0) acc_phase ^= 1;
       }
 
-      if (q_row < a.nq) {
-        uint64_t* dst = a.cand + (int64_t(q_row) * a.chunks + chunk) * kK2Cand;
-#pragma unroll
-        for (int i = 0; i < kK2Cand; ++i) dst[i] = make_sim_key(ls[i], li[i]);
-      }
+      if (live) top.store(a.cand + (int64_t(q_row) * a.chunks + chunk) * kK2Cand);
     }
   }
 
@@ -251,37 +184,6 @@ __global__ void __launch_bounds__(kK2Threads, 1)
 }
 
 // ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-      qres != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
-// [rows][dim] bf16 row-major; box = 64 elements x box_rows rows, 128-byte swizzle
-static bool make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int dim, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(rows)};
-  cuuint64_t gstride[1] = {cuuint64_t(dim) * 2};
-  cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 bool k2_supported(int dim) { return dim % kBK == 0 && dim >= kBK && dim <= 4096; }
 
 K2Plan k2_plan(int64_t n_rows, int nq, int sm_count) {
@@ -314,7 +216,8 @@ K2Plan k2_plan(int64_t n_rows, int nq, int sm_count) {
 
 cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* db_bf16,
                             int64_t db_rows_padded, int64_t n_rows, int dim, int nq,
-                            const K2Plan& plan, uint64_t* cand, cudaStream_t st) {
+                            const K2Plan& plan, uint64_t* cand, uint32_t* gthr,
+                            cudaStream_t st) {
   CUtensorMap tm_q, tm_db;
   if (!make_tmap(&tm_q, q_bf16, q_rows_padded, dim, kBM) ||
       !make_tmap(&tm_db, db_bf16, db_rows_padded, dim, kBN))
@@ -328,6 +231,8 @@ cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* d
   a.chunks = plan.chunks;
   a.tiles_per_chunk = plan.tiles_per_chunk;
   a.cand = cand;
+  a.gthr = gthr;
+  a.debug = k2_debug_mode();
   const size_t smem = K2Smem::kTotal + 1024;
   cudaError_t e = cudaFuncSetAttribute(k2_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        int(smem));

@@ -138,35 +138,77 @@ __device__ __forceinline__ void emit_filtered(EntryFn entry, int n_sorted, int k
 }
 
 // ---- K3 -------------------------------------------------------------------------------------
+// Candidates arrive as `n_runs` runs of `run_len` keys, each run sorted best-first (one run per
+// K1 CTA / K2 chunk). A full sort of up to 16 K keys is shared-memory-bandwidth bound (~80 us on
+// one SM), so selection is done on the run heads instead: with R = rerank, the R-th best key
+// overall can be no worse than T = the R-th best run head, hence only keys <= T (in key order)
+// can matter, and they all live in the (exactly R, keys are unique) runs whose head is <= T.
+// Sort 512 heads -> T -> compact the qualifying keys (<= R * run_len <= 2048) -> sort those.
 constexpr int kMaxRerank = 64;
+constexpr int kMaxRuns = 512;
+constexpr int kMaxSel = 2048;
+constexpr int kK3Threads = 512;
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-    k3_merge_rerank_kernel(const uint64_t* __restrict__ cand, int cands_per_query, int padded,
+__global__ void __launch_bounds__(kK3Threads)
+    k3_merge_rerank_kernel(const uint64_t* __restrict__ cand, int n_runs, int run_len,
                            const float* __restrict__ db, int dim, const float* __restrict__ queries,
                            const int32_t* __restrict__ row_group,
                            const int32_t* __restrict__ exclude_group, int filter_mode, int metric,
                            int rerank, int k, int64_t index_base, float* __restrict__ out_dist,
                            int64_t* __restrict__ out_idx, int32_t* __restrict__ out_group) {
-  extern __shared__ __align__(16) uint64_t keys[];  // [padded]
-  __shared__ uint64_t rr_keys[kMaxRerank];          // (ordered distance << 32) | local row
+  __shared__ uint64_t heads[kMaxRuns];      // run heads, unsorted (index = run)
+  __shared__ uint64_t sorted_heads[kMaxRuns];
+  __shared__ uint64_t sel[kMaxSel];
+  __shared__ uint64_t rr_keys[kMaxRerank];  // (ordered distance << 32) | local row
+  __shared__ int n_sel_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = blockIdx.x;
+  const uint64_t* src = cand + int64_t(q) * n_runs * run_len;
 
-  const uint64_t* src = cand + int64_t(q) * cands_per_query;
-  for (int i = tid; i < padded; i += THREADS) keys[i] = (i < cands_per_query) ? src[i] : kEmptyKey;
-  bitonic_sort_smem(keys, padded, tid, THREADS);
+  int heads_pad = 64;
+  while (heads_pad < n_runs) heads_pad <<= 1;
+  for (int r = tid; r < heads_pad; r += kK3Threads) {
+    const uint64_t h = (r < n_runs) ? src[int64_t(r) * run_len] : kEmptyKey;
+    heads[r] = h;
+    sorted_heads[r] = h;
+  }
+  if (tid == 0) n_sel_s = 0;
+  if (tid < kMaxRerank) rr_keys[tid] = kEmptyKey;
+  uint64_t T = kEmptyKey;  // select everything unless there are more runs than needed
+  if (n_runs > rerank) {
+    bitonic_sort_smem(sorted_heads, heads_pad, tid, kK3Threads);
+    T = sorted_heads[rerank - 1];
+  } else {
+    __syncthreads();
+  }
+  // compact keys <= T from qualifying runs: one warp per run, lane = position in the run
+  for (int r = warp; r < n_runs; r += kK3Threads / 32) {
+    if (heads[r] > T) continue;  // warp-uniform
+    const uint64_t key = (lane < run_len) ? src[int64_t(r) * run_len + lane] : kEmptyKey;
+    const bool take = (key <= T) && (uint32_t(key) < uint32_t(kInvalidIdx));
+    const uint32_t m = __ballot_sync(0xffffffffu, take);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(&n_sel_s, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) {
+      const int pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < kMaxSel) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  const int n_sel = min(n_sel_s, kMaxSel);
+  int sel_pad = 64;
+  while (sel_pad < n_sel) sel_pad <<= 1;
+  for (int i = n_sel + tid; i < sel_pad; i += kK3Threads) sel[i] = kEmptyKey;
+  bitonic_sort_smem(sel, sel_pad, tid, kK3Threads);
 
   // exact fp32 distances for the best `rerank` candidates: one warp per candidate
   const float4* qv = reinterpret_cast<const float4*>(queries + int64_t(q) * dim);
   const int nv = dim >> 2;
-  if (tid < kMaxRerank) rr_keys[tid] = kEmptyKey;
-  __syncthreads();
-  const int n_rr = min(rerank, min(padded, kMaxRerank));
-  for (int c = warp; c < n_rr; c += THREADS / 32) {
-    const uint64_t key = keys[c];
+  const int n_rr = min(rerank, min(n_sel, kMaxRerank));
+  for (int c = warp; c < n_rr; c += kK3Threads / 32) {
+    const uint64_t key = sel[c];
     const uint32_t idx = uint32_t(key);
-    if (idx >= uint32_t(kInvalidIdx)) continue;  // empty slot (warp-uniform)
     const float4* dv = reinterpret_cast<const float4*>(db + int64_t(idx) * dim);
     float l2 = 0.f, dot = 0.f, qq = 0.f, dd = 0.f;
     for (int i = lane; i < nv; i += 32) {
@@ -197,7 +239,7 @@ __global__ void __launch_bounds__(THREADS)
     else dist = 1.f - dot;
     if (lane == 0) rr_keys[c] = (uint64_t(f32_to_ordered(dist)) << 32) | idx;
   }
-  bitonic_sort_smem(rr_keys, kMaxRerank, tid, THREADS);
+  bitonic_sort_smem(rr_keys, kMaxRerank, tid, kK3Threads);
 
   if (warp == 0) {
     const int exclude = (exclude_group != nullptr) ? exclude_group[q] : -1;
@@ -224,28 +266,19 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
-cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int cands_per_query, const float* db_f32,
-                                   int dim, const float* queries, int nq,
+cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len,
+                                   const float* db_f32, int dim, const float* queries, int nq,
                                    const int32_t* row_group, const int32_t* exclude_group,
                                    int filter_mode, int metric, int rerank, int k,
                                    int64_t index_base, float* out_dist, int64_t* out_idx,
                                    int32_t* out_group, cudaStream_t st) {
-  int padded = 64;
-  while (padded < cands_per_query) padded <<= 1;
-  if (padded > 16384) return cudaErrorInvalidValue;
-  const size_t smem = size_t(padded) * sizeof(uint64_t);
-  if (padded > 2048) {
-    auto kern = k3_merge_rerank_kernel<1024>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
-    if (e != cudaSuccess) return e;
-    kern<<<nq, 1024, smem, st>>>(cand, cands_per_query, padded, db_f32, dim, queries, row_group,
-                                 exclude_group, filter_mode, metric, rerank, k, index_base,
-                                 out_dist, out_idx, out_group);
-  } else {
-    k3_merge_rerank_kernel<256><<<nq, 256, smem, st>>>(
-        cand, cands_per_query, padded, db_f32, dim, queries, row_group, exclude_group, filter_mode,
-        metric, rerank, k, index_base, out_dist, out_idx, out_group);
-  }
+  if (n_runs < 1 || n_runs > kMaxRuns || run_len < 1 || run_len > 32 || rerank < 1 ||
+      rerank > kMaxRerank || int64_t(rerank) * run_len > kMaxSel)
+    return cudaErrorInvalidValue;
+  k3_merge_rerank_kernel<<<nq, kK3Threads, 0, st>>>(cand, n_runs, run_len, db_f32, dim, queries,
+                                                    row_group, exclude_group, filter_mode, metric,
+                                                    rerank, k, index_base, out_dist, out_idx,
+                                                    out_group);
   note_launch();
   return cudaGetLastError();
 }

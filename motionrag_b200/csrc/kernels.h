@@ -36,13 +36,20 @@ constexpr int kK2Cand = 32;  // candidates kept per (query, chunk)
 bool k2_supported(int dim);
 K2Plan k2_plan(int64_t n_rows, int nq, int sm_count);
 // q_bf16 [q_rows_padded][dim] (rows >= nq zero), db_bf16 [db_rows_padded][dim] (rows >= n_rows
-// zero), both padded to whole tiles; cand [nq][chunks][32] u64 keys
+// zero), both padded to whole tiles; cand [nq][chunks][32] u64 keys; gthr [nq] u32 zeroed
 cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* db_bf16,
                             int64_t db_rows_padded, int64_t n_rows, int dim, int nq,
-                            const K2Plan& plan, uint64_t* cand, cudaStream_t st);
+                            const K2Plan& plan, uint64_t* cand, uint32_t* gthr, cudaStream_t st);
+
+// CTA-pair (cta_group::2) form of K2 for nq > 128: q_rows_padded must cover whole 256-row pairs
+K2Plan k2_plan_pair(int64_t n_rows, int nq, int sm_count);
+cudaError_t launch_k2_batch_pair(const void* q_bf16, int q_rows_padded, const void* db_bf16,
+                                 int64_t db_rows_padded, int64_t n_rows, int dim, int nq,
+                                 const K2Plan& plan, uint64_t* cand, uint32_t* gthr, cudaStream_t st);
 
 // K3: candidate merge + exact fp32 re-score + filter --------------------------------------
-cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int cands_per_query,
+// cand: per query n_runs runs of run_len keys, each run sorted best-first
+cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len,
                                    const float* db_f32, int dim, const float* queries, int nq,
                                    const int32_t* row_group, const int32_t* exclude_group,
                                    int filter_mode, int metric, int rerank, int k,

@@ -97,6 +97,9 @@ class ShardedRetriever:
                filter_mode: str = "post") -> SearchResult:
         """Same contract as EmbeddingStore.search, over the union of all shards. Every rank
         passes the same queries and gets the same (global-index) result."""
+        if self.world == 1:   # one shard: the local search already is the answer (no exchange)
+            return self._local_search(queries, k, metric, path, refine, exclude_group,
+                                      filter_mode if exclude_group is not None else "none", 0, None)
         nq = queries.shape[0]
         lay = PackedLayout(nq, k)
         key = (nq, k)
@@ -111,10 +114,7 @@ class ShardedRetriever:
         self._local_search(queries, k, metric, path, refine,
                            exclude_group if local_filter == "pre" else None, local_filter,
                            self.rank * self.rows_per_shard, local)
-        if self.world == 1:
-            recv = send
-        else:
-            dist.all_gather_into_tensor(recv, send, group=self.group)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
         dv, gv, iv = lay.views(recv, self.world)
         return self._merge(dv, iv, gv, k, exclude_group,
                            filter_mode if exclude_group is not None else "none", lay.nbytes)

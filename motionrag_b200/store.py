@@ -68,7 +68,10 @@ class EmbeddingStore:
     def append(self, rows: torch.Tensor | np.ndarray, normalise: bool = True) -> None:
         """Append fp32 rows [n, dim] from host (numpy / CPU tensor) or device memory."""
         if isinstance(rows, np.ndarray):
-            rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32))
+            rows = np.ascontiguousarray(rows, dtype=np.float32)
+            if not rows.flags.writeable:   # e.g. a read-only np.load(mmap_mode="r") slice
+                rows = rows.copy()
+            rows = torch.from_numpy(rows)
         rows = rows.to(torch.float32).contiguous()
         if rows.ndim != 2 or rows.shape[1] != self.dim:
             raise ValueError(f"rows must be [n, {self.dim}], got {tuple(rows.shape)}")

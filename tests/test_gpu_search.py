@@ -64,6 +64,17 @@ def test_tensor_bf16_matches_oracle(case, nq, k):
     _run(case, nq, k, "tensor_bf16")
 
 
+@pytest.mark.parametrize("nq,k", [(129, 12), (200, 12), (256, 5), (300, 32)])
+def test_tensor_single_cta_kernel_on_multi_tile_batches(case, nq, k, monkeypatch):
+    """nq > 128 defaults to the CTA-pair kernel; MRAG_K2_SINGLE=1 keeps the single-CTA one covered."""
+    nq = min(nq, case["q"].shape[0])
+    monkeypatch.setenv("MRAG_K2_SINGLE", "1")
+    assert case["store"].plan(nq, k=k).grid % 2 == 1 or case["store"].plan(nq, k=k).grid <= 148
+    _run(case, nq, k, "tensor_bf16")
+    monkeypatch.delenv("MRAG_K2_SINGLE")
+    _run(case, nq, k, "tensor_bf16")
+
+
 @pytest.mark.parametrize("path,nq", [("stream_f32", 4), ("stream_bf16", 3), ("tensor_bf16", 64)])
 @pytest.mark.parametrize("metric", ["cosine", "dot"])
 def test_metrics(case, path, nq, metric):

@@ -39,6 +39,15 @@ WORKLOADS = {
 POOL = 16  # distinct query batches cycled through the steps
 
 
+def ncu_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (or None)."""
+    f = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(f.read_text()).get(workload, {}).get("traffic_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -218,7 +227,8 @@ def run_ours(args):
             ach = plan.scan_flops / (scan_ms / 1e3) / 1e12
             peak = pk["bf16_tflops_sustained"] if steps * scan_ms > 2000 else pk["bf16_tflops"]
             out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                               "frac": ach / peak, "traffic": None, "kernel": "k2_batch_kernel",
+                               "frac": ach / peak, "traffic": ncu_traffic(name) if world == 1 else None,
+                               "kernel": "k2_batch2_kernel" if nq > 128 else "k2_batch_kernel",
                                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / (ms_total / steps),
                                "peak_source": pk["source"],
                                "plan": {"grid": plan.grid, "m_tiles": plan.m_tiles, "n_tiles": plan.n_tiles,
@@ -226,7 +236,8 @@ def run_ours(args):
         else:
             ach = plan.scan_bytes / (scan_ms / 1e3) / 1e9
             out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                               "frac": ach / pk["hbm_gbs"], "traffic": None, "kernel": "k1_stream_kernel<float>",
+                               "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(name) if world == 1 else None,
+                               "kernel": "k1_stream_kernel<float>",
                                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / (ms_total / steps),
                                "peak_source": pk["source"], "bytes_per_launch": plan.scan_bytes,
                                "plan": {"grid": plan.grid, "cands_per_query": plan.cands_per_query}}

@@ -7,7 +7,8 @@ top (`RAGDatabase`, src/data/rag.py; the ActionTransformer context contract,
 src/projects/condition/module.py:298-301). No CPU fallback exists anywhere in this package.
 """
 from ._cabi import MragError, launch_count  # noqa: F401
-from .context import MotionContext, attach, block_causal_mask, gather_context, sinusoid_table  # noqa: F401
+from .context import (MotionContext, attach, block_causal_mask, gather_context, select_refs,  # noqa: F401
+                      sinusoid_table)
 from .parallel import ShardedRetriever, alloc_feature_block, open_peer_tables, shard_range  # noqa: F401
 from .rag import RAGDatabase, save_table  # noqa: F401
 from .store import EmbeddingStore, FeatureTable, SearchResult, merge_topk  # noqa: F401

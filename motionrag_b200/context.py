@@ -90,6 +90,33 @@ def gather_context(table: FeatureTable, ref_index: torch.Tensor, sos: torch.Tens
     return out
 
 
+def select_refs(index: torch.Tensor, distance: torch.Tensor, ref_video_num: int,
+                uncond_video_ratio: float = 0.0, generator: torch.Generator | None = None):
+    """The per-sample reference selection of VideoDataset.get_ref_videos
+    (src/data/dataset.py:285-312) on retrieval results instead of decoded clips:
+    keep the first `ref_video_num` hits (`ref_videos[:K]`, :296), drop each one with probability
+    `uncond_video_ratio` (`random.random() > ratio` keeps, :297) — a dropped or missing slot
+    becomes index -1 (the all-zero clip -> uncond row) with `_distance` 1.0 (:305-310).
+
+    index / distance: [b, k>=K] from a search (unused slots -1 / inf). Returns
+    (ref_index int64 [b, K], ref_distance float32 [b, K])."""
+    K = int(ref_video_num)
+    idx = index[:, :K].clone()
+    dist = distance[:, :K].clone().to(torch.float32)
+    if idx.shape[1] < K:   # fewer results than slots: the reference leaves zeros there
+        pad = K - idx.shape[1]
+        idx = torch.cat([idx, idx.new_full((idx.shape[0], pad), -1)], 1)
+        dist = torch.cat([dist, dist.new_full((dist.shape[0], pad), 1.0)], 1)
+    drop = idx < 0
+    if uncond_video_ratio > 0:
+        gdev = generator.device if generator is not None else idx.device
+        u = torch.rand(idx.shape, generator=generator, device=gdev).to(idx.device)
+        drop = drop | ~(u > uncond_video_ratio)
+    idx = torch.where(drop, torch.full_like(idx, -1), idx)
+    dist = torch.where(drop, torch.ones_like(dist), dist)
+    return idx.contiguous(), dist.contiguous()
+
+
 class MotionContext:
     """Holds what the gather needs besides the table: SOS block, uncond row, position table."""
 

@@ -110,20 +110,24 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
   } else if (path == MRAG_PATH_TENSOR_BF16) {
     if (!k2_supported(s->dim))
       return fail(MRAG_ERR_UNSUPPORTED, "tensor path needs dim %% 64 == 0 (dim=%d)", s->dim);
-    pl.kc = kK2Cand;
-    // the shared per-query bound guarantees the global top-32 by bf16 score, not more
-    pl.rerank = refine > kK2Cand ? kK2Cand : refine;
+    // per-run list length: 16 entries when k <= 12 (the reference asks for K+3 = 12), else 32.
+    // The shared per-query bound guarantees the global top-KC by bf16 score, not more, so the
+    // fp32 re-rank covers at most KC candidates. MRAG_K2_KC=32 forces the long list.
+    const char* kc_env = getenv("MRAG_K2_KC");
+    pl.kc = (p->k <= 12 && p->filter_mode != MRAG_FILTER_PRE && !(kc_env && atoi(kc_env) == 32)) ? 16 : 32;
+    pl.rerank = refine > pl.kc ? pl.kc : refine;
     // more than one query tile: the CTA-pair kernel (M = 256 per cluster); MRAG_K2_SINGLE=1
     // forces the single-CTA kernel for A/B measurements
     const char* force = getenv("MRAG_K2_SINGLE");
     pl.k2_pair = nq > 128 && !(force && force[0] == '1');
     pl.k2 = pl.k2_pair ? k2_plan_pair(s->n_rows, nq, s->sm_count) : k2_plan(s->n_rows, nq, s->sm_count);
     pl.q_rows_padded = pl.k2_pair ? ((pl.k2.m_tiles + 1) / 2) * 256 : pl.k2.m_tiles * 128;
-    pl.cands_per_query = pl.k2.chunks * kK2Cand;
+    pl.k2.kc = pl.kc;
+    pl.cands_per_query = pl.k2.chunks * pl.k2.epi_sets * pl.kc;
   } else {
     return fail(MRAG_ERR_ARG, "unknown path %d", p->path);
   }
-  if (pl.cands_per_query / pl.kc > 512)
+  if (pl.cands_per_query / pl.kc > 1024)
     return fail(MRAG_ERR_UNSUPPORTED, "too many candidate runs per query (%d)",
                 pl.cands_per_query / pl.kc);
   size_t off = 0;

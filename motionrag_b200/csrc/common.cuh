@@ -210,7 +210,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t target_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(target_rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  // relaxed: the only data handed over is TMEM contents, ordered by tcgen05.fence::before_thread_sync;
+  // a release at cluster scope would drain this thread's outstanding memory traffic (~1300 cycles)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // TMA load issued by either CTA of a pair; completion bytes are credited to the mbarrier of the
 // even (leader) CTA: clearing bit 24 of the shared::cluster address selects the pair's CTA 0

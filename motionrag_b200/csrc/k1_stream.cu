@@ -9,6 +9,8 @@
 // sort and written as u64 keys (score descending, index ascending); K3 finishes the job.
 //
 // Algorithmic bytes: n_rows * dim * sizeof(T) per launch (T = float or bf16).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -184,24 +186,50 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
 }
 
 // ---- host side ------------------------------------------------------------------------------
-template <typename T, int D, int Q>
-struct K1Cfg {
-  // rows in flight per warp: 2 x 3 KB (fp32) / 4 x 1.5 KB (bf16)
-  static constexpr int R = (sizeof(T) == 4) ? 2 : 4;
-  static constexpr int MINB = 3;
+// (rows in flight per warp, resident CTAs per SM). Variant 0 is the shipped configuration;
+// MRAG_K1_VARIANT selects the others for tuning runs.
+struct K1Variant {
+  int r, minb;
 };
+static const K1Variant kVariantsF32[] = {{2, 2}, {4, 2}, {2, 3}, {2, 4}, {1, 4}, {3, 2}};
+static const K1Variant kVariantsBF16[] = {{4, 3}, {8, 2}, {4, 2}, {4, 4}, {2, 4}, {6, 2}};
+
+static int k1_variant_index() {
+  const char* e = getenv("MRAG_K1_VARIANT");
+  int v = e ? atoi(e) : 0;
+  return (v < 0 || v > 5) ? 0 : v;
+}
+static K1Variant k1_variant(int elt_bytes) {
+  return elt_bytes == 4 ? kVariantsF32[k1_variant_index()] : kVariantsBF16[k1_variant_index()];
+}
+
+template <typename T, int D, int Q, int R, int MINB>
+static cudaError_t launch_cfg(const void* db, int64_t n_rows, const float* queries, uint64_t* cand,
+                              int kc, int grid, cudaStream_t st) {
+  const int64_t quantum = int64_t(kK1Warps) * R;
+  int64_t rows_per_cta = (n_rows + grid - 1) / grid;
+  rows_per_cta = (rows_per_cta + quantum - 1) / quantum * quantum;
+  k1_stream_kernel<T, D, Q, R, MINB><<<grid, kK1Threads, 0, st>>>(
+      static_cast<const T*>(db), n_rows, queries, cand, kc, rows_per_cta);
+  note_launch();
+  return cudaGetLastError();
+}
 
 template <typename T, int D, int Q>
 static cudaError_t launch_one(const void* db, int64_t n_rows, const float* queries, uint64_t* cand,
                               int kc, int grid, cudaStream_t st) {
-  using C = K1Cfg<T, D, Q>;
-  const int64_t quantum = int64_t(kK1Warps) * C::R;
-  int64_t rows_per_cta = (n_rows + grid - 1) / grid;
-  rows_per_cta = (rows_per_cta + quantum - 1) / quantum * quantum;
-  k1_stream_kernel<T, D, Q, C::R, C::MINB><<<grid, kK1Threads, 0, st>>>(
-      static_cast<const T*>(db), n_rows, queries, cand, kc, rows_per_cta);
-  note_launch();
-  return cudaGetLastError();
+  constexpr bool F = sizeof(T) == 4;
+  if constexpr (D == 768 && Q == 1) {  // tuning variants exist for the headline shape only
+    switch (k1_variant_index()) {
+      case 1: return launch_cfg<T, D, Q, F ? 4 : 8, 2>(db, n_rows, queries, cand, kc, grid, st);
+      case 2: return launch_cfg<T, D, Q, F ? 2 : 4, F ? 3 : 2>(db, n_rows, queries, cand, kc, grid, st);
+      case 3: return launch_cfg<T, D, Q, F ? 2 : 4, 4>(db, n_rows, queries, cand, kc, grid, st);
+      case 4: return launch_cfg<T, D, Q, F ? 1 : 2, 4>(db, n_rows, queries, cand, kc, grid, st);
+      case 5: return launch_cfg<T, D, Q, F ? 3 : 6, 2>(db, n_rows, queries, cand, kc, grid, st);
+      default: break;
+    }
+  }
+  return launch_cfg<T, D, Q, F ? 2 : 4, F ? 2 : 3>(db, n_rows, queries, cand, kc, grid, st);
 }
 
 template <typename T, int D>
@@ -233,13 +261,12 @@ bool k1_supported(int dim, int nq) {
 }
 
 int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count) {
-  (void)dim;
-  (void)nq;
-  const int r = (elt_bytes == 4) ? 2 : 4;
-  const int64_t quantum = int64_t(kK1Warps) * r;
-  // one resident wave: 3 CTAs per SM (see K1Cfg::MINB); small tables get fewer CTAs
+  K1Variant v = (dim == 768 && nq == 1) ? k1_variant(elt_bytes)
+                                        : (elt_bytes == 4 ? kVariantsF32[0] : kVariantsBF16[0]);
+  const int64_t quantum = int64_t(kK1Warps) * v.r;
+  // one resident wave; small tables get fewer CTAs
   int64_t want = (n_rows + quantum - 1) / quantum;
-  int64_t cap = int64_t(sm_count) * 3;
+  int64_t cap = int64_t(sm_count) * v.minb;
   return int(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 

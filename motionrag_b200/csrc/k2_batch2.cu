@@ -24,11 +24,12 @@ constexpr uint32_t kStageBytes2 = kABytes2 + kBBytes2;
 struct K2Smem2 {
   static constexpr uint32_t kTiles = 0;
   static constexpr uint32_t kEpiStage = kStages2 * kStageBytes2;
-  static constexpr uint32_t kBars = kEpiStage + kEpiWarps * 32 * 32 * 4;
+  static constexpr uint32_t kBars = kEpiStage + 2 * kEpiWarps * 32 * 32 * 4;
   static constexpr uint32_t kTotal = kBars + 256;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kK2Threads, 1)
+template <int SETS, int KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(SETS), 1)
     k2_batch2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                      const K2Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -42,6 +43,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kK2Threads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t_start = clk();
+  long long w_a = 0, w_b = 0, busy = 0, served = 0;  // role-specific wait / work counters
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -81,9 +84,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kK2Threads, 1)
         const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
         const int q_row0 = (mp * 2 + int(cta_rank)) * kBM;
         for (int t = t0; t < t1; ++t) {
+          ++served;
           const int db_row0 = t * kBN + int(cta_rank) * (kBN / 2);
           for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_timed(&empty_bar[stage], phase ^ 1, w_a);
             uint8_t* sa = smem + K2Smem2::kTiles + stage * kStageBytes2;
             uint8_t* sb = sa + kABytes2;
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes2);
@@ -110,11 +114,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kK2Threads, 1)
         const int t0 = chunk * a.tiles_per_chunk;
         const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, w_b);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc) * kBN;
           for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
+            mbar_wait_timed(&full_bar[stage], phase, w_a);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + K2Smem2::kTiles + stage * kStageBytes2);
             const uint64_t da = umma_desc_k_sw128(sa);
@@ -137,38 +141,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kK2Threads, 1)
     }
   } else {
     // ================= epilogue (both CTAs, own 128 query rows) =================
-    const int quarter = warp & 3;
-    const int ew = warp - 2;
-    float* stg = reinterpret_cast<float*>(smem + K2Smem2::kEpiStage) + ew * 32 * 32;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may read
+    const int set = (warp - 2) >> 2;   // which accumulator buffer (tile parity) this warp serves
+    float* stg = reinterpret_cast<float*>(smem + K2Smem2::kEpiStage) + (warp - 2) * 32 * 32;
+    uint32_t n = 0;                    // running tile count of this CTA, same in every role
+    uint32_t ph0 = 0u, ph1 = 0u;
     for (int item = pair_id; item < total_items; item += n_pairs) {
       const int mp = item % m_pairs, chunk = item / m_pairs;
       const int t0 = chunk * a.tiles_per_chunk;
       const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
       const int q_row = (mp * 2 + int(cta_rank)) * kBM + quarter * 32 + lane;
 
-      TopList top;
+      TopList<KC> top;
       top.reset();
       const bool live = q_row < a.nq;  // padding rows of the last query tile keep no state
       uint32_t* gthr_q = a.gthr + (live ? q_row : 0);
-      for (int t = t0; t < t1; ++t) {
+      for (int t = t0; t < t1; ++t, ++n) {
+        const int acc = int(n & 1u);
+        if (SETS == 2 && acc != set) continue;
         if (live) top.refresh(gthr_q);
-        mbar_wait(&tfull_bar[acc], acc_phase);
+        mbar_wait_timed(&tfull_bar[acc], acc ? ph1 : ph0, w_a);
         tc_fence_after();
+        const long long t_busy = clk();
         const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc) * kBN;
-        epilogue_tile(top, t_addr, int64_t(t) * kBN, a.n_rows, stg, lane, a.debug);
+        epilogue_tile<SETS == 1, KC>(top, t_addr, int64_t(t) * kBN, a.n_rows, stg, lane, a.debug);
         if (live) top.publish(gthr_q);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (acc) ph1 ^= 1; else ph0 ^= 1;
+        busy += clk() - t_busy;
+        ++served;
       }
-      if (live) top.store(a.cand + (int64_t(q_row) * a.chunks + chunk) * kK2Cand);
+      if (live) top.store(a.cand + ((int64_t(q_row) * a.chunks + chunk) * SETS + set) * KC);
     }
   }
 
+  if (a.stats != nullptr && lane == 0) {
+    unsigned long long* st = a.stats + size_t(blockIdx.x) * 8;
+    if (warp == 0) {
+      st[6] = (unsigned long long)served;
+      st[0] = (unsigned long long)(clk() - t_start);
+      st[1] = (unsigned long long)w_a;
+    } else if (warp == 1) {
+      st[2] = (unsigned long long)w_a;
+      st[3] = (unsigned long long)w_b;
+    } else if (warp == 2) {
+      st[4] = (unsigned long long)w_a;
+      st[5] = (unsigned long long)busy;
+      st[7] = (unsigned long long)served;
+    }
+  }
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();  // nobody leaves while the pair's MMAs / remote arrives may still land
@@ -202,6 +225,7 @@ K2Plan k2_plan_pair(int64_t n_rows, int nq, int sm_count) {
   p.tiles_per_chunk = (p.n_tiles + best - 1) / best;
   const int64_t items = int64_t(m_pairs) * p.chunks;
   p.grid = 2 * int(items < pairs ? items : pairs);
+  p.epi_sets = k2_epi_sets();
   return p;
 }
 
@@ -224,13 +248,22 @@ cudaError_t launch_k2_batch_pair(const void* q_bf16, int q_rows_padded, const vo
   a.cand = cand;
   a.gthr = gthr;
   a.debug = k2_debug_mode();
+  a.stats = k2_stats_alloc(plan.grid);
   const size_t smem = K2Smem2::kTotal + 1024;
-  cudaError_t e = cudaFuncSetAttribute(k2_batch2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(smem));
+  cudaError_t e = cudaErrorInvalidValue;
+  auto go = [&](auto kern, int threads) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess) kern<<<plan.grid, threads, smem, st>>>(tm_q, tm_db, a);
+  };
+  if (plan.epi_sets == 2 && plan.kc == 16) go(k2_batch2_kernel<2, 16>, k2_threads(2));
+  else if (plan.epi_sets == 2) go(k2_batch2_kernel<2, 32>, k2_threads(2));
+  else if (plan.kc == 16) go(k2_batch2_kernel<1, 16>, k2_threads(1));
+  else go(k2_batch2_kernel<1, 32>, k2_threads(1));
   if (e != cudaSuccess) return e;
-  k2_batch2_kernel<<<plan.grid, kK2Threads, smem, st>>>(tm_q, tm_db, a);
   note_launch();
-  return cudaGetLastError();
+  cudaError_t le = cudaGetLastError();
+  k2_stats_report(a.stats, plan.grid, st, "pair");
+  return le;
 }
 
 }  // namespace mrag

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -13,8 +14,10 @@ constexpr int kBM = 128;     // queries per CTA tile (UMMA M per CTA)
 constexpr int kBN = 256;     // database rows per tile (UMMA N)
 constexpr int kBK = 64;      // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;   // K per tcgen05.mma for 16-bit inputs
-constexpr int kK2Threads = 192;  // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+// warp 0 TMA, warp 1 MMA, then SETS x 4 epilogue warps (one warp per TMEM lane quarter). With
+// SETS = 2 the sets alternate tiles (set s serves accumulator s) and keep their own top lists.
 constexpr int kEpiWarps = 4;
+constexpr int k2_threads(int sets) { return 64 + 128 * sets; }
 constexpr uint32_t kTmemCols = 512;  // two 128 x 256 fp32 accumulators
 
 struct K2Args {
@@ -22,26 +25,31 @@ struct K2Args {
   int dim;
   int64_t n_rows;
   int m_tiles, n_tiles, chunks, tiles_per_chunk;
-  uint64_t* cand;  // [nq][chunks][32]
+  uint64_t* cand;  // [nq][chunks][SETS][KC]
   // [nq] running lower bound of each query's global 32nd-best score (ordered-uint encoding,
-  // zero-initialised), shared by every CTA / chunk working on that query: a CTA's local 32nd
-  // best is such a bound, so scores below it can never reach the global top-32 and are
+  // zero-initialised), shared by every CTA / chunk working on that query: a CTA's local KC-th
+  // best is such a bound, so scores below it can never reach the global top-KC and are
   // dropped before the insertion path. Makes the epilogue's insert count ~ln(N) per query
   // instead of ~chunks * ln(N / chunks).
   uint32_t* gthr;
+  // profiling only (MRAG_K2_STATS=1): per CTA {total, producer wait-empty, mma wait-full,
+  // mma wait-tmem-empty, epilogue wait-tmem-full, epilogue busy, tiles} in SM cycles (epilogue
+  // numbers are from the first epilogue warp)
+  unsigned long long* stats;
   int debug;  // profiling only (MRAG_K2_DEBUG): 1 = epilogue skips TMEM reads, 2 = reads but never inserts
 };
 
-// running top-32 of one query row, sorted descending, held in registers
+// running top-KC of one query row, sorted descending, held in registers
+template <int KC>
 struct TopList {
-  float ls[kK2Cand];
-  int li[kK2Cand];
+  float ls[KC];
+  int li[KC];
   float thr;        // max(local 32nd best, global bound): scores must beat it to be inserted
   float gbound;     // last global bound read
   float published;  // last local 32nd best pushed to the global bound
   __device__ __forceinline__ void reset() {
 #pragma unroll
-    for (int i = 0; i < kK2Cand; ++i) {
+    for (int i = 0; i < KC; ++i) {
       ls[i] = -INFINITY;
       li[i] = kInvalidIdx;
     }
@@ -61,7 +69,7 @@ struct TopList {
     }
   }
   __device__ __forceinline__ void publish(uint32_t* gthr_q) {
-    const float mine = ls[kK2Cand - 1];
+    const float mine = ls[KC - 1];
     if (mine > published) {
       published = mine;
       atomicMax(gthr_q, f32_to_ordered(mine));
@@ -70,7 +78,7 @@ struct TopList {
   // bubble a new entry down the list; strict '>' keeps the earlier (lower) row ahead on ties
   __device__ __forceinline__ void insert(float cv, int ci) {
 #pragma unroll
-    for (int i = 0; i < kK2Cand; ++i) {
+    for (int i = 0; i < KC; ++i) {
       const bool sw = cv > ls[i];
       const float ts = ls[i];
       const int ti = li[i];
@@ -79,47 +87,79 @@ struct TopList {
       cv = sw ? ts : cv;
       ci = sw ? ti : ci;
     }
-    thr = fmaxf(ls[kK2Cand - 1], gbound);
+    thr = fmaxf(ls[KC - 1], gbound);
   }
   __device__ __forceinline__ void store(uint64_t* dst) const {
 #pragma unroll
-    for (int i = 0; i < kK2Cand; ++i) dst[i] = make_sim_key(ls[i], li[i]);
+    for (int i = 0; i < KC; ++i) dst[i] = make_sim_key(ls[i], li[i]);
   }
 };
 
+// 32 scores of one query row (32 consecutive database rows starting at col0).
+// Fast path: one max-tree + one compare rejects the whole group (the common case once the
+// threshold is warm). Slow path, only for lanes that have a candidate: park the scores in this
+// warp's scratch (column-major per lane, conflict-free) and walk the hit mask.
+template <int KC>
+__device__ __forceinline__ void process_group(TopList<KC>& top, const uint32_t (&v)[32], int col0,
+                                              bool ragged, int64_t n_rows, float* stg, int lane) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    f[j] = __uint_as_float(v[j]);
+    if (ragged && int64_t(col0) + j >= n_rows) f[j] = -INFINITY;  // rows past the table
+  }
+  float m[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) m[j] = fmaxf(f[j], f[j + 16]);
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
+  if (m[0] > top.thr) {
+    uint32_t hits = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      stg[j * 32 + lane] = f[j];
+      hits |= (f[j] > top.thr) ? (1u << j) : 0u;
+    }
+    while (hits) {
+      const int j = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const float cv = stg[j * 32 + lane];
+      if (cv > top.thr) top.insert(cv, col0 + j);
+    }
+  }
+}
+
 // One 128 x 256 accumulator tile: this warp's 32 query rows (TMEM lanes) x 256 columns, read
-// 32 columns at a time; thread = query row. `stg` is this warp's private [32][32] float scratch.
-__device__ __forceinline__ void epilogue_tile(TopList& top, uint32_t t_addr, int64_t row_base,
+// 32 columns at a time with the next tcgen05.ld in flight while the current group is scanned;
+// thread = query row. `stg` is this warp's private [32][32] float scratch.
+template <bool DOUBLE_BUFFER, int KC>
+__device__ __forceinline__ void epilogue_tile(TopList<KC>& top, uint32_t t_addr, int64_t row_base,
                                               int64_t n_rows, float* stg, int lane, int debug) {
   if (debug == 1) return;
   if (debug == 2) top.thr = INFINITY;
   const bool ragged = row_base + kBN > n_rows;  // last tile: rows past the table are zero-filled
+  if constexpr (!DOUBLE_BUFFER) {  // two warps per scheduler already hide the TMEM latency
 #pragma unroll 1
-  for (int c = 0; c < kBN / 32; ++c) {
-    uint32_t v[32];
-    tmem_ld_32x32(t_addr + c * 32, v);
+    for (int c = 0; c < kBN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_addr + c * 32, v);
+      tmem_ld_wait();
+      process_group(top, v, int(row_base) + c * 32, ragged, n_rows, stg, lane);
+    }
+    return;
+  }
+  uint32_t va[32], vb[32];
+  tmem_ld_32x32(t_addr, va);
+#pragma unroll 1
+  for (int c = 0; c < kBN / 32; c += 2) {
     tmem_ld_wait();
-    const int col0 = int(row_base) + c * 32;
-    if (ragged) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (int64_t(col0) + j >= n_rows) v[j] = 0xff800000u;  // -inf
-    }
-    uint32_t hits = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) hits |= (__uint_as_float(v[j]) > top.thr) ? (1u << j) : 0u;
-    if (__any_sync(0xffffffffu, hits != 0)) {
-      // rare path: park the 32 scores (column-major per lane, conflict-free) and let each
-      // thread walk its own hit mask
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stg[j * 32 + lane] = __uint_as_float(v[j]);
-      while (hits) {
-        const int j = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const float cv = stg[j * 32 + lane];
-        if (cv > top.thr) top.insert(cv, col0 + j);
-      }
-    }
+    tmem_ld_32x32(t_addr + (c + 1) * 32, vb);
+    process_group(top, va, int(row_base) + c * 32, ragged, n_rows, stg, lane);
+    tmem_ld_wait();
+    if (c + 2 < kBN / 32) tmem_ld_32x32(t_addr + (c + 2) * 32, va);
+    process_group(top, vb, int(row_base) + (c + 1) * 32, ragged, n_rows, stg, lane);
   }
 }
 
@@ -127,6 +167,51 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline int k2_epi_sets() {
+  const char* e = getenv("MRAG_K2_SETS");
+  const int v = e ? atoi(e) : 1;
+  return v == 2 ? 2 : 1;
+}
+
+__device__ __forceinline__ long long clk() { return clock64(); }
+// mbar_wait that charges the waited cycles to `acc`
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clk();
+  while (!mbar_try_wait(bar, parity)) {
+  }
+  acc += clk() - t0;
+}
+
+// host: allocate / print the stats buffer when MRAG_K2_STATS=1
+inline unsigned long long* k2_stats_alloc(int n_ctas) {
+  const char* e = getenv("MRAG_K2_STATS");
+  if (!e || e[0] != '1') return nullptr;
+  unsigned long long* p = nullptr;
+  if (cudaMalloc(&p, size_t(n_ctas) * 8 * 8) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, size_t(n_ctas) * 8 * 8);
+  return p;
+}
+inline void k2_stats_report(unsigned long long* dev, int n_ctas, cudaStream_t st, const char* what) {
+  if (!dev) return;
+  cudaStreamSynchronize(st);
+  unsigned long long* h = new unsigned long long[size_t(n_ctas) * 8];
+  cudaMemcpy(h, dev, size_t(n_ctas) * 64, cudaMemcpyDeviceToHost);
+  double s[8] = {0};
+  for (int c = 0; c < n_ctas; ++c)
+    for (int j = 0; j < 8; ++j) s[j] += double(h[c * 8 + j]);
+  for (int j = 0; j < 8; ++j) s[j] /= n_ctas;
+  const double tiles = s[6] > 0 ? s[6] : 1;
+  fprintf(stderr,
+          "[k2 stats %s] per CTA: total %.0f cyc, tiles %.0f (%.0f cyc/tile) | producer wait-empty %.1f%% | "
+          "mma wait-full %.1f%% wait-tmem-empty %.1f%% | epilogue(w0) wait-tmem-full %.1f%% busy %.1f%% "
+          "(%.0f cyc/tile served)\n",
+          what, s[0], tiles, s[0] / tiles, 100 * s[1] / s[0], 100 * s[2] / s[0], 100 * s[3] / s[0],
+          100 * s[4] / s[0], 100 * s[5] / s[0], s[7] > 0 ? s[5] / s[7] : 0.0);
+  delete[] h;
+  cudaFree(dev);
+}
 
 inline int k2_debug_mode() {
   const char* e = getenv("MRAG_K2_DEBUG");

@@ -143,9 +143,9 @@ __device__ __forceinline__ void emit_filtered(EntryFn entry, int n_sorted, int k
 // one SM), so selection is done on the run heads instead: with R = rerank, the R-th best key
 // overall can be no worse than T = the R-th best run head, hence only keys <= T (in key order)
 // can matter, and they all live in the (exactly R, keys are unique) runs whose head is <= T.
-// Sort 512 heads -> T -> compact the qualifying keys (<= R * run_len <= 2048) -> sort those.
+// Sort <= 1024 heads -> T -> compact the qualifying keys (<= R * run_len <= 2048) -> sort those.
 constexpr int kMaxRerank = 64;
-constexpr int kMaxRuns = 512;
+constexpr int kMaxRuns = 1024;
 constexpr int kMaxSel = 2048;
 constexpr int kK3Threads = 512;
 

@@ -31,12 +31,14 @@ struct K2Plan {
   int chunks;           // database split into this many contiguous tile ranges
   int tiles_per_chunk;  // ceil(n_tiles / chunks)
   int grid;             // persistent CTAs
+  int epi_sets;         // epilogue warp sets = candidate runs per (query, chunk)
+  int kc;               // candidates kept per run: 16 or 32
 };
-constexpr int kK2Cand = 32;  // candidates kept per (query, chunk)
+constexpr int kK2CandMax = 32;  // candidates kept per run: 16 (k <= 12) or 32
 bool k2_supported(int dim);
-K2Plan k2_plan(int64_t n_rows, int nq, int sm_count);
+K2Plan k2_plan(int64_t n_rows, int nq, int sm_count);  // caller sets .kc
 // q_bf16 [q_rows_padded][dim] (rows >= nq zero), db_bf16 [db_rows_padded][dim] (rows >= n_rows
-// zero), both padded to whole tiles; cand [nq][chunks][32] u64 keys; gthr [nq] u32 zeroed
+// zero), both padded to whole tiles; cand [nq][chunks][plan.epi_sets][32] u64 keys; gthr [nq] u32 zeroed
 cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* db_bf16,
                             int64_t db_rows_padded, int64_t n_rows, int dim, int nq,
                             const K2Plan& plan, uint64_t* cand, uint32_t* gthr, cudaStream_t st);

@@ -93,3 +93,23 @@ def test_packed_layout_views_alias_one_buffer():
 def test_mask_and_sinusoid_match_oracle():
     assert torch.equal(block_causal_mask(10, 25), cc.block_causal_mask(10, 25))
     assert torch.equal(sinusoid_table(256, 1024), cc.sinusoid_table(256, 1024)[0])
+
+
+def test_select_refs_follows_get_ref_videos_semantics():
+    """src/data/dataset.py:285-312: first K hits, dropped/missing -> (-1, distance 1.0)."""
+    from motionrag_b200 import select_refs
+    idx = torch.tensor([[5, 9, 2, 7, -1, -1], [1, -1, -1, -1, -1, -1]])
+    dist = torch.tensor([[.1, .2, .3, .4, float("inf"), float("inf")], [.5] + [float("inf")] * 5])
+    i, d = select_refs(idx, dist, 4)
+    assert i.tolist() == [[5, 9, 2, 7], [1, -1, -1, -1]]
+    assert d.tolist() == [[pytest.approx(.1), pytest.approx(.2), pytest.approx(.3), pytest.approx(.4)], [.5, 1, 1, 1]]
+    i, d = select_refs(idx[:, :2], dist[:, :2], 4)          # fewer hits than slots
+    assert i.tolist() == [[5, 9, -1, -1], [1, -1, -1, -1]] and d[0, 2:].tolist() == [1.0, 1.0]
+    g = torch.Generator().manual_seed(0)
+    i, d = select_refs(idx, dist, 4, uncond_video_ratio=1.0, generator=g)   # everything dropped
+    assert bool((i == -1).all()) and bool((d == 1.0).all())
+    g = torch.Generator().manual_seed(0)
+    big = torch.arange(4000).view(1000, 4)
+    i, d = select_refs(big, torch.zeros(1000, 4), 4, uncond_video_ratio=0.25, generator=g)
+    frac = float((i == -1).float().mean())
+    assert 0.2 < frac < 0.3 and bool((d[i == -1] == 1.0).all()) and bool((i[i >= 0] == big[i >= 0]).all())

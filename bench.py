@@ -128,6 +128,9 @@ def run_ours(args):
 
     pk = peaks()
     stores = {}
+    # cross-GPU merge: fused into the last search kernel over peer-mapped memory (default) or
+    # one NCCL all-gather + merge kernel (--exchange nccl)
+    xchg = m.PeerExchange(rank, world, dev, nq_cap=4096, k_cap=32) if (world > 1 and args.exchange == "peer") else None
 
     def get_store(n_rows, kind):
         key = (n_rows, kind)
@@ -141,7 +144,7 @@ def run_ours(args):
             st = m.EmbeddingStore(DIM, max(hi - lo, 1), dev)
             synthetic.fill_store(st, hi - lo, kind, seed=0, first_row=lo)
             st.set_groups(synthetic.groups(hi - lo, lo, dev))
-            stores[key] = (st, m.ShardedRetriever(st, rank, world, rps), rps, lo, hi)
+            stores[key] = (st, m.ShardedRetriever(st, rank, world, rps, exchange=xchg), rps, lo, hi)
         return stores[key]
 
     def make_queries(st, nq, seed):
@@ -311,7 +314,10 @@ def run_ours(args):
                 "data": "synthetic (seeded clustered unit vectors, un-normalised queries; random-init features)",
                 "config": {"workload": f"{args.workload}: {desc}", "db_rows": n_rows, "dim": DIM,
                            "queries_per_step": nq, "top_k": TOPK, "filter": 'post-filter video != own',
-                           "sharding": f"rows/{world}", "l2_flush": "none needed: table (>=3 GB) >> 126 MB L2",
+                           "sharding": f"rows/{world}",
+                           "exchange": ("none" if world == 1 else
+                                        ("fused peer-memory exchange in K3 (NVLink stores + flags)" if xchg is not None
+                                         else "NCCL all_gather_into_tensor + merge kernel")), "l2_flush": "none needed: table (>=3 GB) >> 126 MB L2",
                            "query_pool": POOL},
                 "p50_latency_ms": main["p50_ms"], "p95_latency_ms": main["p95_ms"],
                 "e2e": main.get("e2e"), "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
@@ -398,6 +404,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1", choices=list(WORKLOADS))
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

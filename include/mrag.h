@@ -130,6 +130,27 @@ MRAG_API int mrag_search(const mrag_store* s, const float* queries_dev, int32_t 
                 const mrag_search_params* p, const int32_t* exclude_group_dev,
                 float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
                 void* workspace_dev, size_t workspace_bytes, void* stream);
+/* ---- row-sharded search with the cross-GPU merge fused into the last kernel -----------------
+ * One process per GPU; every rank holds a contiguous row range (params.index_base = its first
+ * global row) and an exchange buffer of mrag_exchange_bytes() zero-initialised bytes that all
+ * peers have mapped (mrag_ipc_export/open). Each K3 block stores its shard's top-k straight into
+ * every rank's buffer over NVLink, raises per-query flags and merges world*k candidates as
+ * soon as the peers' flags arrive — no collective call and no extra launch. All ranks must
+ * issue the same sequence of calls (same nq, k) with the same epoch = 1, 2, 3, ... */
+typedef struct mrag_exchange {
+  int32_t world, rank;     /* world <= 8 */
+  int32_t nq_cap, k_cap;   /* capacity the buffers were sized for (k_cap <= 32) */
+  uint32_t epoch;          /* call counter, identical on all ranks, starts at 1 */
+  int32_t reserved;
+  void* const* bufs_dev;   /* device array [world]: exchange-buffer base of every rank */
+} mrag_exchange;
+MRAG_API size_t mrag_exchange_bytes(int32_t world, int32_t nq_cap, int32_t k_cap);
+MRAG_API int mrag_search_sharded(const mrag_store* s, const float* queries_dev, int32_t nq,
+                const mrag_search_params* p, const int32_t* exclude_group_dev,
+                float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
+                void* workspace_dev, size_t workspace_bytes, const mrag_exchange* xchg,
+                void* stream);
+
 /* mrag_search bracketed by CUDA events on `stream`: *scan_ms_out = duration of the scan kernel
  * alone (K1 or K2), *total_ms_out = the whole call on the device. Synchronises the stream.
  * Used by bench.py for the roofline of the dominant kernel. */
@@ -139,7 +160,8 @@ MRAG_API int mrag_search_timed(const mrag_store* s, const float* queries_dev, in
                 void* workspace_dev, size_t workspace_bytes, void* stream,
                 float* scan_ms_out, float* total_ms_out);
 /* same call with HOST buffers: copies in, searches, copies out, synchronises the stream.
- * Allocates its device scratch from the stream-ordered pool. */
+ * Device scratch and a pinned staging block live in the store and are reused; concurrent
+ * host-buffer calls on one store serialise on an internal mutex. */
 MRAG_API int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
                      const mrag_search_params* p, const int32_t* exclude_group_host,
                      float* out_dist_host, int64_t* out_idx_host, int32_t* out_group_host,

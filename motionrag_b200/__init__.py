@@ -9,7 +9,8 @@ src/projects/condition/module.py:298-301). No CPU fallback exists anywhere in th
 from ._cabi import MragError, launch_count  # noqa: F401
 from .context import (MotionContext, attach, block_causal_mask, gather_context, select_refs,  # noqa: F401
                       sinusoid_table)
-from .parallel import ShardedRetriever, alloc_feature_block, open_peer_tables, shard_range  # noqa: F401
+from .parallel import (PeerExchange, ShardedRetriever, alloc_feature_block, open_peer_tables,  # noqa: F401
+                       shard_range)
 from .rag import RAGDatabase, save_table  # noqa: F401
 from .store import EmbeddingStore, FeatureTable, SearchResult, merge_topk  # noqa: F401
 

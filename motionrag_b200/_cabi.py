@@ -48,6 +48,11 @@ class PlanInfo(C.Structure):
                 ("scan_flops", C.c_int64), ("workspace_bytes", C.c_size_t)]
 
 
+class Exchange(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("nq_cap", C.c_int32), ("k_cap", C.c_int32),
+                ("epoch", C.c_uint32), ("reserved", C.c_int32), ("bufs_dev", C.c_void_p)]
+
+
 # name -> (restype, argtypes); mirrors include/mrag.h one to one (tests check the list)
 SIGNATURES = {
     "mrag_abi_version": (C.c_int, []),
@@ -61,6 +66,10 @@ SIGNATURES = {
     "mrag_search_plan": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.POINTER(PlanInfo)]),
     "mrag_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mrag_exchange_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "mrag_search_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.POINTER(Exchange), C.c_void_p]),
     "mrag_search_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                     C.POINTER(C.c_float), C.POINTER(C.c_float)]),

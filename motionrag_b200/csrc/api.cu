@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "../../include/mrag.h"
 #include "kernels.h"
@@ -47,6 +49,26 @@ struct mrag_store {
   void* rows_bf16 = nullptr;
   int32_t* groups = nullptr;
   bool has_groups = false;
+  // scratch of the host-buffer entry point (mrag_search_host): grown on demand, reused
+  mutable std::mutex host_mu;
+  mutable char* host_dev = nullptr;
+  mutable size_t host_dev_bytes = 0;
+  mutable char* host_pin = nullptr;   // pinned staging for small transfers
+  mutable size_t host_pin_bytes = 0;
+  // small host-buffer calls replay a captured CUDA graph (H2D copy -> scan -> K3 -> D2H copy)
+  // on a private stream: one launch instead of five submissions
+  struct HostGraph {
+    int32_t nq, k, metric, path, refine, filter_mode, has_ex;
+    int64_t index_base, n_rows;
+    cudaGraphExec_t exec;
+  };
+  mutable std::vector<HostGraph> host_graphs;
+  mutable cudaStream_t host_stream = nullptr;
+  mutable cudaEvent_t host_event = nullptr;
+  void drop_host_graphs() const {
+    for (auto& g : host_graphs) cudaGraphExecDestroy(g.exec);
+    host_graphs.clear();
+  }
 };
 
 namespace {
@@ -201,6 +223,11 @@ int mrag_store_destroy(mrag_store* s) {
   cudaFree(s->rows_f32);
   cudaFree(s->rows_bf16);
   cudaFree(s->groups);
+  s->drop_host_graphs();
+  if (s->host_stream) cudaStreamDestroy(s->host_stream);
+  if (s->host_event) cudaEventDestroy(s->host_event);
+  cudaFree(s->host_dev);
+  cudaFreeHost(s->host_pin);
   delete s;
   return MRAG_OK;
 }
@@ -221,6 +248,10 @@ int mrag_store_append(mrag_store* s, const float* rows, int64_t n, int32_t rows_
   CK(launch_prepare_rows(dst, static_cast<char*>(s->rows_bf16) + size_t(s->n_rows) * s->dim * 2, n,
                          s->dim, normalise != 0, st));
   s->n_rows += n;
+  {
+    std::lock_guard<std::mutex> lock(s->host_mu);
+    s->drop_host_graphs();
+  }
   return MRAG_OK;
 }
 
@@ -235,6 +266,10 @@ int mrag_store_set_groups(mrag_store* s, const int32_t* groups, int64_t n, int32
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                      static_cast<cudaStream_t>(stream)));
   s->has_groups = true;
+  {
+    std::lock_guard<std::mutex> lock(s->host_mu);
+    s->drop_host_graphs();
+  }
   return MRAG_OK;
 }
 
@@ -280,7 +315,8 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
                        const mrag_search_params* p, const int32_t* exclude_group_dev,
                        float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
                        void* workspace_dev, size_t workspace_bytes, void* stream,
-                       cudaEvent_t before_scan, cudaEvent_t after_scan) {
+                       cudaEvent_t before_scan, cudaEvent_t after_scan,
+                       const mrag_exchange* xchg = nullptr) {
   Plan pl;
   int rc = make_plan(s, nq, p, &pl);
   if (rc != MRAG_OK) return rc;
@@ -322,9 +358,24 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
   if (after_scan) CK(cudaEventRecord(after_scan, st));
   const int32_t* groups = s->has_groups ? s->groups : nullptr;
   const int fm = (exclude_group_dev && groups) ? p->filter_mode : MRAG_FILTER_NONE;
+  ExchangeDesc xd{};
+  const ExchangeDesc* xd_ptr = nullptr;
+  if (xchg != nullptr && xchg->world > 1) {
+    if (!xchg->bufs_dev || xchg->rank < 0 || xchg->rank >= xchg->world || xchg->world > 8 ||
+        nq > xchg->nq_cap || p->k > xchg->k_cap || xchg->k_cap > 32 || xchg->epoch == 0)
+      return fail(MRAG_ERR_ARG, "bad exchange descriptor (world %d rank %d nq %d/%d k %d/%d epoch %u)",
+                  xchg->world, xchg->rank, nq, xchg->nq_cap, p->k, xchg->k_cap, xchg->epoch);
+    xd.world = xchg->world;
+    xd.rank = xchg->rank;
+    xd.nq_cap = xchg->nq_cap;
+    xd.k_cap = xchg->k_cap;
+    xd.epoch = xchg->epoch;
+    xd.bufs_dev = xchg->bufs_dev;
+    xd_ptr = &xd;
+  }
   CK(launch_k3_merge_rerank(cand, pl.cands_per_query / pl.kc, pl.kc, s->rows_f32, s->dim, queries_dev, nq, groups,
                             exclude_group_dev, fm, p->metric, pl.rerank, p->k, p->index_base,
-                            out_dist_dev, out_idx_dev, out_group_dev, st));
+                            out_dist_dev, out_idx_dev, out_group_dev, xd_ptr, st));
   return MRAG_OK;
 }
 
@@ -334,6 +385,21 @@ int mrag_search(const mrag_store* s, const float* queries_dev, int32_t nq,
                 size_t workspace_bytes, void* stream) {
   return search_impl(s, queries_dev, nq, p, exclude_group_dev, out_dist_dev, out_idx_dev,
                      out_group_dev, workspace_dev, workspace_bytes, stream, nullptr, nullptr);
+}
+
+int mrag_search_sharded(const mrag_store* s, const float* queries_dev, int32_t nq,
+                        const mrag_search_params* p, const int32_t* exclude_group_dev,
+                        float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
+                        void* workspace_dev, size_t workspace_bytes, const mrag_exchange* xchg,
+                        void* stream) {
+  if (!xchg) return fail(MRAG_ERR_ARG, "null exchange descriptor");
+  return search_impl(s, queries_dev, nq, p, exclude_group_dev, out_dist_dev, out_idx_dev,
+                     out_group_dev, workspace_dev, workspace_bytes, stream, nullptr, nullptr, xchg);
+}
+
+size_t mrag_exchange_bytes(int32_t world, int32_t nq_cap, int32_t k_cap) {
+  if (world < 1 || world > 8 || nq_cap < 1 || k_cap < 1 || k_cap > 32) return 0;
+  return exchange_bytes(world, nq_cap, k_cap);
 }
 
 int mrag_search_timed(const mrag_store* s, const float* queries_dev, int32_t nq,
@@ -380,42 +446,109 @@ int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
     return fail(MRAG_ERR_ARG, "null host buffer");
   DeviceGuard g(s->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t q_bytes = align_up(size_t(nq) * s->dim * 4, 256);
-  const size_t ex_bytes = align_up(size_t(nq) * 4, 256);
-  const size_t od_bytes = align_up(size_t(nq) * p->k * 4, 256);
-  const size_t oi_bytes = align_up(size_t(nq) * p->k * 8, 256);
-  const size_t og_bytes = od_bytes;
-  const size_t total = q_bytes + ex_bytes + od_bytes + oi_bytes + og_bytes + pl.total;
-  char* buf = nullptr;
-  CK(cudaMallocAsync(reinterpret_cast<void**>(&buf), total, st));
-  char* c = buf;
-  float* q_d = reinterpret_cast<float*>(c); c += q_bytes;
-  int32_t* ex_d = reinterpret_cast<int32_t*>(c); c += ex_bytes;
-  float* od_d = reinterpret_cast<float*>(c); c += od_bytes;
-  int64_t* oi_d = reinterpret_cast<int64_t*>(c); c += oi_bytes;
-  int32_t* og_d = reinterpret_cast<int32_t*>(c); c += og_bytes;
-  void* ws = c;
-  cudaError_t e = cudaMemcpyAsync(q_d, queries_host, size_t(nq) * s->dim * 4, cudaMemcpyHostToDevice, st);
+  std::lock_guard<std::mutex> lock(s->host_mu);  // one host-buffer call at a time per store
+  // device block: [queries | exclude] (one H2D) [dist | idx | group] (one D2H) [workspace]
+  const size_t q_raw = size_t(nq) * s->dim * 4, ex_raw = size_t(nq) * 4;
+  const size_t in_bytes = align_up(q_raw + ex_raw, 256);
+  const size_t nk = size_t(nq) * p->k;
+  const size_t out_raw = nk * 16;  // idx i64 | dist f32 | group i32
+  const size_t out_bytes = align_up(out_raw, 256);
+  const size_t total = in_bytes + out_bytes + pl.total;
+  if (s->host_dev_bytes < total) {
+    s->drop_host_graphs();
+    cudaFree(s->host_dev);
+    s->host_dev = nullptr;
+    s->host_dev_bytes = 0;
+    CK(cudaMalloc(reinterpret_cast<void**>(&s->host_dev), total));
+    s->host_dev_bytes = total;
+  }
+  char* base = s->host_dev;
+  float* q_d = reinterpret_cast<float*>(base);
+  int32_t* ex_d = reinterpret_cast<int32_t*>(base + q_raw);
+  int64_t* oi_d = reinterpret_cast<int64_t*>(base + in_bytes);
+  float* od_d = reinterpret_cast<float*>(base + in_bytes + nk * 8);
+  int32_t* og_d = reinterpret_cast<int32_t*>(base + in_bytes + nk * 12);
+  void* ws = base + in_bytes + out_bytes;
+  // small transfers go through pinned staging (truly asynchronous, one copy each way)
+  const bool staged = (q_raw + ex_raw) <= (256u << 10) && out_raw <= (256u << 10);
+  if (staged && s->host_pin_bytes < (512u << 10)) {
+    cudaFreeHost(s->host_pin);
+    s->host_pin = nullptr;
+    s->host_pin_bytes = 0;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&s->host_pin), 512u << 10));
+    s->host_pin_bytes = 512u << 10;
+  }
+  cudaError_t e;
+  if (staged) {
+    // ---- graph path: fixed staging + fixed scratch make the whole call a static graph ----
+    if (!s->host_stream) CK(cudaStreamCreateWithFlags(&s->host_stream, cudaStreamNonBlocking));
+    if (!s->host_event) CK(cudaEventCreateWithFlags(&s->host_event, cudaEventDisableTiming));
+    cudaStream_t hs = s->host_stream;
+    memcpy(s->host_pin, queries_host, q_raw);
+    if (exclude_group_host) memcpy(s->host_pin + q_raw, exclude_group_host, ex_raw);
+    char* pin_out = s->host_pin + (256u << 10);
+    CK(cudaEventRecord(s->host_event, st));  // order after the caller's pending work (appends)
+    CK(cudaStreamWaitEvent(hs, s->host_event, 0));
+    const int has_ex = exclude_group_host ? 1 : 0;
+    cudaGraphExec_t exec = nullptr;
+    // (the graph bakes in nk-dependent result offsets: nq and k are part of the key)
+    for (auto& hg : s->host_graphs)
+      if (hg.nq == nq && hg.k == p->k && hg.metric == p->metric && hg.path == p->path &&
+          hg.refine == p->refine && hg.filter_mode == p->filter_mode && hg.has_ex == has_ex &&
+          hg.index_base == p->index_base && hg.n_rows == s->n_rows)
+        exec = hg.exec;
+    if (!exec) {
+      CK(cudaStreamBeginCapture(hs, cudaStreamCaptureModeThreadLocal));
+      e = cudaMemcpyAsync(base, s->host_pin, q_raw + (has_ex ? ex_raw : 0), cudaMemcpyHostToDevice, hs);
+      int crc = MRAG_OK;
+      // results are written by K3 straight into the pinned block (zero-copy stores over PCIe):
+      // no device->host copy node, the graph ends with the kernel
+      if (e == cudaSuccess)
+        crc = search_impl(s, q_d, nq, p, has_ex ? ex_d : nullptr,
+                          reinterpret_cast<float*>(pin_out + nk * 8),
+                          reinterpret_cast<int64_t*>(pin_out),
+                          reinterpret_cast<int32_t*>(pin_out + nk * 12), ws, pl.total, hs, nullptr,
+                          nullptr);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e2 = cudaStreamEndCapture(hs, &graph);
+      if (crc != MRAG_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return crc;
+      }
+      if (e != cudaSuccess || e2 != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return cuda_fail(e != cudaSuccess ? e : e2, "graph capture of the host search");
+      }
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+      if (s->host_graphs.size() >= 64) s->drop_host_graphs();
+      s->host_graphs.push_back({nq, p->k, p->metric, p->path, p->refine, p->filter_mode, has_ex,
+                                p->index_base, s->n_rows, exec});
+    }
+    e = cudaGraphLaunch(exec, hs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(hs);
+    if (e != cudaSuccess) return cuda_fail(e, "graph launch of the host search");
+    note_launch(pl.path == MRAG_PATH_TENSOR_BF16 ? 3 : 2);  // kernels replayed by the graph
+    memcpy(out_idx_host, pin_out, nk * 8);
+    memcpy(out_dist_host, pin_out + nk * 8, nk * 4);
+    if (out_group_host) memcpy(out_group_host, pin_out + nk * 12, nk * 4);
+    return MRAG_OK;
+  }
+  e = cudaMemcpyAsync(q_d, queries_host, q_raw, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && exclude_group_host)
-    e = cudaMemcpyAsync(ex_d, exclude_group_host, size_t(nq) * 4, cudaMemcpyHostToDevice, st);
-  if (e != cudaSuccess) {
-    cudaFreeAsync(buf, st);
-    return cuda_fail(e, "host->device copy");
-  }
-  rc = mrag_search(s, q_d, nq, p, exclude_group_host ? ex_d : nullptr, od_d, oi_d,
-                   out_group_host ? og_d : nullptr, ws, pl.total, stream);
-  if (rc == MRAG_OK) {
-    e = cudaMemcpyAsync(out_dist_host, od_d, size_t(nq) * p->k * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(out_idx_host, oi_d, size_t(nq) * p->k * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && out_group_host)
-      e = cudaMemcpyAsync(out_group_host, og_d, size_t(nq) * p->k * 4, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) rc = cuda_fail(e, "device->host copy");
-  }
-  cudaFreeAsync(buf, st);
-  e = cudaStreamSynchronize(st);
-  if (rc == MRAG_OK && e != cudaSuccess) rc = cuda_fail(e, "stream synchronize");
-  return rc;
+    e = cudaMemcpyAsync(ex_d, exclude_group_host, ex_raw, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
+  rc = mrag_search(s, q_d, nq, p, exclude_group_host ? ex_d : nullptr, od_d, oi_d, og_d, ws,
+                   pl.total, stream);
+  if (rc != MRAG_OK) return rc;
+  e = cudaMemcpyAsync(out_idx_host, oi_d, nk * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist_host, od_d, nk * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && out_group_host)
+    e = cudaMemcpyAsync(out_group_host, og_d, nk * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e, "device->host copy");
+  return MRAG_OK;
 }
 
 int mrag_merge_topk(const float* cand_dist_dev, const int64_t* cand_idx_dev,

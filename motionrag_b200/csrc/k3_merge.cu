@@ -137,6 +137,39 @@ __device__ __forceinline__ void emit_filtered(EntryFn entry, int n_sorted, int k
   }
 }
 
+// ---- cross-GPU exchange fused into K3 (row-sharded stores) -------------------------------------
+// Every rank owns an exchange buffer that all peers have mapped (CUDA IPC over NVLink):
+//   records: [slot 2][src rank][query][ idx i64 x k_cap | dist f32 x k_cap | group i32 x k_cap ]
+//   flags  : [slot 2][src rank][query] u32 epoch
+// A K3 block (one query) stores its shard's top-k record into the same (slot, own rank, query)
+// cell of EVERY rank's buffer with plain NVLink stores, fences at system scope, raises the
+// matching flags, then waits for the flags of all source ranks in its OWN buffer and merges the
+// world * k candidates locally. No collective library call, no extra launch: the exchange
+// overlaps with the other queries' blocks. Slots alternate with the epoch, so a rank can run at
+// most one call ahead of the slowest peer, which cannot still be reading the slot being
+// rewritten.
+struct XchgArgs {
+  int world, rank;      // world <= 1 disables the exchange
+  int nq_cap, k_cap;
+  uint32_t epoch;
+  char* const* bufs;    // device array [world]: exchange-buffer base of every rank
+};
+__host__ __device__ inline size_t xchg_rec_bytes(int k_cap) { return size_t(k_cap) * 16; }
+__host__ __device__ inline size_t xchg_flags_offset(int world, int nq_cap, int k_cap) {
+  return size_t(2) * world * nq_cap * xchg_rec_bytes(k_cap);
+}
+__host__ __device__ inline size_t xchg_total_bytes(int world, int nq_cap, int k_cap) {
+  return xchg_flags_offset(world, nq_cap, k_cap) + size_t(2) * world * nq_cap * 4;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ---- K3 -------------------------------------------------------------------------------------
 // Candidates arrive as `n_runs` runs of `run_len` keys, each run sorted best-first (one run per
 // K1 CTA / K2 chunk). A full sort of up to 16 K keys is shared-memory-bandwidth bound (~80 us on
@@ -155,7 +188,8 @@ __global__ void __launch_bounds__(kK3Threads)
                            const int32_t* __restrict__ row_group,
                            const int32_t* __restrict__ exclude_group, int filter_mode, int metric,
                            int rerank, int k, int64_t index_base, float* __restrict__ out_dist,
-                           int64_t* __restrict__ out_idx, int32_t* __restrict__ out_group) {
+                           int64_t* __restrict__ out_idx, int32_t* __restrict__ out_group,
+                           const XchgArgs x) {
   __shared__ uint64_t heads[kMaxRuns];      // run heads, unsorted (index = run)
   __shared__ uint64_t sorted_heads[kMaxRuns];
   __shared__ uint64_t sel[kMaxSel];
@@ -241,44 +275,130 @@ __global__ void __launch_bounds__(kK3Threads)
   }
   bitonic_sort_smem(rr_keys, kMaxRerank, tid, kK3Threads);
 
+  const int exclude = (exclude_group != nullptr) ? exclude_group[q] : -1;
+  auto entry = [&](int j, bool in_range) {
+    Emit e;
+    e.valid = false;
+    e.dist = INFINITY;
+    e.idx = -1;
+    e.group = -1;
+    if (in_range && j < kMaxRerank) {
+      const uint64_t key = rr_keys[j];
+      const uint32_t idx = uint32_t(key);
+      if (key != kEmptyKey && idx < uint32_t(kInvalidIdx)) {
+        e.valid = true;
+        e.dist = ordered_to_f32(uint32_t(key >> 32));
+        e.idx = index_base + int64_t(idx);
+        e.group = (row_group != nullptr) ? row_group[idx] : -1;
+      }
+    }
+    return e;
+  };
+  if (x.world <= 1) {
+    if (warp == 0)
+      emit_filtered(entry, n_rr, k, filter_mode, exclude, out_dist + int64_t(q) * k,
+                    out_idx + int64_t(q) * k, out_group ? out_group + int64_t(q) * k : nullptr, lane);
+    return;
+  }
+
+  // ---- row-sharded: publish this shard's top-k to every rank, wait for theirs, merge ----
+  __shared__ float rec_dist[32];
+  __shared__ int64_t rec_idx[32];
+  __shared__ int32_t rec_grp[32];
+  // the post-filter belongs after the GLOBAL top-k; a pre-filter can be applied per shard
+  if (warp == 0)
+    emit_filtered(entry, n_rr, k, filter_mode == 2 ? 2 : 0, exclude, rec_dist, rec_idx, rec_grp, lane);
+  __syncthreads();
+  const int slot = int(x.epoch & 1u);
+  const size_t rec_bytes = xchg_rec_bytes(x.k_cap);
+  const size_t cell = (size_t(slot) * x.world + x.rank) * x.nq_cap + q;  // (slot, src = me, query)
+  const size_t flags_off = xchg_flags_offset(x.world, x.nq_cap, x.k_cap);
+  for (int t = tid; t < x.world * k; t += kK3Threads) {
+    const int r = t / k, j = t % k;
+    char* rec = x.bufs[r] + cell * rec_bytes;
+    reinterpret_cast<int64_t*>(rec)[j] = rec_idx[j];
+    reinterpret_cast<float*>(rec + size_t(x.k_cap) * 8)[j] = rec_dist[j];
+    reinterpret_cast<int32_t*>(rec + size_t(x.k_cap) * 12)[j] = rec_grp[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < x.world)
+    st_release_sys(reinterpret_cast<uint32_t*>(x.bufs[tid] + flags_off) + cell, x.epoch);
+  if (tid < x.world) {
+    const size_t src_cell = (size_t(slot) * x.world + tid) * x.nq_cap + q;
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(x.bufs[x.rank] + flags_off) + src_cell;
+    while (ld_acquire_sys(flag) != x.epoch) {
+    }
+  }
+  __syncthreads();
+  // merge world * k candidates; slot order == global row order among equal distances
+  const char* mine = x.bufs[x.rank];
+  const int total = x.world * k;  // <= 256
+  uint64_t* mk = sel;             // reuse: 256 keys
+  if (tid < 256) {
+    uint64_t key = kEmptyKey;
+    if (tid < total) {
+      const int r = tid / k, j = tid % k;
+      const char* rec = mine + ((size_t(slot) * x.world + r) * x.nq_cap + q) * rec_bytes;
+      const int64_t gi = __ldcv(reinterpret_cast<const long long*>(rec) + j);
+      const float gd = __ldcv(reinterpret_cast<const float*>(rec + size_t(x.k_cap) * 8) + j);
+      if (gi >= 0) key = (uint64_t(f32_to_ordered(gd)) << 32) | uint32_t(tid);
+    }
+    mk[tid] = key;
+  }
+  bitonic_sort_smem(mk, 256, tid, kK3Threads);
   if (warp == 0) {
-    const int exclude = (exclude_group != nullptr) ? exclude_group[q] : -1;
-    auto entry = [&](int j, bool in_range) {
+    auto gentry = [&](int j, bool in_range) {
       Emit e;
       e.valid = false;
       e.dist = INFINITY;
       e.idx = -1;
       e.group = -1;
-      if (in_range && j < kMaxRerank) {
-        const uint64_t key = rr_keys[j];
-        const uint32_t idx = uint32_t(key);
-        if (key != kEmptyKey && idx < uint32_t(kInvalidIdx)) {
+      if (in_range) {
+        const uint64_t kk = mk[j];
+        if (kk != kEmptyKey) {
+          const int t = int(uint32_t(kk));
+          const int r = t / k, jj = t % k;
+          const char* rec = mine + ((size_t(slot) * x.world + r) * x.nq_cap + q) * rec_bytes;
           e.valid = true;
-          e.dist = ordered_to_f32(uint32_t(key >> 32));
-          e.idx = index_base + int64_t(idx);
-          e.group = (row_group != nullptr) ? row_group[idx] : -1;
+          e.idx = __ldcv(reinterpret_cast<const long long*>(rec) + jj);
+          e.dist = __ldcv(reinterpret_cast<const float*>(rec + size_t(x.k_cap) * 8) + jj);
+          e.group = __ldcv(reinterpret_cast<const int*>(rec + size_t(x.k_cap) * 12) + jj);
         }
       }
       return e;
     };
-    emit_filtered(entry, n_rr, k, filter_mode, exclude, out_dist + int64_t(q) * k,
+    emit_filtered(gentry, min(total, 64), k, filter_mode, exclude, out_dist + int64_t(q) * k,
                   out_idx + int64_t(q) * k, out_group ? out_group + int64_t(q) * k : nullptr, lane);
   }
 }
+
+size_t exchange_bytes(int world, int nq_cap, int k_cap) { return xchg_total_bytes(world, nq_cap, k_cap); }
 
 cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len,
                                    const float* db_f32, int dim, const float* queries, int nq,
                                    const int32_t* row_group, const int32_t* exclude_group,
                                    int filter_mode, int metric, int rerank, int k,
                                    int64_t index_base, float* out_dist, int64_t* out_idx,
-                                   int32_t* out_group, cudaStream_t st) {
+                                   int32_t* out_group, const ExchangeDesc* xd, cudaStream_t st) {
+  XchgArgs x{};
+  if (xd != nullptr && xd->world > 1) {
+    if (nq > xd->nq_cap || k > xd->k_cap || xd->k_cap > 32 || xd->world * k > 256)
+      return cudaErrorInvalidValue;
+    x.world = xd->world;
+    x.rank = xd->rank;
+    x.nq_cap = xd->nq_cap;
+    x.k_cap = xd->k_cap;
+    x.epoch = xd->epoch;
+    x.bufs = reinterpret_cast<char* const*>(xd->bufs_dev);
+  }
   if (n_runs < 1 || n_runs > kMaxRuns || run_len < 1 || run_len > 32 || rerank < 1 ||
       rerank > kMaxRerank || int64_t(rerank) * run_len > kMaxSel)
     return cudaErrorInvalidValue;
   k3_merge_rerank_kernel<<<nq, kK3Threads, 0, st>>>(cand, n_runs, run_len, db_f32, dim, queries,
                                                     row_group, exclude_group, filter_mode, metric,
                                                     rerank, k, index_base, out_dist, out_idx,
-                                                    out_group);
+                                                    out_group, x);
   note_launch();
   return cudaGetLastError();
 }

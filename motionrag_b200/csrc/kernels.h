@@ -50,13 +50,21 @@ cudaError_t launch_k2_batch_pair(const void* q_bf16, int q_rows_padded, const vo
                                  const K2Plan& plan, uint64_t* cand, uint32_t* gthr, cudaStream_t st);
 
 // K3: candidate merge + exact fp32 re-score + filter --------------------------------------
-// cand: per query n_runs runs of run_len keys, each run sorted best-first
+// peer-memory exchange descriptor (mirrors mrag_exchange of the C ABI)
+struct ExchangeDesc {
+  int world, rank, nq_cap, k_cap;
+  uint32_t epoch;
+  void* const* bufs_dev;
+};
+size_t exchange_bytes(int world, int nq_cap, int k_cap);
+// cand: per query n_runs runs of run_len keys, each run sorted best-first; with xd (world > 1)
+// the kernel also exchanges per-shard results over peer memory and emits the GLOBAL top-k
 cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len,
                                    const float* db_f32, int dim, const float* queries, int nq,
                                    const int32_t* row_group, const int32_t* exclude_group,
                                    int filter_mode, int metric, int rerank, int k,
                                    int64_t index_base, float* out_dist, int64_t* out_idx,
-                                   int32_t* out_group, cudaStream_t st);
+                                   int32_t* out_group, const ExchangeDesc* xd, cudaStream_t st);
 cudaError_t launch_k3_merge_shards(const float* cand_dist, const int64_t* cand_idx,
                                    const int32_t* cand_group, int64_t shard_stride_bytes,
                                    int nshards, int nq, int k_in,

@@ -70,16 +70,73 @@ class PackedLayout:
         return d, g, i
 
 
+class PeerExchange:
+    """Exchange buffers for the fused cross-GPU merge (mrag_search_sharded): one cudaMalloc'ed,
+    zero-initialised block per rank, mapped into every peer with CUDA IPC, plus the device table
+    of the `world` base pointers and the call epoch. Collective constructor (all ranks)."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, nq_cap: int = 4096, k_cap: int = 32,
+                 group: dist.ProcessGroup | None = None):
+        from .store import _view
+        lib = _cabi.load()
+        self.rank, self.world, self.device = rank, world, device
+        self.nq_cap, self.k_cap = int(nq_cap), int(k_cap)
+        nbytes = int(lib.mrag_exchange_bytes(world, self.nq_cap, self.k_cap))
+        if nbytes == 0:
+            raise ValueError("bad exchange shape (world <= 8, k_cap <= 32)")
+        ptr = C.c_void_p()
+        check(lib.mrag_device_alloc(device.index, nbytes, C.byref(ptr)))
+        self._own = ptr
+        self._lib = lib
+        self.buf = _view(ptr.value, (nbytes // 4,), torch.int32, device, self)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        handle = (C.c_ubyte * 64)()
+        check(lib.mrag_ipc_export(ptr, handle))
+        handles: list = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        ptrs = []
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == rank:
+                ptrs.append(ptr.value)
+                continue
+            p = C.c_void_p()
+            check(lib.mrag_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
+            self._opened.append(p)
+            ptrs.append(p.value)
+        self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.epoch = 0
+        dist.barrier(group=group)   # every rank has zeroed and mapped before the first use
+
+    def next(self) -> "_cabi.Exchange":
+        self.epoch += 1
+        return _cabi.Exchange(world=self.world, rank=self.rank, nq_cap=self.nq_cap, k_cap=self.k_cap,
+                              epoch=self.epoch, reserved=0, bufs_dev=self.table.data_ptr())
+
+    def close(self) -> None:
+        for p in getattr(self, "_opened", []):
+            self._lib.mrag_ipc_close(p)
+        self._opened = []
+        if getattr(self, "_own", None):
+            self._lib.mrag_device_free(self.device.index, self._own)
+            self._own = None
+
+
 class ShardedRetriever:
     def __init__(self, store: EmbeddingStore | None, rank: int, world: int, rows_per_shard: int,
                  group: dist.ProcessGroup | None = None, local_search=None, merge=None,
-                 device: torch.device | None = None):
+                 device: torch.device | None = None, exchange: PeerExchange | None = None):
+        """exchange: a PeerExchange makes the cross-GPU merge part of the search's last kernel
+        (NVLink peer stores + flags); without it the per-shard records travel in one NCCL
+        all-gather followed by a merge kernel."""
         self.store, self.rank, self.world = store, rank, world
         self.rows_per_shard = int(rows_per_shard)
         self.group = group
         self.device = device if device is not None else store.device
         self._local_search = local_search or self._cuda_search
         self._merge = merge or self._cuda_merge
+        self.exchange = exchange
         self._bufs: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor]] = {}
 
     # default (product) implementations ------------------------------------------------------
@@ -101,6 +158,12 @@ class ShardedRetriever:
             return self._local_search(queries, k, metric, path, refine, exclude_group,
                                       filter_mode if exclude_group is not None else "none", 0, None)
         nq = queries.shape[0]
+        if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
+            return self.store.search(queries, k, metric=metric, path=path, refine=refine,
+                                     exclude_group=exclude_group,
+                                     filter_mode=filter_mode if exclude_group is not None else "none",
+                                     index_base=self.rank * self.rows_per_shard,
+                                     exchange=self.exchange.next())
         lay = PackedLayout(nq, k)
         key = (nq, k)
         if key not in self._bufs:

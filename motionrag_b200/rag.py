@@ -219,8 +219,9 @@ class RAGDatabase:
         q = q.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
         return q, single
 
-    def _exclusions(self, where, nq: int):
-        """`where` is one SQL string (reference form) or one per query (batched form)."""
+    def _exclusion_ids(self, where, nq: int):
+        """`where` is one SQL string (reference form) or one per query (batched form);
+        -> int32 [nq] group ids to exclude (-1 = none) or None."""
         if where is None:
             return None
         wheres = [where] * nq if isinstance(where, str) else list(where)
@@ -244,7 +245,7 @@ class RAGDatabase:
         if col is None:
             return None
         self._bind_groups(col)
-        return torch.from_numpy(ids).to(self.device, non_blocking=True)
+        return ids
 
     def _group_ids_lookup(self, col: str, value) -> int:
         g = self._groups_for(col)
@@ -271,28 +272,51 @@ class RAGDatabase:
                 raise ValueError(f"unknown column {c!r} in select")
         out = []
         for q in range(idx.shape[0]):
+            rows = idx[q][idx[q] >= 0]
+            n = int(rows.size)
+            # one fancy-index + tolist() per column instead of per-cell numpy scalar handling
+            per_col = []
+            for c, col, is_vec in cols:
+                if is_vec:
+                    per_col.append([np.array(col[int(i)], dtype=np.float32) for i in rows])
+                else:
+                    per_col.append(col[rows].tolist())
+            dist_l = dist[q][:n].tolist()
+            keys = [c for c, _, _ in cols]
             recs = []
-            for d, i in zip(dist[q].tolist(), idx[q].tolist()):
-                if i < 0:
-                    continue
-                r = {}
-                for c, col, is_vec in cols:
-                    v = col[i]
-                    r[c] = np.array(v, dtype=np.float32) if is_vec else (v.item() if isinstance(v, np.generic) else v)
-                r["_distance"] = d
+            for j in range(n):
+                r = {k_: v[j] for k_, v in zip(keys, per_col)}
+                r["_distance"] = dist_l[j]
                 recs.append(r)
             out.append(recs)
         return out
 
     def _search(self, vector, vector_column_name, top_k, where, refine_factor):
+        """-> (distance f32 [nq,k], index i64 [nq,k]) numpy arrays, single?"""
         column = vector_column_name or "text_embedding"
         store = self._store(column)
-        q, single = self._as_queries(vector)
-        excl = self._exclusions(where, q.shape[0])
         refine = int(min(64, max(top_k, top_k * max(1, int(refine_factor)))))
+        mode = "pre" if self.prefilter else "post"
+        on_host = isinstance(vector, np.ndarray) or (isinstance(vector, torch.Tensor) and not vector.is_cuda)
+        if on_host:
+            # the reference's call pattern (a host ndarray per annotation): one C call with host
+            # buffers, one copy each way (mrag_search_host)
+            q = np.asarray(vector.detach().float().numpy() if isinstance(vector, torch.Tensor) else vector,
+                           dtype=np.float32)
+            single = q.ndim == 1
+            q = np.ascontiguousarray(q[None] if single else q)
+            if q.ndim != 2:
+                raise ValueError(f"query must be [dim] or [nq, dim], got {tuple(q.shape)}")
+            excl = self._exclusion_ids(where, q.shape[0])
+            dist, idx, _ = store.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
+                                             exclude_group=excl, filter_mode=mode)
+            return dist, idx, single
+        q, single = self._as_queries(vector)
+        excl = self._exclusion_ids(where, q.shape[0])
+        excl_d = None if excl is None else torch.from_numpy(excl).to(self.device, non_blocking=True)
         res = store.search(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
-                           exclude_group=excl, filter_mode="pre" if self.prefilter else "post")
-        return res, single
+                           exclude_group=excl_d, filter_mode=mode)
+        return res.distance.cpu().numpy(), res.index.cpu().numpy(), single
 
     def vector_search(self, vector, vector_column_name: str = None, top_k: int = 10, table=None,
                       where: str = None, select: list[str] = None, nprobes: int = 50, refine_factor: int = 30,
@@ -303,9 +327,7 @@ class RAGDatabase:
         if output_format not in ("pandas", "pyarrow", "dict", "list"):
             raise ValueError(f'Invalid format: {output_format}')
         db = self if table is None else table
-        res, single = db._search(vector, vector_column_name, top_k, where, refine_factor)
-        dist = res.distance.cpu().numpy()
-        idx = res.index.cpu().numpy()
+        dist, idx, single = db._search(vector, vector_column_name, top_k, where, refine_factor)
         recs = db._records(dist, idx, select)
         if single:
             return self.format_result(recs[0], output_format)
@@ -335,14 +357,12 @@ class RAGDatabase:
         candidate set (the reference materialises a temporary table; here the k0 candidate rows
         become a temporary HBM store searched by the same kernels)."""
         db = self if table is None else table
-        res, single = db._search(text, "text_embedding", top_k[0], where, refine_factor)
+        _, idx0, single = db._search(text, "text_embedding", top_k[0], where, refine_factor)
         if not single:
             raise ValueError("text_image_search takes one query at a time, like the reference")
-        idx0 = res.index[0]
-        idx0 = idx0[idx0 >= 0]
-        if idx0.numel() == 0:
+        rows = idx0[0][idx0[0] >= 0]
+        if rows.size == 0:
             return self.format_result([], output_format)
-        rows = idx0.cpu().numpy()
         img = np.ascontiguousarray(np.asarray(db._vectors["image_embedding"])[rows], dtype=np.float32)
         tmp = EmbeddingStore(img.shape[1], img.shape[0], self.device)
         try:
@@ -368,8 +388,8 @@ class RAGDatabase:
         out: list[list[dict]] = []
         for s in range(0, q_all.shape[0], batch):
             w = None if wheres is None else wheres[s:s + batch]
-            res, _ = self._search(q_all[s:s + batch], vector_column_name, top_k, w, refine_factor)
-            out.extend(self._records(res.distance.cpu().numpy(), res.index.cpu().numpy(), select))
+            dist, idx, _ = self._search(q_all[s:s + batch], vector_column_name, top_k, w, refine_factor)
+            out.extend(self._records(dist, idx, select))
         return out
 
     def retrieve_for_annotations(self, annotations: list[dict], ref_video_num: int,

@@ -122,7 +122,8 @@ class EmbeddingStore:
     def search(self, queries: torch.Tensor, k: int, *, metric: str = "l2", path: str = "auto",
                refine: int = 0, exclude_group: torch.Tensor | None = None,
                filter_mode: str = "post", index_base: int = 0,
-               out: SearchResult | None = None, timings: list | None = None) -> SearchResult:
+               out: SearchResult | None = None, timings: list | None = None,
+               exchange=None) -> SearchResult:
         """Device-resident search: queries [nq, dim] fp32 on this store's GPU -> SearchResult.
 
         Asynchronous on the current stream; nothing is copied to the host.
@@ -147,7 +148,9 @@ class EmbeddingStore:
                 C.c_void_p(out.distance.data_ptr()), C.c_void_p(out.index.data_ptr()),
                 C.c_void_p(out.group.data_ptr()), C.c_void_p(self._ws.data_ptr()), self._ws.numel(),
                 _stream_ptr(self.device))
-        if timings is None:
+        if exchange is not None:   # row-sharded: cross-GPU merge fused into the last kernel
+            check(self._lib.mrag_search_sharded(*args[:-1], C.byref(exchange), args[-1]))
+        elif timings is None:
             check(self._lib.mrag_search(*args))
         else:  # synchronous, event-bracketed variant: appends (scan_ms, total_ms)
             a, b = C.c_float(), C.c_float()

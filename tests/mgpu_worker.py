@@ -21,6 +21,18 @@ from oracle import cama_context as cc  # noqa: E402
 from oracle import compare, flat_search as fs  # noqa: E402
 
 
+def check_retriever(retr, db, q, groups, excl, k, dev):
+    for nq, path in ((1, "stream_f32"), (4, "stream_bf16"), (300, "tensor_bf16"), (64, "auto")):
+        for filt in (None, "post", "pre"):
+            ex = None if filt is None else torch.from_numpy(excl[:nq]).to(dev)
+            r = retr.search(torch.from_numpy(q[:nq]).to(dev), k, path=path, exclude_group=ex, filter_mode=filt or "post")
+            rd, ri = fs.flat_search(db, q[:nq], k, "l2", groups if filt else None, excl[:nq] if filt else None,
+                                    prefilter=(filt == "pre"))
+            compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[:nq])
+            gi = r.index.cpu().numpy()
+            assert np.all(r.group.cpu().numpy()[gi >= 0] == groups[gi[gi >= 0]])
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -37,16 +49,15 @@ def main():
     shard = m.EmbeddingStore(dim, hi - lo, dev)
     shard.append(db[lo:hi], normalise=False)
     shard.set_groups(groups[lo:hi])
-    retr = m.ShardedRetriever(shard, rank, world, rps)
-    for nq, path in ((1, "stream_f32"), (4, "stream_bf16"), (300, "tensor_bf16"), (64, "auto")):
-        for filt in (None, "post", "pre"):
-            ex = None if filt is None else torch.from_numpy(excl[:nq]).to(dev)
-            r = retr.search(torch.from_numpy(q[:nq]).to(dev), k, path=path, exclude_group=ex, filter_mode=filt or "post")
-            rd, ri = fs.flat_search(db, q[:nq], k, "l2", groups if filt else None, excl[:nq] if filt else None,
-                                    prefilter=(filt == "pre"))
-            compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[:nq])
-            gi = r.index.cpu().numpy()
-            assert np.all(r.group.cpu().numpy()[gi >= 0] == groups[gi[gi >= 0]])
+    xchg = m.PeerExchange(rank, world, dev, nq_cap=512, k_cap=32)
+    for retr in (m.ShardedRetriever(shard, rank, world, rps),                    # NCCL all-gather + merge kernel
+                 m.ShardedRetriever(shard, rank, world, rps, exchange=xchg)):     # exchange fused into K3 over peer memory
+        check_retriever(retr, db, q, groups, excl, k, dev)
+    retr = m.ShardedRetriever(shard, rank, world, rps, exchange=xchg)
+    for rep in range(40):    # slot reuse / epoch ordering under back-to-back calls
+        r = retr.search(torch.from_numpy(q[rep:rep + 3]).to(dev), k, path="stream_f32")
+        rd, ri = fs.flat_search(db, q[rep:rep + 3], k)
+        compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[rep:rep + 3])
     # every rank must hold the identical answer
     r = retr.search(torch.from_numpy(q[:64]).to(dev), k)
     ref = r.index.clone()

@@ -108,6 +108,21 @@ def test_host_buffer_entry_point_equals_device_path(case):
     np.testing.assert_array_equal(g, res.group.cpu().numpy())
 
 
+@pytest.mark.parametrize("nq,path", [(1, "auto"), (4, "stream_bf16"), (64, "auto"), (200, "auto")])
+def test_host_buffer_path_replays_and_matches_oracle(case, nq, path):
+    """Small host calls run as a captured CUDA graph; repeated calls with different data and a
+    store mutation in between must stay correct."""
+    for rep in range(3):
+        q = case["q"][rep * 5: rep * 5 + nq]
+        ex = case["excl"][rep * 5: rep * 5 + nq]
+        d, i, g = case["store"].search_host(q, 12, path=path, exclude_group=ex)
+        rd, ri = fs.flat_search(case["db"], q, 12, "l2", case["groups"], ex)
+        compare.check_retrieval(d, i, rd, ri, case["db"], q)
+    case["store"].set_groups(case["groups"])          # drops cached graphs
+    d2, i2, _ = case["store"].search_host(q, 12, path=path, exclude_group=ex)
+    np.testing.assert_array_equal(i2, i)
+
+
 def test_index_base_offsets_global_ids(case):
     qd = torch.from_numpy(case["q"][:2]).cuda()
     a = case["store"].search(qd, 5).index.cpu()

@@ -35,7 +35,9 @@ WORKLOADS = {
     "c3q1": (10_000_000, 1, "clustered", "10M-entry DB row-sharded, single query"),
     "c3q4096": (10_000_000, 4096, "clustered", "10M-entry DB row-sharded, 4096-query batch"),
     "c4": (1_000_000, 16, "clustered", "1M-entry DB, 16-query batch + gather into CAMA context [16,250,1024] bf16"),
+    "c1b": (1_000_000, 1, "clustered", "1M-entry DB, single query, bf16 shadow stream + fp32 re-rank (2 B/elt)"),
 }
+PATHS = {"c1b": "stream_bf16"}
 POOL = 16  # distinct query batches cycled through the steps
 
 
@@ -163,6 +165,7 @@ def run_ours(args):
         st, retr, rps, lo, hi = get_store(n_rows, kind)
         q, ex = make_queries(st, nq, seed=100 + nq)
         gather = name == "c4"
+        spath = PATHS.get(name, "auto")
         ctx = None
         if gather:
             n_feat = 65_536                    # feature rows kept resident for the gather (3.4 GB bf16)
@@ -176,9 +179,9 @@ def run_ours(args):
         def step(i, timings=None):
             j = i % POOL
             if timings is not None and world == 1:
-                r = st.search(q[j], TOPK, exclude_group=ex[j], filter_mode="post", timings=timings)
+                r = st.search(q[j], TOPK, path=spath, exclude_group=ex[j], filter_mode="post", timings=timings)
             else:
-                r = retr.search(q[j], TOPK, exclude_group=ex[j], filter_mode="post")
+                r = retr.search(q[j], TOPK, path=spath, exclude_group=ex[j], filter_mode="post")
             if gather:
                 ref = torch.where(r.index[:, :K_REF] >= 0, r.index[:, :K_REF] % n_feat, r.index[:, :K_REF])
                 return ctx.build(ref.contiguous(), cond)
@@ -223,9 +226,9 @@ def run_ours(args):
         # roofline of the dominant (scan) kernel: event-bracketed launches on this rank's shard
         tm = []
         for i in range(min(steps, 50)):
-            st.search(q[i % POOL], TOPK, exclude_group=ex[i % POOL], filter_mode="post", timings=tm)
+            st.search(q[i % POOL], TOPK, path=spath, exclude_group=ex[i % POOL], filter_mode="post", timings=tm)
         scan_ms = allmax(statistics.mean(t[0] for t in tm))
-        plan = st.plan(nq, k=TOPK, filter_mode="post")
+        plan = st.plan(nq, k=TOPK, filter_mode="post", path=spath)
         if plan.path == 3:
             ach = plan.scan_flops / (scan_ms / 1e3) / 1e12
             peak = pk["bf16_tflops_sustained"] if steps * scan_ms > 2000 else pk["bf16_tflops"]
@@ -240,7 +243,7 @@ def run_ours(args):
             ach = plan.scan_bytes / (scan_ms / 1e3) / 1e9
             out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                "frac": ach / pk["hbm_gbs"], "traffic": ncu_traffic(name) if world == 1 else None,
-                               "kernel": "k1_stream_kernel<float>",
+                               "kernel": "k1_stream_kernel<float>" if plan.path == 1 else "k1_stream_kernel<bf16>",
                                "kernel_ms": scan_ms, "kernel_share_of_step": scan_ms / (ms_total / steps),
                                "peak_source": pk["source"], "bytes_per_launch": plan.scan_bytes,
                                "plan": {"grid": plan.grid, "cands_per_query": plan.cands_per_query}}
@@ -252,7 +255,7 @@ def run_ours(args):
         if with_e2e:
             q_host = q.cpu().pin_memory()
             ex_host = ex.cpu().pin_memory()
-            if world == 1 and not gather and nq == 1:
+            if world == 1 and not gather and nq == 1 and spath == "auto":
                 # the reference-facing call itself: RAGDatabase.text_search(ndarray) -> list[dict]
                 videos = [f"video_{j // 3:07d}.mp4" for j in range(n_rows)]
                 import numpy as np
@@ -271,7 +274,7 @@ def run_ours(args):
                     j = i % POOL
                     qd = q_host[j].to(dev, non_blocking=True)
                     exd = ex_host[j].to(dev, non_blocking=True)
-                    r = retr.search(qd, TOPK, exclude_group=exd, filter_mode="post")
+                    r = retr.search(qd, TOPK, path=spath, exclude_group=exd, filter_mode="post")
                     if gather:
                         ref = torch.where(r.index[:, :K_REF] >= 0, r.index[:, :K_REF] % n_feat, r.index[:, :K_REF])
                         x = ctx.build(ref.contiguous(), cond)
@@ -291,16 +294,55 @@ def run_ours(args):
                           "h2d_bytes_per_step": nq * (DIM * 4 + 4), "d2h_bytes_per_step": d2h, "api": api}
         return out
 
+    def measure_gather(b=4096, steps=20, warmup=3):
+        """K4 alone at bulk size: feature rows -> [b,250,1024] bf16 context with +pe and +cond fused.
+        Bytes per sample: 9 rows x 51 200 B read + 512 000 B cond read + 512 000 B written."""
+        for old in list(stores):
+            stores.pop(old)[0].close()
+        torch.cuda.empty_cache()
+        n_feat = 65_536
+        table = synthetic.features(n_feat, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev)
+        gg = torch.Generator(device=dev).manual_seed(4)
+        sos = (torch.randn(1, L_TOK, C_FEAT, generator=gg, device=dev) / 32).bfloat16()
+        un = torch.randn(L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
+        cond = torch.randn(b, (K_REF + 1) * L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
+        idx = torch.randint(0, n_feat, (4, b, K_REF), generator=gg, device=dev)
+        idx[:, ::7, 3] = -1
+        ctx = m.MotionContext(m.FeatureTable(table), sos, un, pe_max_length=256)
+        out = torch.empty(b, (K_REF + 1) * L_TOK, C_FEAT, dtype=torch.bfloat16, device=dev)
+        for i in range(warmup):
+            ctx.build(idx[i % 4], cond, out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            ctx.build(idx[i % 4], cond, out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        row = L_TOK * C_FEAT * 2
+        nbytes = b * (K_REF * row + 2 * (K_REF + 1) * row)
+        ach = nbytes / (ms / 1e3) / 1e9
+        return {"workload": f"K4 gather_context b={b}, K=9, +pe +cond fused, bf16", "ms_per_step": ms,
+                "value": b / (ms / 1e3), "unit": "samples/s",
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / pk["hbm_gbs"], "bytes_per_launch": nbytes, "kernel": "k4_gather_kernel<bf16>"}}
+
     main = measure(args.workload, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
     extra = {}
     if not args.no_extras:
-        todo = [w for w in ("c1", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
+        todo = [w for w in ("c1", "c1b", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
         for w in todo:
             try:
                 steps = 200 if WORKLOADS[w][1] == 1 else (30 if WORKLOADS[w][1] <= 16 else 8)
                 extra[w] = measure(w, steps, 3, with_e2e=(w in ("c2", "c4")))
             except Exception as e:  # an extra must never take the headline line down
                 extra[w] = {"error": f"{type(e).__name__}: {e}"}
+        if world == 1:
+            try:
+                extra["k4_gather"] = measure_gather()
+            except Exception as e:
+                extra["k4_gather"] = {"error": f"{type(e).__name__}: {e}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

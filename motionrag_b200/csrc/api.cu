@@ -108,7 +108,8 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
     return fail(MRAG_ERR_ARG, "unknown filter_mode %d", p->filter_mode);
   if (s->n_rows < 1) return fail(MRAG_ERR_ARG, "store is empty");
   int path = p->path;
-  if (path == MRAG_PATH_AUTO) path = (nq <= 4) ? MRAG_PATH_STREAM_F32 : MRAG_PATH_TENSOR_BF16;
+  if (path == MRAG_PATH_AUTO)
+    path = (nq <= 4 && k1_supported(s->dim, nq)) ? MRAG_PATH_STREAM_F32 : MRAG_PATH_TENSOR_BF16;
   int refine = p->refine > 0 ? p->refine : 32;
   if (refine < p->k) refine = p->k;
   if (refine > 64) refine = 64;

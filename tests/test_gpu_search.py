@@ -182,6 +182,37 @@ def test_tiny_tables_pad_with_minus_one(n, path, nq):
     st.close()
 
 
+@pytest.mark.parametrize("dim", [256, 512, 1024])
+@pytest.mark.parametrize("path,nq", [("stream_f32", 3), ("stream_bf16", 2), ("tensor_bf16", 70)])
+def test_other_embedding_widths(dim, path, nq):
+    """dim is a store property (gte-base is 768; the image column of rag.py:82-99 may differ)."""
+    from motionrag_b200 import EmbeddingStore
+    rng = np.random.default_rng(dim)
+    n = 3001
+    db = fs.normalise_rows(rng.standard_normal((n, dim)).astype(np.float32))
+    q = (db[rng.integers(0, n, nq)] + 0.02 * rng.standard_normal((nq, dim)).astype(np.float32)) * 7
+    st = EmbeddingStore(dim, n, 0)
+    st.append(db, normalise=False)
+    res = st.search(torch.from_numpy(q.astype(np.float32)).cuda(), 12, path=path)
+    rd, ri = fs.flat_search(db, q, 12)
+    compare.check_retrieval(res.distance.cpu().numpy(), res.index.cpu().numpy(), rd, ri, db, q)
+    st.close()
+
+
+def test_unsupported_width_is_loud():
+    from motionrag_b200 import EmbeddingStore, MragError
+    with pytest.raises(MragError, match="dim must be"):
+        EmbeddingStore(100, 10, 0)
+    st = EmbeddingStore(320, 10, 0)                      # tensor path handles any multiple of 64 ...
+    st.append(np.random.default_rng(0).standard_normal((10, 320)).astype(np.float32))
+    q = torch.randn(9, 320).cuda()
+    assert st.search(q, 3).index.shape == (9, 3)
+    assert st.plan(1, k=3).path == 3                      # ... and AUTO routes around the streaming kernels,
+    with pytest.raises(MragError, match="streaming path"):  # which are instantiated per width
+        st.search(q[:1].contiguous(), 3, path="stream_f32")
+    st.close()
+
+
 def test_store_normalises_on_upload():
     from motionrag_b200 import EmbeddingStore
     raw = np.random.default_rng(1).standard_normal((1000, 512)).astype(np.float32) * 5

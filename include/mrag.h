@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MRAG_ABI_VERSION 1
+#define MRAG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MRAG_API __attribute__((visibility("default")))
@@ -54,8 +54,8 @@ typedef enum mrag_metric {
 
 /* which scan kernel serves the query batch */
 typedef enum mrag_path {
-  MRAG_PATH_AUTO = 0,        /* nq <= 4 (and dim in {256,512,768,1024}): STREAM_F32, else TENSOR_BF16 */
-  MRAG_PATH_STREAM_F32 = 1,  /* K1 on the fp32 master rows (exact ranking, 4 B/elt streamed) */
+  MRAG_PATH_AUTO = 0,        /* nq <= 4 (and dim in {256,512,768,1024}): STREAM_BF16, else TENSOR_BF16 */
+  MRAG_PATH_STREAM_F32 = 1,  /* K1 on the fp32 master rows (ranking exact in fp32, 4 B/elt streamed) */
   MRAG_PATH_STREAM_BF16 = 2, /* K1 on the bf16 shadow rows + fp32 re-rank (2 B/elt streamed) */
   MRAG_PATH_TENSOR_BF16 = 3  /* K2 tcgen05 GEMM with fused epilogue top-k + fp32 re-rank */
 } mrag_path;
@@ -90,6 +90,15 @@ typedef struct mrag_search_params {
   int32_t filter_mode; /* mrag_filter; needs store groups + exclude_group */
   int32_t reserved;
   int64_t index_base;  /* added to local row numbers in out_idx (row-sharded stores) */
+  /* optional output, float[nq] (device memory for mrag_search*, host memory for
+   * mrag_search_host; NULL = not wanted): exactness certificate of the bf16 scan paths.
+   *   margin = (true q.d of the k-th result - bf16 score of the weakest re-ranked candidate) / |q|
+   * Every row that was NOT re-ranked has a bf16 score <= that weakest candidate, and for unit
+   * rows |bf16 score - true q.d| <= eps |q| with eps = 2^-9 (STREAM_BF16: rows rounded) or
+   * 2^-8 (TENSOR_BF16: rows and queries rounded). Hence margin > eps proves the returned
+   * top-k is the exact fp32 top-k; otherwise re-issue that query with MRAG_PATH_STREAM_F32.
+   * +inf when everything was re-ranked; NaN for MRAG_FILTER_PRE and for sharded searches. */
+  float* out_margin;
 } mrag_search_params;
 
 MRAG_API int mrag_abi_version(void);

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "libmrag.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of include/mrag.h
 METRIC = {"l2": 0, "cosine": 1, "dot": 2}
@@ -38,7 +38,7 @@ class StoreInfo(C.Structure):
 class SearchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("metric", C.c_int32), ("path", C.c_int32),
                 ("refine", C.c_int32), ("filter_mode", C.c_int32), ("reserved", C.c_int32),
-                ("index_base", C.c_int64)]
+                ("index_base", C.c_int64), ("out_margin", C.c_void_p)]
 
 
 class PlanInfo(C.Structure):

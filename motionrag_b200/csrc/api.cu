@@ -108,8 +108,10 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
     return fail(MRAG_ERR_ARG, "unknown filter_mode %d", p->filter_mode);
   if (s->n_rows < 1) return fail(MRAG_ERR_ARG, "store is empty");
   int path = p->path;
+  // AUTO: scan the bf16 shadow (half the bytes), re-rank the candidates in fp32 from the master
+  // rows — the role refine_factor plays in the reference's own call (src/data/rag.py:54)
   if (path == MRAG_PATH_AUTO)
-    path = (nq <= 4 && k1_supported(s->dim, nq)) ? MRAG_PATH_STREAM_F32 : MRAG_PATH_TENSOR_BF16;
+    path = (nq <= 4 && k1_supported(s->dim, nq)) ? MRAG_PATH_STREAM_BF16 : MRAG_PATH_TENSOR_BF16;
   int refine = p->refine > 0 ? p->refine : 32;
   if (refine < p->k) refine = p->k;
   if (refine > 64) refine = 64;
@@ -126,7 +128,9 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
       pl.rerank = pl.kc;
     } else {
       pl.kc = 32;
-      pl.rerank = f32 ? (refine > 32 ? 32 : refine) : refine;
+      // never re-rank more than a run holds: only then is the re-ranked set exactly the global
+      // top-`rerank` by scan score, which the exactness certificate (out_margin) relies on
+      pl.rerank = refine > 32 ? 32 : refine;
     }
     pl.k1_grid = k1_grid(s->n_rows, f32 ? 4 : 2, s->dim, nq, s->sm_count);
     pl.cands_per_query = pl.k1_grid * pl.kc;
@@ -376,7 +380,7 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
   }
   CK(launch_k3_merge_rerank(cand, pl.cands_per_query / pl.kc, pl.kc, s->rows_f32, s->dim, queries_dev, nq, groups,
                             exclude_group_dev, fm, p->metric, pl.rerank, p->k, p->index_base,
-                            out_dist_dev, out_idx_dev, out_group_dev, xd_ptr, st));
+                            out_dist_dev, out_idx_dev, out_group_dev, p->out_margin, xd_ptr, st));
   return MRAG_OK;
 }
 
@@ -452,7 +456,8 @@ int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
   const size_t q_raw = size_t(nq) * s->dim * 4, ex_raw = size_t(nq) * 4;
   const size_t in_bytes = align_up(q_raw + ex_raw, 256);
   const size_t nk = size_t(nq) * p->k;
-  const size_t out_raw = nk * 16;  // idx i64 | dist f32 | group i32
+  const bool want_margin = p->out_margin != nullptr;
+  const size_t out_raw = nk * 16 + size_t(nq) * 4;  // idx i64 | dist f32 | group i32 | margin f32
   const size_t out_bytes = align_up(out_raw, 256);
   const size_t total = in_bytes + out_bytes + pl.total;
   if (s->host_dev_bytes < total) {
@@ -469,7 +474,9 @@ int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
   int64_t* oi_d = reinterpret_cast<int64_t*>(base + in_bytes);
   float* od_d = reinterpret_cast<float*>(base + in_bytes + nk * 8);
   int32_t* og_d = reinterpret_cast<int32_t*>(base + in_bytes + nk * 12);
+  float* om_d = reinterpret_cast<float*>(base + in_bytes + nk * 16);
   void* ws = base + in_bytes + out_bytes;
+  mrag_search_params pd = *p;   // device-side view of the parameters (margin pointer swapped)
   // small transfers go through pinned staging (truly asynchronous, one copy each way)
   const bool staged = (q_raw + ex_raw) <= (256u << 10) && out_raw <= (256u << 10);
   if (staged && s->host_pin_bytes < (512u << 10)) {
@@ -490,7 +497,8 @@ int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
     char* pin_out = s->host_pin + (256u << 10);
     CK(cudaEventRecord(s->host_event, st));  // order after the caller's pending work (appends)
     CK(cudaStreamWaitEvent(hs, s->host_event, 0));
-    const int has_ex = exclude_group_host ? 1 : 0;
+    const int has_ex = (exclude_group_host ? 1 : 0) | (want_margin ? 2 : 0);
+    pd.out_margin = want_margin ? reinterpret_cast<float*>(pin_out + nk * 16) : nullptr;
     cudaGraphExec_t exec = nullptr;
     // (the graph bakes in nk-dependent result offsets: nq and k are part of the key)
     for (auto& hg : s->host_graphs)
@@ -500,12 +508,12 @@ int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
         exec = hg.exec;
     if (!exec) {
       CK(cudaStreamBeginCapture(hs, cudaStreamCaptureModeThreadLocal));
-      e = cudaMemcpyAsync(base, s->host_pin, q_raw + (has_ex ? ex_raw : 0), cudaMemcpyHostToDevice, hs);
+      e = cudaMemcpyAsync(base, s->host_pin, q_raw + (exclude_group_host ? ex_raw : 0), cudaMemcpyHostToDevice, hs);
       int crc = MRAG_OK;
       // results are written by K3 straight into the pinned block (zero-copy stores over PCIe):
       // no device->host copy node, the graph ends with the kernel
       if (e == cudaSuccess)
-        crc = search_impl(s, q_d, nq, p, has_ex ? ex_d : nullptr,
+        crc = search_impl(s, q_d, nq, &pd, exclude_group_host ? ex_d : nullptr,
                           reinterpret_cast<float*>(pin_out + nk * 8),
                           reinterpret_cast<int64_t*>(pin_out),
                           reinterpret_cast<int32_t*>(pin_out + nk * 12), ws, pl.total, hs, nullptr,
@@ -534,16 +542,20 @@ int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
     memcpy(out_idx_host, pin_out, nk * 8);
     memcpy(out_dist_host, pin_out + nk * 8, nk * 4);
     if (out_group_host) memcpy(out_group_host, pin_out + nk * 12, nk * 4);
+    if (want_margin) memcpy(p->out_margin, pin_out + nk * 16, size_t(nq) * 4);
     return MRAG_OK;
   }
+  pd.out_margin = want_margin ? om_d : nullptr;
   e = cudaMemcpyAsync(q_d, queries_host, q_raw, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess && exclude_group_host)
     e = cudaMemcpyAsync(ex_d, exclude_group_host, ex_raw, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
-  rc = mrag_search(s, q_d, nq, p, exclude_group_host ? ex_d : nullptr, od_d, oi_d, og_d, ws,
+  rc = mrag_search(s, q_d, nq, &pd, exclude_group_host ? ex_d : nullptr, od_d, oi_d, og_d, ws,
                    pl.total, stream);
   if (rc != MRAG_OK) return rc;
   e = cudaMemcpyAsync(out_idx_host, oi_d, nk * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && want_margin)
+    e = cudaMemcpyAsync(p->out_margin, om_d, size_t(nq) * 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist_host, od_d, nk * 4, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && out_group_host)
     e = cudaMemcpyAsync(out_group_host, og_d, nk * 4, cudaMemcpyDeviceToHost, st);

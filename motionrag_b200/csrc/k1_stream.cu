@@ -192,7 +192,7 @@ struct K1Variant {
   int r, minb;
 };
 static const K1Variant kVariantsF32[] = {{2, 2}, {4, 2}, {2, 3}, {2, 4}, {1, 4}, {3, 2}};
-static const K1Variant kVariantsBF16[] = {{4, 3}, {8, 2}, {4, 2}, {4, 4}, {2, 4}, {6, 2}};
+static const K1Variant kVariantsBF16[] = {{6, 2}, {8, 2}, {4, 2}, {4, 4}, {2, 4}, {4, 3}};
 
 static int k1_variant_index() {
   const char* e = getenv("MRAG_K1_VARIANT");
@@ -225,10 +225,11 @@ static cudaError_t launch_one(const void* db, int64_t n_rows, const float* queri
       case 2: return launch_cfg<T, D, Q, F ? 2 : 4, F ? 3 : 2>(db, n_rows, queries, cand, kc, grid, st);
       case 3: return launch_cfg<T, D, Q, F ? 2 : 4, 4>(db, n_rows, queries, cand, kc, grid, st);
       case 4: return launch_cfg<T, D, Q, F ? 1 : 2, 4>(db, n_rows, queries, cand, kc, grid, st);
-      case 5: return launch_cfg<T, D, Q, F ? 3 : 6, 2>(db, n_rows, queries, cand, kc, grid, st);
+      case 5: return launch_cfg<T, D, Q, F ? 3 : 4, F ? 2 : 3>(db, n_rows, queries, cand, kc, grid, st);
       default: break;
     }
   }
+  if constexpr (D == 768 && Q == 1) return launch_cfg<T, D, Q, F ? 2 : 6, 2>(db, n_rows, queries, cand, kc, grid, st);
   return launch_cfg<T, D, Q, F ? 2 : 4, F ? 2 : 3>(db, n_rows, queries, cand, kc, grid, st);
 }
 
@@ -261,8 +262,9 @@ bool k1_supported(int dim, int nq) {
 }
 
 int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count) {
+  // the headline shape (768-d, one query) has tuned variants; other shapes use (2,2) / (4,3)
   K1Variant v = (dim == 768 && nq == 1) ? k1_variant(elt_bytes)
-                                        : (elt_bytes == 4 ? kVariantsF32[0] : kVariantsBF16[0]);
+                                        : (elt_bytes == 4 ? K1Variant{2, 2} : K1Variant{4, 3});
   const int64_t quantum = int64_t(kK1Warps) * v.r;
   // one resident wave; small tables get fewer CTAs
   int64_t want = (n_rows + quantum - 1) / quantum;

@@ -189,11 +189,14 @@ __global__ void __launch_bounds__(kK3Threads)
                            const int32_t* __restrict__ exclude_group, int filter_mode, int metric,
                            int rerank, int k, int64_t index_base, float* __restrict__ out_dist,
                            int64_t* __restrict__ out_idx, int32_t* __restrict__ out_group,
-                           const XchgArgs x) {
+                           float* __restrict__ out_margin, const XchgArgs x) {
   __shared__ uint64_t heads[kMaxRuns];      // run heads, unsorted (index = run)
   __shared__ uint64_t sorted_heads[kMaxRuns];
   __shared__ uint64_t sel[kMaxSel];
   __shared__ uint64_t rr_keys[kMaxRerank];  // (ordered distance << 32) | local row
+  __shared__ float rr_dot[kMaxRerank];      // true q.d of candidate slot c
+  __shared__ uint32_t rr_row[kMaxRerank];   // local row of candidate slot c
+  __shared__ float q_norm_s;
   __shared__ int n_sel_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = blockIdx.x;
@@ -271,9 +274,34 @@ __global__ void __launch_bounds__(kK3Threads)
     if (metric == 0) dist = l2;
     else if (metric == 1) dist = 1.f - dot / fmaxf(sqrtf(qq) * sqrtf(dd), 1e-30f);
     else dist = 1.f - dot;
-    if (lane == 0) rr_keys[c] = (uint64_t(f32_to_ordered(dist)) << 32) | idx;
+    if (lane == 0) {
+      rr_keys[c] = (uint64_t(f32_to_ordered(dist)) << 32) | idx;
+      rr_dot[c] = dot;
+      rr_row[c] = idx;
+      if (c == 0) q_norm_s = sqrtf(qq);
+    }
   }
   bitonic_sort_smem(rr_keys, kMaxRerank, tid, kK3Threads);
+
+  // exactness certificate of the bf16 scan (see mrag_search_params.out_margin)
+  if (out_margin != nullptr && tid == 0) {
+    float margin = INFINITY;
+    if (x.world > 1 || filter_mode == 2) {
+      margin = __int_as_float(0x7fc00000);  // NaN: not defined for sharded / pre-filtered searches
+    } else if (n_rr == rerank && n_rr > 0) {
+      // rows outside the re-ranked set may exist (with fewer than `rerank` candidates no run was
+      // full, so every row was a candidate and was re-ranked): the re-ranked set is the global
+      // top-`rerank` by scan score (rerank <= run length), so their score is <= the weakest one
+      const float weakest = sim_key_score(sel[n_rr - 1]);
+      const int kth = min(k, n_rr) - 1;
+      const uint32_t row = uint32_t(rr_keys[kth]);
+      float dk = -INFINITY;
+      for (int c = 0; c < n_rr; ++c)
+        if (rr_row[c] == row) dk = rr_dot[c];
+      margin = (dk - weakest) / fmaxf(q_norm_s, 1e-30f);
+    }
+    out_margin[q] = margin;
+  }
 
   const int exclude = (exclude_group != nullptr) ? exclude_group[q] : -1;
   auto entry = [&](int j, bool in_range) {
@@ -380,7 +408,8 @@ cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len
                                    const int32_t* row_group, const int32_t* exclude_group,
                                    int filter_mode, int metric, int rerank, int k,
                                    int64_t index_base, float* out_dist, int64_t* out_idx,
-                                   int32_t* out_group, const ExchangeDesc* xd, cudaStream_t st) {
+                                   int32_t* out_group, float* out_margin, const ExchangeDesc* xd,
+                                   cudaStream_t st) {
   XchgArgs x{};
   if (xd != nullptr && xd->world > 1) {
     if (nq > xd->nq_cap || k > xd->k_cap || xd->k_cap > 32 || xd->world * k > 256)
@@ -398,7 +427,7 @@ cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len
   k3_merge_rerank_kernel<<<nq, kK3Threads, 0, st>>>(cand, n_runs, run_len, db_f32, dim, queries,
                                                     row_group, exclude_group, filter_mode, metric,
                                                     rerank, k, index_base, out_dist, out_idx,
-                                                    out_group, x);
+                                                    out_group, out_margin, x);
   note_launch();
   return cudaGetLastError();
 }

@@ -64,7 +64,8 @@ cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len
                                    const int32_t* row_group, const int32_t* exclude_group,
                                    int filter_mode, int metric, int rerank, int k,
                                    int64_t index_base, float* out_dist, int64_t* out_idx,
-                                   int32_t* out_group, const ExchangeDesc* xd, cudaStream_t st);
+                                   int32_t* out_group, float* out_margin, const ExchangeDesc* xd,
+                                   cudaStream_t st);
 cudaError_t launch_k3_merge_shards(const float* cand_dist, const int64_t* cand_idx,
                                    const int32_t* cand_group, int64_t shard_stride_bytes,
                                    int nshards, int nq, int k_in,

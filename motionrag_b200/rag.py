@@ -308,8 +308,14 @@ class RAGDatabase:
             if q.ndim != 2:
                 raise ValueError(f"query must be [dim] or [nq, dim], got {tuple(q.shape)}")
             excl = self._exclusion_ids(where, q.shape[0])
-            dist, idx, _ = store.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
-                                             exclude_group=excl, filter_mode=mode)
+            if self.path == "stream_f32" or self.prefilter:
+                dist, idx, _ = store.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
+                                                 exclude_group=excl, filter_mode=mode)
+                return dist, idx, single
+            dist, idx, _, margin = store.search_host(q, int(top_k), metric=self.metric, path=self.path,
+                                                     refine=refine, exclude_group=excl, filter_mode=mode,
+                                                     certify=True)
+            self._recheck(store, q, excl, dist, idx, margin, top_k, mode)
             return dist, idx, single
         q, single = self._as_queries(vector)
         excl = self._exclusion_ids(where, q.shape[0])
@@ -317,6 +323,19 @@ class RAGDatabase:
         res = store.search(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
                            exclude_group=excl_d, filter_mode=mode)
         return res.distance.cpu().numpy(), res.index.cpu().numpy(), single
+
+    def _recheck(self, store, q, excl, dist, idx, margin, top_k, mode) -> None:
+        """Queries whose bf16-scan result is not certified exact (margin <= eps, see mrag.h) are
+        re-run on the fp32 master rows, 4 per pass; results are patched in place."""
+        from .store import EPS
+        eps = EPS["stream_bf16"] if (q.shape[0] <= 4 and self.path != "tensor_bf16") else EPS["tensor_bf16"]
+        doubt = np.nonzero(~(margin > eps))[0]          # NaN counts as doubt
+        self.fp32_rechecks = getattr(self, "fp32_rechecks", 0) + int(doubt.size)
+        for s in range(0, doubt.size, 4):
+            rows = doubt[s:s + 4]
+            d2, i2, _ = store.search_host(q[rows], int(top_k), metric=self.metric, path="stream_f32",
+                                          exclude_group=None if excl is None else excl[rows], filter_mode=mode)
+            dist[rows], idx[rows] = d2, i2
 
     def vector_search(self, vector, vector_column_name: str = None, top_k: int = 10, table=None,
                       where: str = None, select: list[str] = None, nprobes: int = 50, refine_factor: int = 30,

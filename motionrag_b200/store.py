@@ -29,6 +29,11 @@ class SearchResult:
     distance: torch.Tensor  # float32, ascending
     index: torch.Tensor     # int64 global row ids
     group: torch.Tensor     # int32 group id of each hit
+    margin: torch.Tensor | None = None  # float32 [nq] exactness certificate (see EPS / mrag.h)
+
+
+# |bf16 scan score - true q.d| <= EPS[path] * |q| for unit rows: margin > EPS proves exactness
+EPS = {"stream_f32": 0.0, "stream_bf16": 2.0 ** -9, "tensor_bf16": 2.0 ** -8}
 
 
 class EmbeddingStore:
@@ -107,7 +112,8 @@ class EmbeddingStore:
     # -- search -----------------------------------------------------------------------------
     def _params(self, k, metric, path, refine, filter_mode, index_base) -> SearchParams:
         return SearchParams(k=int(k), metric=METRIC[metric], path=PATH[path], refine=int(refine),
-                            filter_mode=FILTER[filter_mode], reserved=0, index_base=int(index_base))
+                            filter_mode=FILTER[filter_mode], reserved=0, index_base=int(index_base),
+                            out_margin=None)
 
     def plan(self, nq: int, params: SearchParams | None = None, **kw) -> PlanInfo:
         """How a search of nq queries would run (path, grid, candidates, workspace, work)."""
@@ -123,7 +129,7 @@ class EmbeddingStore:
                refine: int = 0, exclude_group: torch.Tensor | None = None,
                filter_mode: str = "post", index_base: int = 0,
                out: SearchResult | None = None, timings: list | None = None,
-               exchange=None) -> SearchResult:
+               exchange=None, certify: bool = False) -> SearchResult:
         """Device-resident search: queries [nq, dim] fp32 on this store's GPU -> SearchResult.
 
         Asynchronous on the current stream; nothing is copied to the host.
@@ -137,6 +143,9 @@ class EmbeddingStore:
             raise ValueError("exclude_group must be int32 on the store's device")
         p = self._params(k, metric, path, refine, filter_mode, index_base)
         need = int(self.plan(nq, p).workspace_bytes)
+        if certify:
+            out_margin = torch.empty(nq, dtype=torch.float32, device=self.device)
+            p.out_margin = out_margin.data_ptr()
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         if out is None:
@@ -156,14 +165,17 @@ class EmbeddingStore:
             a, b = C.c_float(), C.c_float()
             check(self._lib.mrag_search_timed(*args, C.byref(a), C.byref(b)))
             timings.append((a.value, b.value))
+        if certify:
+            out.margin = out_margin
         return out
 
     def search_host(self, queries: np.ndarray, k: int, *, metric: str = "l2", path: str = "auto",
                     refine: int = 0, exclude_group: np.ndarray | None = None,
-                    filter_mode: str = "post", index_base: int = 0):
+                    filter_mode: str = "post", index_base: int = 0, certify: bool = False):
         """Host-buffer search through `mrag_search_host` (copies inside, synchronous).
 
-        Returns (distance f32 [nq,k], index i64 [nq,k], group i32 [nq,k]) numpy arrays.
+        Returns (distance f32 [nq,k], index i64 [nq,k], group i32 [nq,k]) numpy arrays, plus the
+        float32 [nq] exactness margin when certify=True.
         """
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim != 2 or q.shape[1] != self.dim:
@@ -178,11 +190,17 @@ class EmbeddingStore:
         dist = np.empty((nq, k), dtype=np.float32)
         idx = np.empty((nq, k), dtype=np.int64)
         grp = np.empty((nq, k), dtype=np.int32)
+        margin = None
+        if certify:
+            margin = np.empty(nq, dtype=np.float32)
+            p.out_margin = margin.ctypes.data
         check(self._lib.mrag_search_host(
             self._h, q.ctypes.data_as(C.c_void_p), nq, C.byref(p),
             ex.ctypes.data_as(C.c_void_p) if ex is not None else None,
             dist.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p),
             grp.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)))
+        if certify:
+            return dist, idx, grp, margin
         return dist, idx, grp
 
 

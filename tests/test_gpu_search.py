@@ -90,10 +90,10 @@ def test_video_exclusion_filter(case, path, nq, filt):
 
 def test_auto_path_dispatch(case):
     st = case["store"]
-    assert st.plan(1, k=12).path == 1 and st.plan(4, k=12).path == 1 and st.plan(5, k=12).path == 3
-    p = st.plan(1, k=12)
+    assert st.plan(1, k=12).path == 2 and st.plan(4, k=12).path == 2 and st.plan(5, k=12).path == 3
+    p = st.plan(1, k=12, path="stream_f32")
     assert p.scan_bytes == case["n"] * 768 * 4 and p.cands_per_query == p.grid * 16
-    assert st.plan(1, k=12, path="stream_bf16").scan_bytes == case["n"] * 768 * 2
+    assert st.plan(1, k=12).scan_bytes == case["n"] * 768 * 2 and st.plan(1, k=12).cands_per_query == st.plan(1, k=12).grid * 32
     p2 = st.plan(4096, k=12)
     assert p2.m_tiles == 32 and p2.n_tiles == (case["n"] + 255) // 256 and p2.scan_flops == 2 * 4096 * case["n"] * 768
 
@@ -121,6 +121,65 @@ def test_host_buffer_path_replays_and_matches_oracle(case, nq, path):
     case["store"].set_groups(case["groups"])          # drops cached graphs
     d2, i2, _ = case["store"].search_host(q, 12, path=path, exclude_group=ex)
     np.testing.assert_array_equal(i2, i)
+
+
+def _bf16_round(a):
+    return torch.from_numpy(a).bfloat16().float().numpy()
+
+
+@pytest.mark.parametrize("path,nq,rr", [("stream_bf16", 3, 32), ("tensor_bf16", 40, 16), ("tensor_bf16", 200, 16)])
+def test_exactness_margin_matches_its_definition(case, path, nq, rr):
+    """margin = (true q.d of the k-th hit - scan score of the weakest re-ranked row) / |q|."""
+    from motionrag_b200.store import EPS
+    q = case["q"][50:50 + nq]
+    res = case["store"].search(torch.from_numpy(q).cuda(), 12, path=path, certify=True)
+    m = res.margin.cpu().numpy()
+    db16 = _bf16_round(case["db"])
+    q16 = _bf16_round(q) if path == "tensor_bf16" else q
+    scan = (q16.astype(np.float64) @ db16.T.astype(np.float64))
+    true = (q.astype(np.float64) @ case["db"].T.astype(np.float64))
+    idx = res.index.cpu().numpy()
+    for r in range(nq):
+        weakest = np.sort(scan[r])[::-1][rr - 1]
+        want = (true[r, idx[r, 11]] - weakest) / np.linalg.norm(q[r])
+        assert m[r] == pytest.approx(want, abs=2e-4), (r, m[r], want)
+    assert np.all(m > EPS[path])                     # well-separated synthetic data certifies
+    # the fp32 stream has nothing to certify against rounding: margins are >= 0 by construction
+    r32 = case["store"].search(torch.from_numpy(q[:4]).cuda(), 12, path="stream_f32", certify=True)
+    assert bool((r32.margin >= 0).all())
+
+
+def test_uncertified_queries_fall_back_to_the_fp32_scan():
+    """Rows that differ only below bf16 resolution: the bf16 scan cannot rank them, the margin
+    says so, and RAGDatabase re-runs those queries on the fp32 master rows -> exact answer."""
+    from motionrag_b200 import EmbeddingStore, RAGDatabase
+    from motionrag_b200.store import EPS
+    rng = np.random.default_rng(0)
+    n, dim = 4000, 768
+    base = fs.normalise_rows(rng.standard_normal((1, dim)).astype(np.float32))[0]
+    db = fs.normalise_rows(rng.standard_normal((n, dim)).astype(np.float32))
+    twins = rng.choice(n, 200, replace=False)
+    db[twins] = fs.normalise_rows(base[None] + 3e-3 / np.sqrt(dim) * rng.standard_normal((200, dim)).astype(np.float32))
+    q = (base * 9).astype(np.float32)[None]
+    st = EmbeddingStore(dim, n, 0)
+    st.append(db, normalise=False)
+    res = st.search(torch.from_numpy(q).cuda(), 12, path="stream_bf16", certify=True)
+    assert float(res.margin[0]) <= EPS["stream_bf16"]                       # flagged
+    cols = {"text_embedding": db, "video": np.array([f"v{j}" for j in range(n)])}
+    rdb = RAGDatabase(None, None, columns=cols)
+    got = rdb.text_search(q[0], top_k=12, select=["video"])
+    rd, ri = fs.flat_search(db, q, 12)
+    assert rdb.fp32_rechecks == 1
+    rep = compare.check_retrieval(np.array([[r["_distance"] for r in got]]),
+                                  np.array([[int(r["video"][1:]) for r in got]]), rd, ri, db, q)
+    assert rep["positions"] == 12
+    exact_set = set(ri[0].tolist())
+    assert len(exact_set & {int(r["video"][1:]) for r in got}) >= 10        # fp32 resolves the twins ...
+    assert len(exact_set & set(res.index[0].tolist())) <= 8                 # ... the bf16 scan alone cannot
+    # an ordinary query on the same table is certified and does not pay the second scan
+    got2 = rdb.text_search(db[7] * 3, top_k=5, select=["video"])
+    assert got2[0]["video"] == "v7" and rdb.fp32_rechecks == 1
+    st.close()
 
 
 def test_index_base_offsets_global_ids(case):

@@ -82,6 +82,26 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* keys, int n, int tid
   __syncthreads();
 }
 
+// ---- barrier-light sort of a small key array: rank by counting -----------------------------------
+// Thread i (i < n) counts the keys that precede its own (ties by position) and writes its key
+// to that rank in `out`. n iterations of a broadcast smem read, two block barriers in total —
+// for n <= a few hundred this beats the ~log^2(n) barriers of the bitonic network. `out` must
+// not alias `keys`; entries >= n of `out` are left untouched.
+__device__ __forceinline__ void rank_sort_smem(const uint64_t* keys, uint64_t* out, int n, int tid,
+                                               int nthreads) {
+  __syncthreads();
+  for (int i = tid; i < n; i += nthreads) {
+    const uint64_t mine = keys[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const uint64_t o = keys[j];
+      r += (o < mine) || (o == mine && j < i);
+    }
+    out[r] = mine;
+  }
+  __syncthreads();
+}
+
 // ---- mbarrier / TMA / tcgen05 wrappers ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

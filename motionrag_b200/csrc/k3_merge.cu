@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(kK3Threads)
                            int rerank, int k, int64_t index_base, float* __restrict__ out_dist,
                            int64_t* __restrict__ out_idx, int32_t* __restrict__ out_group,
                            float* __restrict__ out_margin, const XchgArgs x) {
-  __shared__ uint64_t heads[kMaxRuns];      // run heads, unsorted (index = run)
-  __shared__ uint64_t sorted_heads[kMaxRuns];
+  __shared__ uint64_t heads[kMaxRuns];      // run heads (index = run)
+  __shared__ uint64_t small_sorted[256];    // output of the rank sorts
   __shared__ uint64_t sel[kMaxSel];
   __shared__ uint64_t rr_keys[kMaxRerank];  // (ordered distance << 32) | local row
   __shared__ float rr_dot[kMaxRerank];      // true q.d of candidate slot c
@@ -207,14 +207,25 @@ __global__ void __launch_bounds__(kK3Threads)
   for (int r = tid; r < heads_pad; r += kK3Threads) {
     const uint64_t h = (r < n_runs) ? src[int64_t(r) * run_len] : kEmptyKey;
     heads[r] = h;
-    sorted_heads[r] = h;
   }
   if (tid == 0) n_sel_s = 0;
   if (tid < kMaxRerank) rr_keys[tid] = kEmptyKey;
   uint64_t T = kEmptyKey;  // select everything unless there are more runs than needed
+  __shared__ uint64_t T_s;
   if (n_runs > rerank) {
-    bitonic_sort_smem(sorted_heads, heads_pad, tid, kK3Threads);
-    T = sorted_heads[rerank - 1];
+    // T = the rerank-th best run head: rank by counting (no sorting network, one barrier)
+    __syncthreads();
+    for (int i = tid; i < n_runs; i += kK3Threads) {
+      const uint64_t mine = heads[i];
+      int r = 0;
+      for (int j = 0; j < n_runs; ++j) {
+        const uint64_t o = heads[j];
+        r += (o < mine) || (o == mine && j < i);
+      }
+      if (r == rerank - 1) T_s = mine;
+    }
+    __syncthreads();
+    T = T_s;
   } else {
     __syncthreads();
   }
@@ -236,8 +247,14 @@ __global__ void __launch_bounds__(kK3Threads)
   const int n_sel = min(n_sel_s, kMaxSel);
   int sel_pad = 64;
   while (sel_pad < n_sel) sel_pad <<= 1;
-  for (int i = n_sel + tid; i < sel_pad; i += kK3Threads) sel[i] = kEmptyKey;
-  bitonic_sort_smem(sel, sel_pad, tid, kK3Threads);
+  if (n_sel <= 256) {
+    rank_sort_smem(sel, small_sorted, n_sel, tid, kK3Threads);
+    for (int i = tid; i < n_sel; i += kK3Threads) sel[i] = small_sorted[i];
+    __syncthreads();
+  } else {
+    for (int i = n_sel + tid; i < sel_pad; i += kK3Threads) sel[i] = kEmptyKey;
+    bitonic_sort_smem(sel, sel_pad, tid, kK3Threads);
+  }
 
   // exact fp32 distances for the best `rerank` candidates: one warp per candidate
   const float4* qv = reinterpret_cast<const float4*>(queries + int64_t(q) * dim);
@@ -281,7 +298,9 @@ __global__ void __launch_bounds__(kK3Threads)
       if (c == 0) q_norm_s = sqrtf(qq);
     }
   }
-  bitonic_sort_smem(rr_keys, kMaxRerank, tid, kK3Threads);
+  rank_sort_smem(rr_keys, small_sorted, kMaxRerank, tid, kK3Threads);
+  if (tid < kMaxRerank) rr_keys[tid] = small_sorted[tid];
+  __syncthreads();
 
   // exactness certificate of the bf16 scan (see mrag_search_params.out_margin)
   if (out_margin != nullptr && tid == 0) {
@@ -374,7 +393,9 @@ __global__ void __launch_bounds__(kK3Threads)
     }
     mk[tid] = key;
   }
-  bitonic_sort_smem(mk, 256, tid, kK3Threads);
+  rank_sort_smem(mk, small_sorted, 256, tid, kK3Threads);
+  if (tid < 256) mk[tid] = small_sorted[tid];
+  __syncthreads();
   if (warp == 0) {
     auto gentry = [&](int j, bool in_range) {
       Emit e;

@@ -64,7 +64,7 @@ class RAGDatabase:
                  device: Literal['cpu', 'cuda'] | str | torch.device = 'cpu', *,
                  columns: dict | None = None, embed_fn: Callable | None = None,
                  metric: str = "l2", prefilter: bool = False, normalise: bool = False,
-                 path: str = "auto"):
+                 path: str = "auto", recheck: str | None = "auto"):
         """db_path / table_name / device as in the reference (src/data/rag.py:12-15). In the
         reference `device` only places the query-text embedding model; the store itself always
         lives on the current CUDA device (or on `device` when it names a cuda:N).
@@ -73,11 +73,17 @@ class RAGDatabase:
         (text -> vector, for str queries; the reference delegates that to LanceDB's registered
         gte-base-en-v1.5 function), `metric` / `prefilter` (LanceDB 0.14 defaults: "l2", post-
         filter), `normalise` (L2-normalise rows on upload; the reference's tables already are),
-        `path` (force a scan kernel: auto | stream_f32 | stream_bf16 | tensor_bf16).
+        `path` (force a scan kernel: auto | stream_f32 | stream_bf16 | tensor_bf16), `recheck`
+        (what to do with the exactness margin of the bf16 scans, see mrag.h: "auto" re-runs a
+        host call of <= 4 queries on the fp32 master rows when its margin is below 6 sigma of
+        the bf16 rounding noise; "strict" does so for any batch whenever the margin does not
+        rigorously prove exactness; None never re-runs).
         """
         self.db_path, self.table_name = db_path, table_name
         self._ctor = dict(device=str(device), metric=metric, prefilter=prefilter, normalise=normalise,
-                          path=path)
+                          path=path, recheck=recheck)
+        self.recheck = recheck
+        self.fp32_rechecks = 0
         self.embed_fn = embed_fn
         self.metric, self.prefilter, self.path = metric, prefilter, path
         dev = torch.device(device) if not isinstance(device, torch.device) else device
@@ -111,6 +117,8 @@ class RAGDatabase:
         self._ctor, self.embed_fn = {}, kw.get("embed_fn")
         self.metric, self.prefilter = kw.get("metric", "l2"), kw.get("prefilter", False)
         self.path = kw.get("path", "auto")
+        self.recheck = kw.get("recheck", "auto")
+        self.fp32_rechecks = 0
         self.device = store.device
         self._from_memory = True
         self._columns = {k: v for k, v in columns.items() if k not in VECTOR_COLUMNS}
@@ -181,7 +189,8 @@ class RAGDatabase:
     def __setstate__(self, st):
         c = st["ctor"]
         self.__init__(st["db_path"], st["table_name"], c["device"], embed_fn=st["embed_fn"],
-                      metric=c["metric"], prefilter=c["prefilter"], normalise=c["normalise"], path=c["path"])
+                      metric=c["metric"], prefilter=c["prefilter"], normalise=c["normalise"], path=c["path"],
+                      recheck=c.get("recheck", "auto"))
 
     # -- reference API ------------------------------------------------------------------------
     @staticmethod
@@ -308,7 +317,8 @@ class RAGDatabase:
             if q.ndim != 2:
                 raise ValueError(f"query must be [dim] or [nq, dim], got {tuple(q.shape)}")
             excl = self._exclusion_ids(where, q.shape[0])
-            if self.path == "stream_f32" or self.prefilter:
+            certify = (self.recheck == "strict" or (self.recheck == "auto" and q.shape[0] <= 4))
+            if self.path == "stream_f32" or self.prefilter or not certify:
                 dist, idx, _ = store.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
                                                  exclude_group=excl, filter_mode=mode)
                 return dist, idx, single
@@ -327,10 +337,11 @@ class RAGDatabase:
     def _recheck(self, store, q, excl, dist, idx, margin, top_k, mode) -> None:
         """Queries whose bf16-scan result is not certified exact (margin <= eps, see mrag.h) are
         re-run on the fp32 master rows, 4 per pass; results are patched in place."""
-        from .store import EPS
-        eps = EPS["stream_bf16"] if (q.shape[0] <= 4 and self.path != "tensor_bf16") else EPS["tensor_bf16"]
+        from .store import EPS, eps_typical
+        used = "stream_bf16" if (q.shape[0] <= 4 and self.path != "tensor_bf16") else "tensor_bf16"
+        eps = EPS[used] if self.recheck == "strict" else eps_typical(used, q.shape[1])
         doubt = np.nonzero(~(margin > eps))[0]          # NaN counts as doubt
-        self.fp32_rechecks = getattr(self, "fp32_rechecks", 0) + int(doubt.size)
+        self.fp32_rechecks += int(doubt.size)
         for s in range(0, doubt.size, 4):
             rows = doubt[s:s + 4]
             d2, i2, _ = store.search_host(q[rows], int(top_k), metric=self.metric, path="stream_f32",

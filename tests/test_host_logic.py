@@ -16,6 +16,7 @@ def _db_no_gpu(n=30, dim=8):
                    "start_sec": np.arange(n, dtype=np.float64)}
     db._vectors = {"text_embedding": rng.standard_normal((n, dim)).astype(np.float32)}
     db._group_ids, db._group_col, db._stores = {}, None, {}
+    db.recheck, db.fp32_rechecks = "auto", 0
     return db
 
 

@@ -79,6 +79,10 @@ typedef struct mrag_store_info {
   const void* rows_f32_dev;  /* [n_rows, dim] float32, L2-normalised when appended with normalise=1 */
   const void* rows_bf16_dev; /* [n_rows, dim] bfloat16 shadow of the same rows */
   const void* groups_dev;    /* [n_rows] int32 group id per row (video identity) or NULL */
+  float max_norm_deviation;  /* max over non-zero rows of | |row|^2 - 1 | as stored; searches with the
+                                l2 / cosine metric are refused above 1e-3 (the scan ranks by q.d) */
+  int32_t reserved;
+  int64_t zero_rows;         /* all-zero rows (LanceDB on_bad_vectors='fill'); they score q.d = 0 */
 } mrag_store_info;
 
 typedef struct mrag_search_params {

@@ -32,7 +32,8 @@ class StoreInfo(C.Structure):
     _fields_ = [("dim", C.c_int32), ("device", C.c_int32), ("n_rows", C.c_int64),
                 ("capacity_rows", C.c_int64), ("has_groups", C.c_int32), ("sm_count", C.c_int32),
                 ("rows_f32_dev", C.c_void_p), ("rows_bf16_dev", C.c_void_p),
-                ("groups_dev", C.c_void_p)]
+                ("groups_dev", C.c_void_p), ("max_norm_deviation", C.c_float), ("reserved", C.c_int32),
+                ("zero_rows", C.c_int64)]
 
 
 class SearchParams(C.Structure):

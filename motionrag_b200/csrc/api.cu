@@ -49,6 +49,9 @@ struct mrag_store {
   void* rows_bf16 = nullptr;
   int32_t* groups = nullptr;
   bool has_groups = false;
+  unsigned int* norm_stats = nullptr;  // device: {max ||row|^2-1| (float bits), zero rows}
+  float max_norm_dev = 0.f;            // host copy, refreshed by every append
+  int64_t zero_rows = 0;
   // scratch of the host-buffer entry point (mrag_search_host): grown on demand, reused
   mutable std::mutex host_mu;
   mutable char* host_dev = nullptr;
@@ -107,6 +110,12 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
   if (p->filter_mode < 0 || p->filter_mode > 2)
     return fail(MRAG_ERR_ARG, "unknown filter_mode %d", p->filter_mode);
   if (s->n_rows < 1) return fail(MRAG_ERR_ARG, "store is empty");
+  // the scan ranks by q.d, which orders like squared-L2 / cosine only when every row has unit norm
+  if (p->metric != MRAG_METRIC_DOT && s->max_norm_dev > 1e-3f)
+    return fail(MRAG_ERR_UNSUPPORTED,
+                "rows are not unit-norm (max ||d|^2-1| = %.3g): append with normalise=1 (the reference "
+                "table is normalised, tools/build_rag_database.py:31-37) or search with metric=dot",
+                s->max_norm_dev);
   int path = p->path;
   // AUTO: scan the bf16 shadow (half the bytes), re-rank the candidates in fp32 from the master
   // rows — the role refine_factor plays in the reference's own call (src/data/rag.py:54)
@@ -211,10 +220,13 @@ int mrag_store_create(int32_t dim, int64_t capacity_rows, int32_t device, mrag_s
   if (e == cudaSuccess) e = cudaMemset(s->rows_f32, 0, elems * 4);
   if (e == cudaSuccess) e = cudaMemset(s->rows_bf16, 0, elems * 2);
   if (e == cudaSuccess) e = cudaMemset(s->groups, 0xff, size_t(s->capacity) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&s->norm_stats, 8);
+  if (e == cudaSuccess) e = cudaMemset(s->norm_stats, 0, 8);
   if (e != cudaSuccess) {
     cudaFree(s->rows_f32);
     cudaFree(s->rows_bf16);
     cudaFree(s->groups);
+    cudaFree(s->norm_stats);
     delete s;
     return cuda_fail(e, "store allocation");
   }
@@ -233,6 +245,7 @@ int mrag_store_destroy(mrag_store* s) {
   if (s->host_event) cudaEventDestroy(s->host_event);
   cudaFree(s->host_dev);
   cudaFreeHost(s->host_pin);
+  cudaFree(s->norm_stats);
   delete s;
   return MRAG_OK;
 }
@@ -251,7 +264,12 @@ int mrag_store_append(mrag_store* s, const float* rows, int64_t n, int32_t rows_
   CK(cudaMemcpyAsync(dst, rows, size_t(n) * s->dim * 4,
                      rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   CK(launch_prepare_rows(dst, static_cast<char*>(s->rows_bf16) + size_t(s->n_rows) * s->dim * 2, n,
-                         s->dim, normalise != 0, st));
+                         s->dim, normalise != 0, s->norm_stats, st));
+  unsigned int host_stats[2] = {0, 0};
+  CK(cudaMemcpyAsync(host_stats, s->norm_stats, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(&s->max_norm_dev, &host_stats[0], 4);
+  s->zero_rows = host_stats[1];
   s->n_rows += n;
   {
     std::lock_guard<std::mutex> lock(s->host_mu);
@@ -289,6 +307,8 @@ int mrag_store_get_info(const mrag_store* s, mrag_store_info* out) {
   out->rows_f32_dev = s->rows_f32;
   out->rows_bf16_dev = s->rows_bf16;
   out->groups_dev = s->has_groups ? s->groups : nullptr;
+  out->max_norm_deviation = s->max_norm_dev;
+  out->zero_rows = s->zero_rows;
   return MRAG_OK;
 }
 

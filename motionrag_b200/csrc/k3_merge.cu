@@ -15,26 +15,34 @@ namespace mrag {
 // ---- K0 -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     k0_prepare_rows_kernel(float* __restrict__ rows, __nv_bfloat16* __restrict__ shadow, int64_t n,
-                           int dim, int normalise) {
+                           int dim, int normalise, unsigned int* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= n) return;
   float4* p = reinterpret_cast<float4*>(rows + row * dim);
   const int nv = dim >> 2;
   float scale = 1.f;
-  if (normalise) {
-    float ss = 0.f;
-    for (int i = lane; i < nv; i += 32) {
-      float4 v = p[i];
-      ss = fmaf(v.x, v.x, ss);
-      ss = fmaf(v.y, v.y, ss);
-      ss = fmaf(v.z, v.z, ss);
-      ss = fmaf(v.w, v.w, ss);
-    }
+  float ss = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float4 v = p[i];
+    ss = fmaf(v.x, v.x, ss);
+    ss = fmaf(v.y, v.y, ss);
+    ss = fmaf(v.z, v.z, ss);
+    ss = fmaf(v.w, v.w, ss);
+  }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    // x / max(|x|, eps), the torch.nn.functional.normalize convention
-    scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+  // x / max(|x|, eps), the torch.nn.functional.normalize convention
+  if (normalise) scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0 && stats != nullptr) {
+    // stats[0] = max | |row|^2 - 1 | over non-zero rows as stored (float bits, >= 0 so uint order
+    // works); stats[1] = number of all-zero rows (LanceDB's on_bad_vectors='fill' produces them)
+    if (ss == 0.f) {
+      atomicAdd(&stats[1], 1u);
+    } else {
+      const float stored = normalise ? ss * scale * scale : ss;
+      atomicMax(&stats[0], __float_as_uint(fabsf(stored - 1.f)));
+    }
   }
   uint2* o = reinterpret_cast<uint2*>(shadow + row * dim);
   for (int i = lane; i < nv; i += 32) {
@@ -69,12 +77,12 @@ __global__ void __launch_bounds__(256)
 }
 
 cudaError_t launch_prepare_rows(float* rows_f32, void* rows_bf16, int64_t n, int dim,
-                                bool normalise, cudaStream_t st) {
+                                bool normalise, unsigned int* stats, cudaStream_t st) {
   if (n == 0) return cudaSuccess;
   const int64_t threads = n * 32;
   const int64_t blocks = (threads + 255) / 256;
   k0_prepare_rows_kernel<<<unsigned(blocks), 256, 0, st>>>(
-      rows_f32, static_cast<__nv_bfloat16*>(rows_bf16), n, dim, normalise ? 1 : 0);
+      rows_f32, static_cast<__nv_bfloat16*>(rows_bf16), n, dim, normalise ? 1 : 0, stats);
   note_launch();
   return cudaGetLastError();
 }

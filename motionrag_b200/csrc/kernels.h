@@ -10,8 +10,9 @@ void note_launch(int n = 1);
 
 // K0: store preparation -------------------------------------------------------------------
 // rows (fp32, in place when normalise) -> bf16 shadow; one warp per row
+// stats (device, 2 x u32, may be null): [0] max ||row|^2 - 1| as float bits, [1] zero-row count
 cudaError_t launch_prepare_rows(float* rows_f32, void* rows_bf16, int64_t n, int dim,
-                                bool normalise, cudaStream_t st);
+                                bool normalise, unsigned int* stats, cudaStream_t st);
 cudaError_t launch_cast_queries_bf16(const float* q, void* q_bf16, int nq, int dim,
                                      cudaStream_t st);
 

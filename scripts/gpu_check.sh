@@ -19,13 +19,17 @@ echo "smoke rc=$?" | tee -a $OUT/summary.txt; tail -3 $OUT/smoke.log | tee -a $O
 if [ "${1:-}" != "quick" ]; then
   timeout 900 python bench.py --steps 200 --warmup 10 > $OUT/bench.json 2> $OUT/bench.err
   echo "bench rc=$?" | tee -a $OUT/summary.txt; tail -c 3000 $OUT/bench.json | tee -a $OUT/summary.txt; tail -5 $OUT/bench.err
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
-      --log-file $OUT/launches.csv python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:k[0-9]_" -c 80 --csv \
+      --log-file $OUT/launches.csv python bench.py --steps 8 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
   echo "ncu launches rc=$?" | tee -a $OUT/summary.txt
 fi
 if [ "${1:-}" == "prof" ] || [ "${2:-}" == "prof" ]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_stream -s 4 -c 2 -f -o $OUT/prof_k1 \
       python bench.py --steps 3 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_k1.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_stream -s 4 -c 1 -f -o $OUT/prof_k1_f32 \
+      python bench.py --workload c1f --steps 3 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_k1f.log 2>&1
+  timeout 600 ncu --set full --clock-control none -k regex:k4_gather -c 2 -f -o $OUT/prof_k4 \
+      python bench.py --workload c4 --steps 3 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_k4.log 2>&1
   echo "ncu k1 rc=$?" | tee -a $OUT/summary.txt
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k2_batch -s 2 -c 1 -f -o $OUT/prof_k2 \
       python bench.py --workload c2 --steps 3 --warmup 3 --no-extras --no-cpu-baseline > $OUT/ncu_k2.log 2>&1

@@ -46,7 +46,7 @@ def test_header_compiles_as_plain_c(tmp_path):
 def test_struct_layouts_match_header():
     from motionrag_b200 import _cabi
     assert C.sizeof(_cabi.SearchParams) == 40
-    assert C.sizeof(_cabi.StoreInfo) == 56
+    assert C.sizeof(_cabi.StoreInfo) == 72
     assert C.sizeof(_cabi.PlanInfo) == 56
 
 

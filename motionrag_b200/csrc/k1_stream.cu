@@ -72,6 +72,9 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
   __shared__ uint64_t merge_keys[kK1Threads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // programmatic dependent launch: let the (1-4 block) K3 grid become resident now; it parks
+  // in griddepcontrol.wait until this grid has completed and its candidate keys are visible
+  asm volatile("griddepcontrol.launch_dependents;");
   for (int e = tid; e < Q * D; e += kK1Threads) {
     int q = e / D, d = e % D;
     int vec = d / EPV, c = d % EPV;           // vec = step*32 + lane

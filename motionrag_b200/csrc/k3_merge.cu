@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(kK3Threads)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q = blockIdx.x;
   const uint64_t* src = cand + int64_t(q) * n_runs * run_len;
+  // launched with programmatic stream serialization: wait here for the scan kernel's results
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   int heads_pad = 64;
   while (heads_pad < n_runs) heads_pad <<= 1;
@@ -453,12 +455,21 @@ cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len
   if (n_runs < 1 || n_runs > kMaxRuns || run_len < 1 || run_len > 32 || rerank < 1 ||
       rerank > kMaxRerank || int64_t(rerank) * run_len > kMaxSel)
     return cudaErrorInvalidValue;
-  k3_merge_rerank_kernel<<<nq, kK3Threads, 0, st>>>(cand, n_runs, run_len, db_f32, dim, queries,
-                                                    row_group, exclude_group, filter_mode, metric,
-                                                    rerank, k, index_base, out_dist, out_idx,
-                                                    out_group, out_margin, x);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(nq));
+  cfg.blockDim = dim3(kK3Threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, k3_merge_rerank_kernel, cand, n_runs, run_len, db_f32, dim,
+                                      queries, row_group, exclude_group, filter_mode, metric, rerank, k,
+                                      index_base, out_dist, out_idx, out_group, out_margin, x);
   note_launch();
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 // ---- cross-shard merge ----------------------------------------------------------------------

@@ -84,29 +84,46 @@ class PeerExchange:
         nbytes = int(lib.mrag_exchange_bytes(world, self.nq_cap, self.k_cap))
         if nbytes == 0:
             raise ValueError("bad exchange shape (world <= 8, k_cap <= 32)")
-        ptr = C.c_void_p()
-        check(lib.mrag_device_alloc(device.index, nbytes, C.byref(ptr)))
-        self._own = ptr
-        self._lib = lib
-        self.buf = _view(ptr.value, (nbytes // 4,), torch.int32, device, self)
-        self.buf.zero_()
-        torch.cuda.synchronize(device)
-        handle = (C.c_ubyte * 64)()
-        check(lib.mrag_ipc_export(ptr, handle))
+        self._lib, self._own, self._opened, self.epoch = lib, None, [], 0
+        # Every step that can fail locally is followed by a collective vote, so that all ranks
+        # raise (or none does) and nobody is left waiting in a collective.
+        mine, err = None, None
+        try:
+            ptr = C.c_void_p()
+            check(lib.mrag_device_alloc(device.index, nbytes, C.byref(ptr)))
+            self._own = ptr
+            self.buf = _view(ptr.value, (nbytes // 4,), torch.int32, device, self)
+            self.buf.zero_()
+            torch.cuda.synchronize(device)
+            handle = (C.c_ubyte * 64)()
+            check(lib.mrag_ipc_export(ptr, handle))
+            mine = bytes(handle)
+        except Exception as e:  # noqa: BLE001
+            err = e
         handles: list = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=group)
+        dist.all_gather_object(handles, mine, group=group)
         ptrs = []
-        self._opened = []
-        for r, h in enumerate(handles):
-            if r == rank:
-                ptrs.append(ptr.value)
-                continue
-            p = C.c_void_p()
-            check(lib.mrag_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
-            self._opened.append(p)
-            ptrs.append(p.value)
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r, h in enumerate(handles):
+                    if r == rank:
+                        ptrs.append(self._own.value)
+                        continue
+                    p = C.c_void_p()
+                    check(lib.mrag_ipc_open((C.c_ubyte * 64).from_buffer_copy(h), C.byref(p)))
+                    self._opened.append(p)
+                    ptrs.append(p.value)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer rank could not export its exchange buffer")
+        oks: list = [None] * world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            self.close()
+            raise RuntimeError(f"peer exchange setup failed on rank(s) {[r for r, o in enumerate(oks) if not o]}"
+                               + (f": {err}" if err is not None else ""))
         self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
-        self.epoch = 0
         dist.barrier(group=group)   # every rank has zeroed and mapped before the first use
 
     def next(self) -> "_cabi.Exchange":

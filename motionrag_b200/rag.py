@@ -279,25 +279,25 @@ class RAGDatabase:
                 cols.append((c, self._vectors[c], True))
             else:
                 raise ValueError(f"unknown column {c!r} in select")
-        out = []
-        for q in range(idx.shape[0]):
-            rows = idx[q][idx[q] >= 0]
-            n = int(rows.size)
-            # one fancy-index + tolist() per column instead of per-cell numpy scalar handling
-            per_col = []
-            for c, col, is_vec in cols:
-                if is_vec:
-                    per_col.append([np.array(col[int(i)], dtype=np.float32) for i in rows])
-                else:
-                    per_col.append(col[rows].tolist())
-            dist_l = dist[q][:n].tolist()
-            keys = [c for c, _, _ in cols]
-            recs = []
-            for j in range(n):
-                r = {k_: v[j] for k_, v in zip(keys, per_col)}
-                r["_distance"] = dist_l[j]
-                recs.append(r)
-            out.append(recs)
+        # one fancy-index + tolist() per column for the WHOLE batch, then C-speed dict(zip(...));
+        # per-cell numpy scalar handling would dominate a 4096-query batch
+        nq, k = idx.shape
+        valid = idx >= 0
+        flat = idx[valid]
+        counts = valid.sum(-1).tolist()
+        keys = [c for c, _, _ in cols] + ["_distance"]
+        per_col = []
+        for c, col, is_vec in cols:
+            if is_vec:
+                per_col.append([np.array(col[int(i)], dtype=np.float32) for i in flat])
+            else:
+                per_col.append(col[flat].tolist())
+        per_col.append(dist[valid].tolist())
+        recs = [dict(zip(keys, vals)) for vals in zip(*per_col)]
+        out, pos = [], 0
+        for n in counts:
+            out.append(recs[pos:pos + n])
+            pos += n
         return out
 
     def _search(self, vector, vector_column_name, top_k, where, refine_factor):

@@ -112,6 +112,44 @@ class EmbeddingStore:
         if not on_dev:
             torch.cuda.current_stream(self.device).synchronize()
 
+    # -- shard files (fast reload; the bf16 shadow and norm statistics are rebuilt on load) ----
+    def save(self, path) -> None:
+        """Write this store (one shard) as <path>/{meta.json, rows_f32.npy[, groups.npy]}."""
+        import json
+        from pathlib import Path
+        root = Path(path)
+        root.mkdir(parents=True, exist_ok=True)
+        inf = self.info()
+        n = int(inf.n_rows)
+        step = max(1, (256 << 20) // (self.dim * 4))
+        out = np.lib.format.open_memmap(root / "rows_f32.npy", mode="w+", dtype=np.float32, shape=(n, self.dim))
+        rows = self.rows_f32()
+        for s0 in range(0, n, step):
+            out[s0:s0 + step] = rows[s0:s0 + step].cpu().numpy()
+        out.flush()
+        if inf.has_groups:
+            np.save(root / "groups.npy", _view(inf.groups_dev, (n,), torch.int32, self.device, self).cpu().numpy())
+        (root / "meta.json").write_text(json.dumps({"format": "mrag-shard-1", "dim": self.dim, "n_rows": n,
+                                                    "has_groups": bool(inf.has_groups)}))
+
+    @classmethod
+    def load(cls, path, device: int | str | torch.device = 0, capacity_rows: int | None = None) -> "EmbeddingStore":
+        import json
+        from pathlib import Path
+        root = Path(path)
+        meta = json.loads((root / "meta.json").read_text())
+        if meta.get("format") != "mrag-shard-1":
+            raise ValueError(f"{root} is not an mrag shard directory")
+        n, dim = int(meta["n_rows"]), int(meta["dim"])
+        st = cls(dim, max(capacity_rows or n, n, 1), device)
+        rows = np.load(root / "rows_f32.npy", mmap_mode="r")
+        step = max(1, (256 << 20) // (dim * 4))
+        for s0 in range(0, n, step):
+            st.append(np.ascontiguousarray(rows[s0:s0 + step]), normalise=False)
+        if meta.get("has_groups"):
+            st.set_groups(np.load(root / "groups.npy"))
+        return st
+
     def rows_f32(self) -> torch.Tensor:
         """Zero-copy view of the fp32 master rows (for tests / re-use by torch code)."""
         inf = self.info()

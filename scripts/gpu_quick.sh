@@ -15,3 +15,4 @@ try:
 except Exception as e:
     print("ERR", e, open("gpurun_out/bench.err").read()[-1500:])
 PY
+timeout 300 python scripts/e2e_breakdown.py > $OUT/e2e_breakdown.txt 2>&1; cat $OUT/e2e_breakdown.txt | tee -a $OUT/summary.txt

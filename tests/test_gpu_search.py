@@ -311,6 +311,20 @@ def test_non_unit_rows_are_refused_for_l2_and_cosine():
     st2.close()
 
 
+def test_shard_save_load_roundtrip(case, tmp_path):
+    from motionrag_b200 import EmbeddingStore
+    case["store"].save(tmp_path / "shard0")
+    st = EmbeddingStore.load(tmp_path / "shard0", 0)
+    assert len(st) == case["n"] and st.info().has_groups == 1
+    assert torch.equal(st.rows_f32(), case["store"].rows_f32()) and torch.equal(st.rows_bf16(), case["store"].rows_bf16())
+    qd = torch.from_numpy(case["q"][:4]).cuda()
+    exd = torch.from_numpy(case["excl"][:4]).cuda()
+    a = case["store"].search(qd, 12, exclude_group=exd)
+    b = st.search(qd, 12, exclude_group=exd)
+    assert torch.equal(a.index, b.index) and torch.equal(a.distance, b.distance)
+    st.close()
+
+
 def test_merge_topk_matches_numpy():
     from motionrag_b200 import merge_topk
     rng = np.random.default_rng(2)

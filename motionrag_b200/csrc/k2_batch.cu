@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
   const long long t_start = clk();
   long long w_a = 0, w_b = 0, busy = 0, served = 0;  // role-specific wait / work counters
   const int kblocks = a.dim / kBK;
-  const int total_items = a.m_tiles * a.chunks;
+  const int unit = blockIdx.x;
+  K2Seg sg;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -82,11 +83,9 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
       const uint64_t pol_db = policy_evict_normal(); // shared by the CTAs of the same chunk
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int m = item % a.m_tiles, chunk = item / a.m_tiles;
-        const int t0 = chunk * a.tiles_per_chunk;
-        const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-        for (int t = t0; t < t1; ++t) {
+      for (int si = 0; k2_segment(a, unit, si, sg); ++si) {
+        const int m = sg.m;
+        for (int t = sg.t0; t < sg.t1; ++t) {
           ++served;
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait_timed(&empty_bar[stage], phase ^ 1, w_a);
@@ -111,11 +110,8 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int chunk = item / a.m_tiles;
-        const int t0 = chunk * a.tiles_per_chunk;
-        const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-        for (int t = t0; t < t1; ++t) {
+      for (int si = 0; k2_segment(a, unit, si, sg); ++si) {
+        for (int t = sg.t0; t < sg.t1; ++t) {
           mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, w_b);  // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc) * kBN;
@@ -150,11 +146,9 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
     float* stg = reinterpret_cast<float*>(smem + K2Smem::kEpiStage) + (warp - 2) * 32 * 32;
     uint32_t n = 0;                    // running tile count of this CTA, same in every role
     uint32_t ph0 = 0u, ph1 = 0u;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int m = item % a.m_tiles, chunk = item / a.m_tiles;
-      const int t0 = chunk * a.tiles_per_chunk;
-      const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-      const int q_row = m * kBM + quarter * 32 + lane;
+    for (int si = 0; k2_segment(a, unit, si, sg); ++si) {
+      const int t0 = sg.t0, t1 = sg.t1;
+      const int q_row = sg.m * kBM + quarter * 32 + lane;
 
       TopList<KC> top;
       top.reset();
@@ -177,7 +171,7 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
         busy += clk() - t_busy;
         ++served;
       }
-      if (live) top.store(a.cand + ((int64_t(q_row) * a.chunks + chunk) * SETS + set) * KC);
+      if (live) top.store(a.cand + ((int64_t(q_row) * a.runs + sg.run) * SETS + set) * KC);
     }
   }
 
@@ -208,30 +202,11 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
 bool k2_supported(int dim) { return dim % kBK == 0 && dim >= kBK && dim <= 4096; }
 
 K2Plan k2_plan(int64_t n_rows, int nq, int sm_count) {
-  K2Plan p;
+  K2Plan p{};
   p.m_tiles = (nq + kBM - 1) / kBM;
   p.n_tiles = int((n_rows + kBN - 1) / kBN);
-  // choose the chunk count that minimises the makespan (items per CTA x tiles per item);
-  // prefer fewer chunks on ties (fewer candidates, fewer list restarts)
-  const int max_chunks = p.n_tiles < 160 ? p.n_tiles : 160;
-  int64_t best_cost = -1;
-  int best = 1;
-  for (int c = 1; c <= max_chunks; ++c) {
-    const int tpc = (p.n_tiles + c - 1) / c;
-    const int eff_chunks = (p.n_tiles + tpc - 1) / tpc;
-    if (eff_chunks != c) continue;
-    const int64_t items = int64_t(p.m_tiles) * c;
-    const int64_t waves = (items + sm_count - 1) / sm_count;
-    const int64_t cost = waves * tpc;
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = c;
-    }
-  }
-  p.chunks = best;
-  p.tiles_per_chunk = (p.n_tiles + best - 1) / best;
-  const int64_t items = int64_t(p.m_tiles) * p.chunks;
-  p.grid = int(items < sm_count ? items : sm_count);
+  k2_assign(p, sm_count, p.m_tiles);
+  p.grid = sm_count;  // every unit runs: each (query, run) cell is written by exactly one unit
   p.epi_sets = k2_epi_sets();
   return p;
 }
@@ -248,10 +223,7 @@ cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* d
   a.nq = nq;
   a.dim = dim;
   a.n_rows = n_rows;
-  a.m_tiles = plan.m_tiles;
-  a.n_tiles = plan.n_tiles;
-  a.chunks = plan.chunks;
-  a.tiles_per_chunk = plan.tiles_per_chunk;
+  k2_fill_args(a, plan);
   a.cand = cand;
   a.gthr = gthr;
   a.debug = k2_debug_mode();

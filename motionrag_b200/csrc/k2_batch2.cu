@@ -47,10 +47,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(SETS), 1)
   long long w_a = 0, w_b = 0, busy = 0, served = 0;  // role-specific wait / work counters
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
-  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int pair_id = blockIdx.x >> 1;
   const int kblocks = a.dim / kBK;
-  const int m_pairs = (a.m_tiles + 1) >> 1;
-  const int total_items = m_pairs * a.chunks;
+  const int unit = pair_id;
+  K2Seg sg;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -78,12 +78,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(SETS), 1)
       const uint64_t pol_db = policy_evict_normal();
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = pair_id; item < total_items; item += n_pairs) {
-        const int mp = item % m_pairs, chunk = item / m_pairs;
-        const int t0 = chunk * a.tiles_per_chunk;
-        const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-        const int q_row0 = (mp * 2 + int(cta_rank)) * kBM;
-        for (int t = t0; t < t1; ++t) {
+      for (int si = 0; k2_segment(a, unit, si, sg); ++si) {
+        const int q_row0 = (sg.m * 2 + int(cta_rank)) * kBM;
+        for (int t = sg.t0; t < sg.t1; ++t) {
           ++served;
           const int db_row0 = t * kBN + int(cta_rank) * (kBN / 2);
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -109,11 +106,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(SETS), 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = pair_id; item < total_items; item += n_pairs) {
-        const int chunk = item / m_pairs;
-        const int t0 = chunk * a.tiles_per_chunk;
-        const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-        for (int t = t0; t < t1; ++t) {
+      for (int si = 0; k2_segment(a, unit, si, sg); ++si) {
+        for (int t = sg.t0; t < sg.t1; ++t) {
           mbar_wait_timed(&tempty_bar[acc], acc_phase ^ 1, w_b);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + uint32_t(acc) * kBN;
@@ -146,11 +140,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(SETS), 1)
     float* stg = reinterpret_cast<float*>(smem + K2Smem2::kEpiStage) + (warp - 2) * 32 * 32;
     uint32_t n = 0;                    // running tile count of this CTA, same in every role
     uint32_t ph0 = 0u, ph1 = 0u;
-    for (int item = pair_id; item < total_items; item += n_pairs) {
-      const int mp = item % m_pairs, chunk = item / m_pairs;
-      const int t0 = chunk * a.tiles_per_chunk;
-      const int t1 = min(a.n_tiles, t0 + a.tiles_per_chunk);
-      const int q_row = (mp * 2 + int(cta_rank)) * kBM + quarter * 32 + lane;
+    for (int si = 0; k2_segment(a, unit, si, sg); ++si) {
+      const int t0 = sg.t0, t1 = sg.t1;
+      const int q_row = (sg.m * 2 + int(cta_rank)) * kBM + quarter * 32 + lane;
 
       TopList<KC> top;
       top.reset();
@@ -173,7 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(SETS), 1)
         busy += clk() - t_busy;
         ++served;
       }
-      if (live) top.store(a.cand + ((int64_t(q_row) * a.chunks + chunk) * SETS + set) * KC);
+      if (live) top.store(a.cand + ((int64_t(q_row) * a.runs + sg.run) * SETS + set) * KC);
     }
   }
 
@@ -203,28 +195,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2_threads(SETS), 1)
 
 // ---- host side ------------------------------------------------------------------------------
 K2Plan k2_plan_pair(int64_t n_rows, int nq, int sm_count) {
-  K2Plan p;
+  K2Plan p{};
   p.m_tiles = (nq + kBM - 1) / kBM;
   p.n_tiles = int((n_rows + kBN - 1) / kBN);
-  const int m_pairs = (p.m_tiles + 1) / 2;
   const int pairs = sm_count / 2;
-  const int max_chunks = p.n_tiles < 160 ? p.n_tiles : 160;
-  int64_t best_cost = -1;
-  int best = 1;
-  for (int c = 1; c <= max_chunks; ++c) {
-    const int tpc = (p.n_tiles + c - 1) / c;
-    if ((p.n_tiles + tpc - 1) / tpc != c) continue;
-    const int64_t items = int64_t(m_pairs) * c;
-    const int64_t cost = ((items + pairs - 1) / pairs) * tpc;
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = c;
-    }
-  }
-  p.chunks = best;
-  p.tiles_per_chunk = (p.n_tiles + best - 1) / best;
-  const int64_t items = int64_t(m_pairs) * p.chunks;
-  p.grid = 2 * int(items < pairs ? items : pairs);
+  k2_assign(p, pairs, (p.m_tiles + 1) / 2);
+  p.grid = 2 * pairs;
   p.epi_sets = k2_epi_sets();
   return p;
 }
@@ -241,10 +217,7 @@ cudaError_t launch_k2_batch_pair(const void* q_bf16, int q_rows_padded, const vo
   a.nq = nq;
   a.dim = dim;
   a.n_rows = n_rows;
-  a.m_tiles = plan.m_tiles;
-  a.n_tiles = plan.n_tiles;
-  a.chunks = plan.chunks;
-  a.tiles_per_chunk = plan.tiles_per_chunk;
+  k2_fill_args(a, plan);
   a.cand = cand;
   a.gthr = gthr;
   a.debug = k2_debug_mode();

@@ -24,8 +24,12 @@ struct K2Args {
   int nq;
   int dim;
   int64_t n_rows;
-  int m_tiles, n_tiles, chunks, tiles_per_chunk;
-  uint64_t* cand;  // [nq][chunks][SETS][KC]
+  int m_tiles, n_tiles;
+  // work assignment (see k2_segment): m_groups query groups (tiles, or tile pairs for the CTA-
+  // pair kernel) x n_tiles database tiles over n_units units (CTAs or CTA pairs)
+  int m_groups, n_units, fixed_per_group, quota, lr_t0, bt, nb;
+  int runs;        // candidate runs per query = fixed_per_group + nb
+  uint64_t* cand;  // [nq][runs][SETS][KC]
   // [nq] running lower bound of each query's global 32nd-best score (ordered-uint encoding,
   // zero-initialised), shared by every CTA / chunk working on that query: a CTA's local KC-th
   // best is such a bound, so scores below it can never reach the global top-KC and are
@@ -38,6 +42,98 @@ struct K2Args {
   unsigned long long* stats;
   int debug;  // profiling only (MRAG_K2_DEBUG): 1 = epilogue skips TMEM reads, 2 = reads but never inserts
 };
+
+// Work assignment. "Fixed" units keep ONE query group for their whole life and walk a contiguous
+// tile range [j*quota, (j+1)*quota): their top lists are never reset, so the insert count per
+// query is ~ln(rows of the range) and the shared bound tightens quickly; the m_groups units with
+// the same j walk the same database tiles side by side, so HBM sees each tile once. The units
+// left over when n_units is not a multiple of m_groups ("floaters") take the remaining tile range
+// [lr_t0, n_tiles) in blocks of bt tiles, query group fastest (they restart their lists per block
+// but start from the tight shared bound). With fewer units than groups everything is a floater.
+struct K2Seg {
+  int m, t0, t1, run;
+};
+__device__ __forceinline__ bool k2_segment(const K2Args& a, int unit, int si, K2Seg& s) {
+  const int n_fixed = a.fixed_per_group * a.m_groups;
+  if (unit < n_fixed) {
+    if (si != 0) return false;
+    const int j = unit / a.m_groups;
+    s.m = unit - j * a.m_groups;
+    s.t0 = min(a.lr_t0, j * a.quota);
+    s.t1 = min(a.lr_t0, s.t0 + a.quota);
+    s.run = j;
+    return true;
+  }
+  const int e = a.n_units - n_fixed;
+  const int id = (unit - n_fixed) + si * e;
+  if (id >= a.nb * a.m_groups) return false;
+  const int b = id / a.m_groups;
+  s.m = id - b * a.m_groups;
+  s.t0 = a.lr_t0 + b * a.bt;
+  s.t1 = min(a.n_tiles, s.t0 + a.bt);
+  s.run = a.fixed_per_group + b;
+  return true;
+}
+
+// host: fill the assignment fields of a plan for `units` units and `groups` query groups
+inline void k2_assign(K2Plan& p, int units, int groups) {
+  const int T = p.n_tiles;
+  int f = units / groups;
+  if (f > T) f = T;
+  p.m_groups = groups;
+  p.n_units = units;
+  p.fixed_per_group = f;
+  p.quota = f > 0 ? int((int64_t(groups) * T + units - 1) / units) : 0;
+  if (f > 0 && int64_t(f) * p.quota > T) p.quota = (T + f - 1) / f;  // never hand out more than exists
+  p.lr_t0 = f > 0 ? (int64_t(f) * p.quota < T ? f * p.quota : T) : 0;
+  const int lr = T - p.lr_t0;
+  const int e = units - f * groups;
+  p.bt = 1;
+  p.nb = 0;
+  if (lr > 0 && e > 0) {
+    // floater makespan for block size bt: ceil(blocks * groups / e) * bt. Take the LARGEST block
+    // (fewest runs / list restarts) whose makespan stays within 1.5 % of the better of the fixed
+    // units' quota and the best achievable.
+    int64_t best = -1;
+    for (int bt = 4; bt <= 128; ++bt) {
+      const int nb = (lr + bt - 1) / bt;
+      if (nb > 200) continue;
+      const int64_t cost = ((int64_t(nb) * groups + e - 1) / e) * bt;
+      if (best < 0 || cost < best) best = cost;
+    }
+    if (best >= 0) {
+      int64_t limit = best > p.quota ? best : p.quota;
+      limit += limit * 15 / 1000;
+      for (int bt = 4; bt <= 128; ++bt) {
+        const int nb = (lr + bt - 1) / bt;
+        if (nb > 200) continue;
+        const int64_t cost = ((int64_t(nb) * groups + e - 1) / e) * bt;
+        if (cost <= limit) {
+          p.bt = bt;
+          p.nb = nb;
+        }
+      }
+    }
+    if (best < 0) {  // very long leftover: cap the block count instead
+      p.nb = 200;
+      p.bt = (lr + 199) / 200;
+    }
+  }
+  p.chunks = p.fixed_per_group + p.nb;  // runs per query (per epilogue set)
+  p.tiles_per_chunk = p.quota > p.bt ? p.quota : p.bt;
+}
+inline void k2_fill_args(K2Args& a, const K2Plan& p) {
+  a.m_tiles = p.m_tiles;
+  a.n_tiles = p.n_tiles;
+  a.m_groups = p.m_groups;
+  a.n_units = p.n_units;
+  a.fixed_per_group = p.fixed_per_group;
+  a.quota = p.quota;
+  a.lr_t0 = p.lr_t0;
+  a.bt = p.bt;
+  a.nb = p.nb;
+  a.runs = p.chunks;
+}
 
 // running top-KC of one query row, sorted descending, held in registers
 template <int KC>

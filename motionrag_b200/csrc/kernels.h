@@ -29,9 +29,11 @@ cudaError_t launch_k1_stream(const void* db, int elt_bytes, int64_t n_rows, int 
 struct K2Plan {
   int m_tiles;          // ceil(nq / 128)
   int n_tiles;          // ceil(n_rows / 256)
-  int chunks;           // database split into this many contiguous tile ranges
-  int tiles_per_chunk;  // ceil(n_tiles / chunks)
+  int chunks;           // candidate runs per query (per epilogue set) = fixed_per_group + nb
+  int tiles_per_chunk;  // longest tile range one list covers
   int grid;             // persistent CTAs
+  // work assignment (k2_common.cuh: k2_segment)
+  int m_groups, n_units, fixed_per_group, quota, lr_t0, bt, nb;
   int epi_sets;         // epilogue warp sets = candidate runs per (query, chunk)
   int kc;               // candidates kept per run: 16 or 32
 };

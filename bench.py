@@ -183,12 +183,24 @@ def run_ours(args):
         ctx = None
         if gather:
             n_feat = 65_536                    # feature rows kept resident for the gather (3.4 GB bf16)
-            table = synthetic.features(n_feat, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev)
+            if world > 1:
+                # row-sharded feature table: each rank owns n_feat / world rows in an IPC-exportable
+                # block; the gather kernel reads peers' rows over NVLink through mapped pointers
+                rows_per = n_feat // world
+                block = m.alloc_feature_block(rows_per, L_TOK, C_FEAT, torch.bfloat16, dev)
+                synthetic.features(rows_per, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev,
+                                   first_row=rank * rows_per, out=block)
+                torch.cuda.synchronize()
+                ftable = m.open_peer_tables(m.FeatureTable(block, rows_per_shard=rows_per, shard_rank=rank,
+                                                           n_shards=world))
+            else:
+                table = synthetic.features(n_feat, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev)
+                ftable = m.FeatureTable(table)
             gg = torch.Generator(device=dev).manual_seed(4)
             sos = (torch.randn(1, L_TOK, C_FEAT, generator=gg, device=dev) / 32).bfloat16()
             un = torch.randn(L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
             cond = torch.randn(nq, (K_REF + 1) * L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
-            ctx = m.MotionContext(m.FeatureTable(table), sos, un, pe_max_length=256)
+            ctx = m.MotionContext(ftable, sos, un, pe_max_length=256)
 
         def step(i, timings=None):
             j = i % POOL

@@ -105,6 +105,9 @@ struct Plan {
 int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan* out) {
   if (!s || !p) return fail(MRAG_ERR_ARG, "null store or params");
   if (nq < 1) return fail(MRAG_ERR_ARG, "nq must be >= 1 (got %d)", nq);
+  if (nq > 65536)
+    return fail(MRAG_ERR_ARG, "nq must be <= 65536 per call (got %d): split the batch, the scan "
+                "cost per query does not improve beyond a few thousand queries", nq);
   if (p->k < 1 || p->k > 32) return fail(MRAG_ERR_ARG, "k must be in 1..32 (got %d)", p->k);
   if (p->metric < 0 || p->metric > 2) return fail(MRAG_ERR_ARG, "unknown metric %d", p->metric);
   if (p->filter_mode < 0 || p->filter_mode > 2)

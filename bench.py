@@ -36,6 +36,7 @@ WORKLOADS = {
     "c3q1": (10_000_000, 1, "clustered", "10M-entry DB row-sharded, single query"),
     "c3q4096": (10_000_000, 4096, "clustered", "10M-entry DB row-sharded, 4096-query batch"),
     "c4": (1_000_000, 16, "clustered", "1M-entry DB, 16-query batch + gather into CAMA context [16,250,1024] bf16"),
+    "c1q4": (1_000_000, 4, "clustered", "1M-entry DB, 4 queries per step (one streaming pass serves all four)"),
     "c1f": (1_000_000, 1, "clustered", "1M-entry DB, single query, fp32 master rows streamed (4 B/elt, ranking exact in fp32)"),
 }
 PATHS = {"c1f": "stream_f32"}
@@ -393,7 +394,7 @@ def run_ours(args):
     main = measure(args.workload, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
     extra = {}
     if not args.no_extras:
-        todo = [w for w in ("c1", "c1f", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
+        todo = [w for w in ("c1", "c1q4", "c1f", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
         for w in todo:
             try:
                 steps = 200 if WORKLOADS[w][1] == 1 else (30 if WORKLOADS[w][1] <= 16 else 8)

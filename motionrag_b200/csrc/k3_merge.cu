@@ -188,7 +188,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 constexpr int kMaxRerank = 64;
 constexpr int kMaxRuns = 1024;
 constexpr int kMaxSel = 2048;
-constexpr int kK3Threads = 512;
+constexpr int kK3Threads = 1024;  // 32 warps: one re-rank candidate / one qualifying run per warp
 
 __global__ void __launch_bounds__(kK3Threads)
     k3_merge_rerank_kernel(const uint64_t* __restrict__ cand, int n_runs, int run_len,
@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(kK3Threads)
     reinterpret_cast<float*>(rec + size_t(x.k_cap) * 8)[j] = rec_dist[j];
     reinterpret_cast<int32_t*>(rec + size_t(x.k_cap) * 12)[j] = rec_grp[j];
   }
-  __threadfence_system();
+  // The record stores above are ordered before the flag by the CTA barrier followed by a
+  // system-scope RELEASE store (release is cumulative over what happened-before it in this
+  // CTA); a separate __threadfence_system() per thread would only add a second fence round trip.
   __syncthreads();
   if (tid < x.world)
     st_release_sys(reinterpret_cast<uint32_t*>(x.bufs[tid] + flags_off) + cell, x.epoch);

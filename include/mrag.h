@@ -54,8 +54,9 @@ typedef enum mrag_metric {
 
 /* which scan kernel serves the query batch */
 typedef enum mrag_path {
-  MRAG_PATH_AUTO = 0,        /* nq <= 4 (and dim in {256,512,768,1024}): STREAM_BF16, else TENSOR_BF16 */
-  MRAG_PATH_STREAM_F32 = 1,  /* K1 on the fp32 master rows (ranking exact in fp32, 4 B/elt streamed) */
+  MRAG_PATH_AUTO = 0,        /* nq == 1 (and dim in {256,512,768,1024}): STREAM_BF16, else TENSOR_BF16 */
+  MRAG_PATH_STREAM_F32 = 1,  /* K1 on the fp32 master rows (ranking exact in fp32, 4 B/elt streamed);
+                                one pass over the table per 4 queries */
   MRAG_PATH_STREAM_BF16 = 2, /* K1 on the bf16 shadow rows + fp32 re-rank (2 B/elt streamed) */
   MRAG_PATH_TENSOR_BF16 = 3  /* K2 tcgen05 GEMM with fused epilogue top-k + fp32 re-rank */
 } mrag_path;

@@ -122,18 +122,21 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
   int path = p->path;
   // AUTO: scan the bf16 shadow (half the bytes), re-rank the candidates in fp32 from the master
   // rows — the role refine_factor plays in the reference's own call (src/data/rag.py:54)
+  // One query streams through K1; from two queries on the CUDA-core FMA rate would cap the bf16
+  // stream (4 queries: 0.55 ms vs 0.24 ms measured), while one padded 128-query tensor tile
+  // serves up to 128 queries at the HBM rate.
   if (path == MRAG_PATH_AUTO)
-    path = (nq <= 4 && k1_supported(s->dim, nq)) ? MRAG_PATH_STREAM_BF16 : MRAG_PATH_TENSOR_BF16;
+    path = (nq == 1 && k1_supported(s->dim, nq)) ? MRAG_PATH_STREAM_BF16 : MRAG_PATH_TENSOR_BF16;
   int refine = p->refine > 0 ? p->refine : 32;
   if (refine < p->k) refine = p->k;
   if (refine > 64) refine = 64;
   Plan pl;
   pl.path = path;
   if (path == MRAG_PATH_STREAM_F32 || path == MRAG_PATH_STREAM_BF16) {
-    if (!k1_supported(s->dim, nq))
+    // more than 4 queries are served by successive passes of <= 4 queries each
+    if (!k1_supported(s->dim, nq < 4 ? nq : 4))
       return fail(MRAG_ERR_UNSUPPORTED,
-                  "streaming path needs nq <= 4 and dim in {256,512,768,1024} (nq=%d dim=%d)", nq,
-                  s->dim);
+                  "streaming path needs dim in {256,512,768,1024} (dim=%d)", s->dim);
     const bool f32 = (path == MRAG_PATH_STREAM_F32);
     if (f32 && p->filter_mode != MRAG_FILTER_PRE) {
       pl.kc = (p->k <= 12) ? 16 : 32;
@@ -144,7 +147,7 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
       // top-`rerank` by scan score, which the exactness certificate (out_margin) relies on
       pl.rerank = refine > 32 ? 32 : refine;
     }
-    pl.k1_grid = k1_grid(s->n_rows, f32 ? 4 : 2, s->dim, nq, s->sm_count);
+    pl.k1_grid = k1_grid(s->n_rows, f32 ? 4 : 2, s->dim, nq < 4 ? nq : 4, s->sm_count);
     pl.cands_per_query = pl.k1_grid * pl.kc;
   } else if (path == MRAG_PATH_TENSOR_BF16) {
     if (!k2_supported(s->dim))
@@ -360,12 +363,16 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
   uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
 
   if (pl.path != MRAG_PATH_TENSOR_BF16 && before_scan) CK(cudaEventRecord(before_scan, st));
-  if (pl.path == MRAG_PATH_STREAM_F32) {
-    CK(launch_k1_stream(s->rows_f32, 4, s->n_rows, s->dim, queries_dev, nq, cand, pl.kc,
-                        pl.k1_grid, st));
-  } else if (pl.path == MRAG_PATH_STREAM_BF16) {
-    CK(launch_k1_stream(s->rows_bf16, 2, s->n_rows, s->dim, queries_dev, nq, cand, pl.kc,
-                        pl.k1_grid, st));
+  if (pl.path == MRAG_PATH_STREAM_F32 || pl.path == MRAG_PATH_STREAM_BF16) {
+    const bool f32 = pl.path == MRAG_PATH_STREAM_F32;
+    const void* rows = f32 ? static_cast<const void*>(s->rows_f32) : s->rows_bf16;
+    for (int q0 = 0; q0 < nq; q0 += 4) {  // one pass over the table per group of <= 4 queries
+      const int nqg = nq - q0 < 4 ? nq - q0 : 4;
+      // a 1..3-query tail uses the kernel instantiated for that count but is launched with the
+      // plan's grid, so every query shares one candidate layout ([nq][grid][kc])
+      CK(launch_k1_stream(rows, f32 ? 4 : 2, s->n_rows, s->dim, queries_dev + size_t(q0) * s->dim, nqg,
+                          cand + size_t(q0) * pl.cands_per_query, pl.kc, pl.k1_grid, st));
+    }
   } else {
     void* qb = ws + pl.off_qbf16;
     const size_t qb_bytes = size_t(pl.q_rows_padded) * s->dim * 2;

@@ -338,7 +338,7 @@ class RAGDatabase:
         """Queries whose bf16-scan result is not certified exact (margin <= eps, see mrag.h) are
         re-run on the fp32 master rows, 4 per pass; results are patched in place."""
         from .store import EPS, eps_typical
-        used = "stream_bf16" if (q.shape[0] <= 4 and self.path != "tensor_bf16") else "tensor_bf16"
+        used = "stream_bf16" if (self.path == "stream_bf16" or (self.path == "auto" and q.shape[0] == 1)) else "tensor_bf16"
         eps = EPS[used] if self.recheck == "strict" else eps_typical(used, q.shape[1])
         doubt = np.nonzero(~(margin > eps))[0]          # NaN counts as doubt
         self.fp32_rechecks += int(doubt.size)

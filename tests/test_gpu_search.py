@@ -54,6 +54,12 @@ def test_stream_f32_matches_oracle(case, nq, k):
     assert rep["index_mismatches"] == rep["near_tie_positions"]
 
 
+@pytest.mark.parametrize("nq,path", [(5, "stream_f32"), (11, "stream_f32"), (9, "stream_bf16")])
+def test_streaming_paths_loop_over_groups_of_four(case, nq, path):
+    rep = _run(case, nq, 12, path, filt="post", qoff=20)
+    assert rep["queries"] == nq
+
+
 @pytest.mark.parametrize("nq,k", [(1, 12), (4, 12), (3, 32), (2, 1)])
 def test_stream_bf16_rerank_matches_oracle(case, nq, k):
     _run(case, nq, k, "stream_bf16", qoff=11)
@@ -90,7 +96,7 @@ def test_video_exclusion_filter(case, path, nq, filt):
 
 def test_auto_path_dispatch(case):
     st = case["store"]
-    assert st.plan(1, k=12).path == 2 and st.plan(4, k=12).path == 2 and st.plan(5, k=12).path == 3
+    assert st.plan(1, k=12).path == 2 and st.plan(2, k=12).path == 3 and st.plan(5, k=12).path == 3
     p = st.plan(1, k=12, path="stream_f32")
     assert p.scan_bytes == case["n"] * 768 * 4 and p.cands_per_query == p.grid * 16
     assert st.plan(1, k=12).scan_bytes == case["n"] * 768 * 2 and st.plan(1, k=12).cands_per_query == st.plan(1, k=12).grid * 32
@@ -196,8 +202,8 @@ def test_argument_errors_are_loud(case):
     qd = torch.from_numpy(case["q"][:5]).cuda()
     with pytest.raises(MragError, match="k must be"):
         case["store"].search(qd, 33)
-    with pytest.raises(MragError, match="nq <= 4"):
-        case["store"].search(qd, 12, path="stream_f32")
+    with pytest.raises(MragError, match="nq must be <= 65536"):
+        case["store"].plan(70000, k=12)
     with pytest.raises(ValueError):
         case["store"].search(qd.double(), 12)
     with pytest.raises(MragError, match="capacity"):

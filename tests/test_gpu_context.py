@@ -83,3 +83,43 @@ def test_gather_argument_checks(libmrag):
         gather_context(ft, torch.zeros(1, 2, dtype=torch.int32).cuda(), z, z)
     with pytest.raises(ValueError):
         gather_context(ft, torch.zeros(1, 2, dtype=torch.int64).cuda(), z.float(), z)
+
+
+def test_attach_drives_a_cama_style_transformer_from_row_ids(libmrag):
+    """Face 2 end to end: a model with the reference's ActionTransformer surface
+    (encode_condition / transformer / batch_forward, src/projects/condition/module.py:270-323)
+    takes batch['ref_index'] after attach() and returns transformer(x, mask) with x built by K4."""
+    import torch.nn as nn
+    from motionrag_b200 import FeatureTable, MotionContext, attach
+    L, C, K, b, n = 25, 1024, 9, 2, 64
+    g = torch.Generator().manual_seed(0)
+    table = torch.randn(n, L, C, generator=g).bfloat16()
+    sos = (torch.randn(1, L, C, generator=g) / 32).bfloat16()
+    un = torch.randn(L, C, generator=g).bfloat16()
+    cond = torch.randn(b, (K + 1) * L, C, generator=g).bfloat16()
+    idx = torch.randint(0, n, (b, K), generator=g)
+    idx[1, 4] = -1
+
+    class Cama(nn.Module):          # the three members attach() touches
+        def __init__(self):
+            super().__init__()
+            layer = nn.TransformerEncoderLayer(C, 16, 4096, 0.0, "gelu", batch_first=True, norm_first=False)
+            self.transformer = nn.TransformerEncoder(layer, 1, enable_nested_tensor=False)
+
+        def encode_condition(self, images):
+            return images                                  # features supplied directly
+
+        def batch_forward(self, batch, return_loss=True, ignore_ref_loss=False):
+            raise AssertionError("the video path must not run when ref_index is given")
+
+    model = Cama().cuda().bfloat16().eval()
+    ctx = MotionContext(FeatureTable(table.cuda()), sos, un, pe_max_length=256)
+    attach(model, ctx)
+    with torch.no_grad():
+        pred = model.batch_forward({"ref_index": idx.cuda(), "ref_images": cond.cuda()}, return_loss=False)
+        x = cc.context_restatement(cc.gather_restatement(table, idx, un), sos, cc.sinusoid_table(256, C), cond.clone())
+        want = model.transformer(x.cuda(), cc.block_causal_mask(K + 1, L).cuda())
+    assert pred.shape == (b, K + 1, L, C)
+    assert torch.equal(pred.reshape(b, -1, C), want)       # same x, same mask -> same bits
+    with pytest.raises(NotImplementedError):
+        model.batch_forward({"ref_index": idx.cuda()}, return_loss=True)

@@ -418,3 +418,31 @@ def test_1m_batch_4096_filter_properties(big):
     for qi in range(0, 4096, 512):
         keep = [i for i, gq in zip(plain.index[qi].tolist(), plain.group[qi].tolist()) if gq != int(ex[qi])]
         assert res.index[qi, :len(keep)].tolist() == keep
+
+
+def test_10m_table_properties_single_gpu(libmrag):
+    """BASELINE config 3 size on one GPU (30.7 GB fp32 + 15.4 GB bf16): self-retrieval, ordering,
+    agreement of the three scan paths, exact distances — properties that need no 10 M-row oracle."""
+    from motionrag_b200 import EmbeddingStore, synthetic
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 << 30:
+        pytest.skip("needs ~50 GB of free HBM")
+    n = 10_000_000
+    st = EmbeddingStore(768, n, 0)
+    synthetic.fill_store(st, n, "clustered", seed=2)
+    assert len(st) == n and st.info().max_norm_deviation < 1e-5
+    src = torch.randint(0, n, (260,), generator=torch.Generator().manual_seed(1)).cuda()
+    q = synthetic.queries_from_rows(st.rows_f32()[src], seed=5)
+    big = st.search(q, 12)                                           # tensor path, CTA pairs
+    assert torch.equal(big.index[:, 0], src)
+    assert bool((big.distance[:, 1:] >= big.distance[:, :-1]).all()) and bool((big.index >= 0).all())
+    rows = st.rows_f32()[big.index.flatten()].view(260, 12, 768).double()
+    exact = ((rows - q[:, None].double()) ** 2).sum(-1)
+    assert torch.allclose(big.distance.double(), exact, rtol=1e-3, atol=1e-6)
+    for path in ("stream_bf16", "stream_f32"):
+        one = st.search(q[:3].contiguous(), 12, path=path)
+        same = one.index == big.index[:3]
+        if not bool(same.all()):                                     # only near-ties may differ
+            assert torch.allclose(one.distance, big.distance[:3], rtol=1e-3, atol=1e-6)
+        assert torch.equal(one.index[:, 0], src[:3])
+    st.close()

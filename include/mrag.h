@@ -209,6 +209,39 @@ MRAG_API int mrag_gather_context(const void* const* shard_ptrs_dev, int32_t nsha
                         void* out_dev, int32_t b, int32_t K, int32_t L, int32_t C, int32_t dtype,
                         void* stream);
 
+/* ---- CAMA causal motion transformer forward (consumer of the gathered context) ----
+ * torch.nn.TransformerEncoder(num_layers, TransformerEncoderLayer(d_model, nhead, dim_feedforward,
+ * dropout=0, activation="gelu", batch_first=True, norm_first=False, bias=True)) with the block-causal
+ * mask of ActionTransformer.get_mask (reference configs/cogvideox/MotionRAG_open.yml:253-267,
+ * src/projects/condition/module.py:131-135, 303-306). All weights are bf16 device pointers in
+ * PyTorch's own layouts (Linear.weight = [out, in]); the caller keeps them alive. */
+typedef struct mrag_cama_layer {
+  const void *w_qkv, *b_qkv; /* self_attn.in_proj_weight [3d, d], in_proj_bias [3d] */
+  const void *w_o, *b_o;     /* self_attn.out_proj.weight [d, d], .bias [d]          */
+  const void *w_1, *b_1;     /* linear1.weight [d_ff, d], .bias [d_ff]               */
+  const void *w_2, *b_2;     /* linear2.weight [d, d_ff], .bias [d]                  */
+  const void *ln1_g, *ln1_b; /* norm1.weight / .bias [d]                             */
+  const void *ln2_g, *ln2_b; /* norm2.weight / .bias [d]                             */
+} mrag_cama_layer;
+typedef struct mrag_cama mrag_cama;
+/* head_dim must be 64, d_model in {256,512,768,1024}, d_ff a multiple of 512; tokens = groups *
+ * group_tokens (10 * 25 in the reference); workspace for max_batch samples is owned by the handle */
+MRAG_API int mrag_cama_create(int32_t n_layers, const mrag_cama_layer* layers, int32_t d_model,
+                              int32_t n_heads, int32_t d_ff, int32_t groups, int32_t group_tokens,
+                              int32_t max_batch, int32_t device, mrag_cama** out);
+MRAG_API int mrag_cama_destroy(mrag_cama* c);
+/* device pointers of the handle's input [max_batch, tokens, d_model] bf16 (write the context here —
+ * mrag_gather_context can target it directly) and output [max_batch, tokens, d_model] bf16 buffers */
+MRAG_API int mrag_cama_io(const mrag_cama* c, void** x_in_dev, void** y_out_dev);
+/* runs the n_layers forward for the first b samples of the input buffer on `stream`; with use_graph
+ * the 7*n_layers launch chain is captured once per b and replayed as one CUDA graph */
+MRAG_API int mrag_cama_forward(mrag_cama* c, int32_t b, int32_t use_graph, void* stream);
+/* the GEMM building block on its own (tests / profiling): C[M,N] = A[M,K] W[N,K]^T (+bias)(gelu) to
+ * bf16, or fp32 partial sums [splits][M,N] when out_bf16_dev is NULL; N %% 128 == 0, K %% 64 == 0 */
+MRAG_API int mrag_linear(const void* a_dev, int32_t a_rows_alloc, const void* w_dev, int32_t M, int32_t N,
+                         int32_t K, const void* bias_dev, int32_t gelu, void* out_bf16_dev,
+                         float* partial_dev, int32_t splits, void* stream);
+
 /* plain cudaMalloc / cudaFree on `device` (IPC-exportable blocks for sharded feature tables) */
 MRAG_API int mrag_device_alloc(int32_t device, size_t bytes, void** dev_ptr_out);
 MRAG_API int mrag_device_free(int32_t device, void* dev_ptr);

@@ -7,6 +7,7 @@ top (`RAGDatabase`, src/data/rag.py; the ActionTransformer context contract,
 src/projects/condition/module.py:298-301). No CPU fallback exists anywhere in this package.
 """
 from ._cabi import MragError, launch_count  # noqa: F401
+from .cama import CamaTransformer  # noqa: F401
 from .context import (MotionContext, attach, block_causal_mask, gather_context, select_refs,  # noqa: F401
                       sinusoid_table)
 from .parallel import (PeerExchange, ShardedRetriever, alloc_feature_block, open_peer_tables,  # noqa: F401

@@ -54,6 +54,11 @@ class Exchange(C.Structure):
                 ("epoch", C.c_uint32), ("reserved", C.c_int32), ("bufs_dev", C.c_void_p)]
 
 
+class CamaLayer(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_qkv", "b_qkv", "w_o", "b_o", "w_1", "b_1", "w_2", "b_2",
+                                          "ln1_g", "ln1_b", "ln2_g", "ln2_b")]
+
+
 # name -> (restype, argtypes); mirrors include/mrag.h one to one (tests check the list)
 SIGNATURES = {
     "mrag_abi_version": (C.c_int, []),
@@ -82,6 +87,13 @@ SIGNATURES = {
     "mrag_gather_context": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "mrag_cama_create": (C.c_int, [C.c_int32, C.POINTER(CamaLayer), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "mrag_cama_destroy": (C.c_int, [C.c_void_p]),
+    "mrag_cama_io": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "mrag_cama_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "mrag_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                              C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mrag_device_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]),
     "mrag_device_free": (C.c_int, [C.c_int32, C.c_void_p]),
     "mrag_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

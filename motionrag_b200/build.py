@@ -20,7 +20,7 @@ OUT_DIR = PKG / "_lib"
 LIB = OUT_DIR / "libmrag.so"
 STAMP = OUT_DIR / "libmrag.stamp"
 
-SOURCES = ["api.cu", "k1_stream.cu", "k2_batch.cu", "k2_batch2.cu", "k3_merge.cu", "k4_gather.cu"]
+SOURCES = ["api.cu", "api_cama.cu", "k1_stream.cu", "k2_batch.cu", "k2_batch2.cu", "k3_merge.cu", "k4_gather.cu", "k5_cama.cu"]
 HEADERS = ["common.cuh", "kernels.h", "k2_common.cuh"]
 
 NVCC_FLAGS = [

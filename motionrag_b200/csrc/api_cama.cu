@@ -1,0 +1,199 @@
+// C ABI of the CAMA transformer forward (include/mrag.h, "next" row f-1). Host orchestration
+// only: buffers, the launch chain of K5/K6/K7 and its CUDA-graph replay.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/mrag.h"
+#include "kernels.h"
+
+namespace mrag {
+int api_fail(int code, const char* fmt, ...);  // api.cu
+}
+using namespace mrag;
+
+struct mrag_cama {
+  int n_layers = 0, d = 0, heads = 0, dff = 0, groups = 0, gtok = 0, T = 0, max_b = 0, device = 0;
+  int rows_alloc = 0;  // max_b * T rounded up to 128
+  std::vector<mrag_cama_layer> layers;
+  char* buf = nullptr;  // one allocation, carved below
+  void *x_in = nullptr, *x_a = nullptr, *x_b = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *y_out = nullptr;
+  float* partial = nullptr;
+  struct Graph {
+    int b;
+    cudaGraphExec_t exec;
+  };
+  std::vector<Graph> graphs;
+  cudaStream_t capture_stream = nullptr;
+};
+
+namespace {
+constexpr int kSplitsO = 4;   // out-proj: K = d      (16 k-blocks at d = 1024)
+constexpr int kSplitsF = 8;   // ffn2    : K = d_ff   (64 k-blocks at d_ff = 4096)
+
+struct Guard {
+  int prev = -1;
+  explicit Guard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~Guard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
+  const int M = b * c->T, d = c->d, dff = c->dff;
+  const void* xin = c->x_in;
+  cudaError_t e = cudaSuccess;
+  for (int l = 0; l < c->n_layers && e == cudaSuccess; ++l) {
+    const mrag_cama_layer& w = c->layers[l];
+    void* x1 = c->x_a;
+    void* x2 = (l == c->n_layers - 1) ? c->y_out : c->x_b;
+    e = launch_k5_linear(xin, c->rows_alloc, w.w_qkv, M, 3 * d, d, w.b_qkv, false, c->qkv, nullptr, 1, st);
+    if (e == cudaSuccess) e = launch_k6_attention(c->qkv, c->att, b, c->T, d, c->heads, c->groups, c->gtok, st);
+    if (e == cudaSuccess)
+      e = launch_k5_linear(c->att, c->rows_alloc, w.w_o, M, d, d, nullptr, false, nullptr, c->partial, kSplitsO, st);
+    if (e == cudaSuccess)
+      e = launch_k7_add_layernorm(xin, c->partial, kSplitsO, w.b_o, w.ln1_g, w.ln1_b, x1, M, d, 1e-5f, st);
+    if (e == cudaSuccess) e = launch_k5_linear(x1, c->rows_alloc, w.w_1, M, dff, d, w.b_1, true, c->h, nullptr, 1, st);
+    if (e == cudaSuccess)
+      e = launch_k5_linear(c->h, c->rows_alloc, w.w_2, M, d, dff, nullptr, false, nullptr, c->partial, kSplitsF, st);
+    if (e == cudaSuccess)
+      e = launch_k7_add_layernorm(x1, c->partial, kSplitsF, w.b_2, w.ln2_g, w.ln2_b, x2, M, d, 1e-5f, st);
+    xin = x2;
+  }
+  return e;
+}
+}  // namespace
+
+extern "C" {
+
+int mrag_cama_create(int32_t n_layers, const mrag_cama_layer* layers, int32_t d_model, int32_t n_heads,
+                     int32_t d_ff, int32_t groups, int32_t group_tokens, int32_t max_batch, int32_t device,
+                     mrag_cama** out) {
+  if (!out || !layers) return api_fail(MRAG_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (n_layers < 1 || n_layers > 64 || max_batch < 1 || groups < 1 || group_tokens < 1)
+    return api_fail(MRAG_ERR_ARG, "bad transformer shape");
+  if (d_model != n_heads * 64 || d_model % 256 != 0 || d_model > 1024 || d_ff % 128 != 0 ||
+      (d_model / 64) % kSplitsO != 0 || (d_ff / 64) % kSplitsF != 0)
+    return api_fail(MRAG_ERR_UNSUPPORTED,
+                    "kernels are built for head_dim 64, d_model in {256,512,768,1024} and d_ff %% 512 == 0 "
+                    "(got d_model %d, heads %d, d_ff %d)", d_model, n_heads, d_ff);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return api_fail(MRAG_ERR_DEVICE, "no such CUDA device %d: libmrag has no CPU path", device);
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return api_fail(MRAG_ERR_DEVICE, "device %d is not sm_100-class", device);
+  Guard g(device);
+  mrag_cama* c = new (std::nothrow) mrag_cama();
+  if (!c) return api_fail(MRAG_ERR_CAPACITY, "host allocation failed");
+  c->n_layers = n_layers;
+  c->d = d_model;
+  c->heads = n_heads;
+  c->dff = d_ff;
+  c->groups = groups;
+  c->gtok = group_tokens;
+  c->T = groups * group_tokens;
+  c->max_b = max_batch;
+  c->device = device;
+  c->rows_alloc = (max_batch * c->T + 127) / 128 * 128;
+  c->layers.assign(layers, layers + n_layers);
+  const size_t R = size_t(c->rows_alloc);
+  const size_t sz_x = R * d_model * 2, sz_qkv = R * 3 * d_model * 2, sz_h = R * d_ff * 2;
+  const size_t sz_p = size_t(kSplitsF) * R * d_model * 4;
+  const size_t total = 5 * sz_x + sz_qkv + sz_h + sz_p;
+  if (cudaMalloc(reinterpret_cast<void**>(&c->buf), total) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return api_fail(MRAG_ERR_CUDA, "cannot allocate %zu bytes of transformer workspace", total);
+  }
+  cudaMemset(c->buf, 0, total);
+  char* p = c->buf;
+  c->x_in = p; p += sz_x;
+  c->x_a = p; p += sz_x;
+  c->x_b = p; p += sz_x;
+  c->att = p; p += sz_x;
+  c->y_out = p; p += sz_x;
+  c->qkv = p; p += sz_qkv;
+  c->h = p; p += sz_h;
+  c->partial = reinterpret_cast<float*>(p);
+  *out = c;
+  return MRAG_OK;
+}
+
+int mrag_cama_destroy(mrag_cama* c) {
+  if (!c) return MRAG_OK;
+  Guard g(c->device);
+  for (auto& gr : c->graphs) cudaGraphExecDestroy(gr.exec);
+  if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
+  cudaFree(c->buf);
+  delete c;
+  return MRAG_OK;
+}
+
+int mrag_cama_io(const mrag_cama* c, void** x_in_dev, void** y_out_dev) {
+  if (!c) return api_fail(MRAG_ERR_ARG, "null handle");
+  if (x_in_dev) *x_in_dev = c->x_in;
+  if (y_out_dev) *y_out_dev = c->y_out;
+  return MRAG_OK;
+}
+
+int mrag_cama_forward(mrag_cama* c, int32_t b, int32_t use_graph, void* stream) {
+  if (!c) return api_fail(MRAG_ERR_ARG, "null handle");
+  if (b < 1 || b > c->max_b) return api_fail(MRAG_ERR_ARG, "batch %d outside 1..%d", b, c->max_b);
+  Guard g(c->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!use_graph) {
+    cudaError_t e = run_chain(c, b, st);
+    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "transformer launch chain: %s", cudaGetErrorString(e));
+    return MRAG_OK;
+  }
+  cudaGraphExec_t exec = nullptr;
+  for (auto& gr : c->graphs)
+    if (gr.b == b) exec = gr.exec;
+  if (!exec) {
+    if (!c->capture_stream &&
+        cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return api_fail(MRAG_ERR_CUDA, "cannot create the capture stream");
+    cudaError_t e = cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e));
+    cudaError_t ce = run_chain(c, b, c->capture_stream);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(c->capture_stream, &graph);
+    if (ce != cudaSuccess || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return api_fail(MRAG_ERR_CUDA, "capture of the transformer chain: %s",
+                      cudaGetErrorString(ce != cudaSuccess ? ce : e));
+    }
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+    c->graphs.push_back({b, exec});
+  }
+  cudaError_t e = cudaGraphLaunch(exec, st);
+  if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "graph launch: %s", cudaGetErrorString(e));
+  note_launch(7 * c->n_layers);
+  return MRAG_OK;
+}
+
+int mrag_linear(const void* a_dev, int32_t a_rows_alloc, const void* w_dev, int32_t M, int32_t N, int32_t K,
+                const void* bias_dev, int32_t gelu, void* out_bf16_dev, float* partial_dev, int32_t splits,
+                void* stream) {
+  if (!a_dev || !w_dev || (!out_bf16_dev && !partial_dev)) return api_fail(MRAG_ERR_ARG, "null device buffer");
+  if (splits < 1 || (K / 64) % splits != 0) return api_fail(MRAG_ERR_ARG, "splits must divide K/64");
+  cudaError_t e = launch_k5_linear(a_dev, a_rows_alloc, w_dev, M, N, K, bias_dev, gelu != 0, out_bf16_dev,
+                                   partial_dev, splits, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "linear: %s", cudaGetErrorString(e));
+  return MRAG_OK;
+}
+
+}  // extern "C"

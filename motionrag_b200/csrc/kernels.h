@@ -82,4 +82,16 @@ cudaError_t launch_k4_gather(const void* const* shard_ptrs, int nshards, int64_t
                              const void* pe, const void* cond, void* out, int b, int K, int L,
                              int C, int dtype, cudaStream_t st);
 
+// K5/K6/K7: CAMA transformer pieces (k5_cama.cu) ------------------------------------------------
+// C[M,N] = A[M,K] W[N,K]^T (+bias)(gelu) -> bf16 `out`, or fp32 partial sums [splits][M,N] when out
+// is null. a_rows_alloc = rows the A buffer really has (>= M rounded up to 128).
+cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w_bf16, int M, int N, int K,
+                             const void* bias, bool gelu, void* out_bf16, float* partial, int splits,
+                             cudaStream_t st);
+cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_model, int heads,
+                                int groups, int group_tokens, cudaStream_t st);
+cudaError_t launch_k7_add_layernorm(const void* resid, const float* partial, int splits, const void* bias,
+                                    const void* gamma, const void* beta, void* out, int M, int d, float eps,
+                                    cudaStream_t st);
+
 }  // namespace mrag

@@ -1,0 +1,98 @@
+"""CAMA transformer forward (K5/K6/K7) against the reference's torch.nn.TransformerEncoder."""
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import cama_context as cc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K,bias,gelu,splits", [(250, 3072, 1024, True, False, 1), (250, 4096, 1024, True, True, 1),
+                                                    (250, 1024, 4096, False, False, 8), (250, 1024, 1024, False, False, 4),
+                                                    (4000, 1024, 1024, True, False, 1), (37, 128, 64, False, False, 1),
+                                                    (129, 256, 192, True, True, 3)])
+def test_linear_matches_fp32_matmul(libmrag, M, N, K, bias, gelu, splits):
+    from motionrag_b200.cama import linear
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, generator=g).bfloat16() if bias else None
+    want = a.float() @ w.float().T
+    got = linear(a.cuda(), w.cuda(), b.cuda() if bias else None, gelu, splits)
+    if splits > 1:
+        got = got.sum(0).cpu()
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-4)          # fp32 partial sums: only fp32 rounding
+    else:
+        if bias:
+            want = want + b.float()
+        if gelu:
+            want = torch.nn.functional.gelu(want)
+        assert torch.allclose(got.float().cpu(), want, rtol=1.6e-2, atol=1e-2)   # one bf16 rounding of the output
+        assert torch.equal(got.cpu(), want.bfloat16()) or (got.float().cpu() - want).abs().max() < 2e-2
+
+
+def _encoder(d, heads, dff, layers, seed):
+    torch.manual_seed(seed)
+    layer = nn.TransformerEncoderLayer(d, heads, dff, 0.0, "gelu", batch_first=True, norm_first=False, bias=True)
+    enc = nn.TransformerEncoder(layer, layers, enable_nested_tensor=False).eval()
+    with torch.no_grad():                       # non-trivial norms / biases, bf16-representable weights
+        for p in enc.parameters():
+            if p.ndim == 1:
+                p.add_(0.1 * torch.randn_like(p))
+            p.copy_(p.bfloat16().float())
+    return enc
+
+
+@pytest.mark.parametrize("b,G,L,d,heads,dff,layers", [(1, 10, 25, 1024, 16, 4096, 4), (3, 10, 25, 1024, 16, 4096, 4),
+                                                      (2, 4, 5, 256, 4, 512, 2)])
+def test_forward_matches_reference_encoder(libmrag, b, G, L, d, heads, dff, layers):
+    """Reference configuration (configs/cogvideox/MotionRAG_open.yml:253-267) and a small one."""
+    from motionrag_b200 import CamaTransformer
+    enc = _encoder(d, heads, dff, layers, seed=b + G)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(b, G * L, d, generator=g).bfloat16()
+    mask = cc.block_causal_mask(G, L)
+    with torch.no_grad():
+        want = enc(x.float(), mask)                                   # fp32 evaluation = the oracle
+        torch_bf16 = enc.cuda().bfloat16()(x.cuda(), mask.cuda()).float().cpu()
+    cama = CamaTransformer(enc, groups=G, group_tokens=L, max_batch=4, device=0)
+    got = cama.forward(x.cuda()).float().cpu()
+    got_nograph = cama.forward(x.cuda(), use_graph=False).float().cpu()
+    assert torch.equal(got, got_nograph)                               # graph replay == direct launches
+    err = (got - want).abs()
+    err_torch = (torch_bf16 - want).abs()
+    # outputs are LayerNorm-ed (unit scale): bf16 carries ~3 significant digits
+    assert float(err.max()) < 6e-2 and float(err.mean()) < 6e-3, (float(err.max()), float(err.mean()))
+    assert float(err.mean()) <= 1.25 * float(err_torch.mean()) + 1e-4, (float(err.mean()), float(err_torch.mean()))
+    assert torch.equal(cama.predict(b=b).float().cpu(), got[:, -L:])
+    # in-place input: the gather can write straight into the handle's buffer
+    cama.input_view(b).copy_(x.cuda())
+    assert torch.equal(cama.forward(b=b).float().cpu(), got)
+    cama.close()
+
+
+def test_block_causality(libmrag):
+    """Changing a later group must not change the outputs of earlier groups (get_mask semantics)."""
+    from motionrag_b200 import CamaTransformer
+    G, L, d = 10, 25, 1024
+    enc = _encoder(d, 16, 4096, 2, seed=3)
+    cama = CamaTransformer(enc, groups=G, group_tokens=L, max_batch=2, device=0)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, G * L, d, generator=g).bfloat16().cuda()
+    y0 = cama.forward(x).clone()
+    x2 = x.clone()
+    x2[:, 6 * L:] += 1.0
+    y1 = cama.forward(x2)
+    assert torch.equal(y0[:, :6 * L], y1[:, :6 * L]) and not torch.equal(y0[:, 6 * L:], y1[:, 6 * L:])
+    cama.close()
+
+
+def test_unsupported_shapes_are_loud(libmrag):
+    from motionrag_b200 import CamaTransformer, MragError
+    enc = _encoder(192, 2, 512, 1, seed=0)                            # head_dim 96
+    with pytest.raises(MragError, match="head_dim 64"):
+        CamaTransformer(enc, groups=2, group_tokens=4, max_batch=1)
+    layer = nn.TransformerEncoderLayer(256, 4, 512, 0.0, "relu", batch_first=True)
+    with pytest.raises(ValueError, match="gelu"):
+        CamaTransformer(nn.TransformerEncoder(layer, 1), groups=2, group_tokens=4)

@@ -34,6 +34,14 @@ namespace {
 constexpr int kSplitsO = 4;   // out-proj: K = d      (16 k-blocks at d = 1024)
 constexpr int kSplitsF = 8;   // ffn2    : K = d_ff   (64 k-blocks at d_ff = 4096)
 
+// split K only as far as needed to give every SM a tile: the fp32 partial sums cost HBM traffic
+int pick_splits(int M, int N, int max_splits) {
+  const int tiles = ((M + 127) / 128) * (N / 128);
+  int s = 1;
+  while (s < max_splits && tiles * s < 148) s *= 2;
+  return s;
+}
+
 struct Guard {
   int prev = -1;
   explicit Guard(int dev) {
@@ -50,6 +58,7 @@ cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
   const int M = b * c->T, d = c->d, dff = c->dff;
   const void* xin = c->x_in;
   cudaError_t e = cudaSuccess;
+  const int so = pick_splits(M, d, kSplitsO), sf = pick_splits(M, d, kSplitsF);
   for (int l = 0; l < c->n_layers && e == cudaSuccess; ++l) {
     const mrag_cama_layer& w = c->layers[l];
     void* x1 = c->x_a;
@@ -57,14 +66,14 @@ cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
     e = launch_k5_linear(xin, c->rows_alloc, w.w_qkv, M, 3 * d, d, w.b_qkv, false, c->qkv, nullptr, 1, st);
     if (e == cudaSuccess) e = launch_k6_attention(c->qkv, c->att, b, c->T, d, c->heads, c->groups, c->gtok, st);
     if (e == cudaSuccess)
-      e = launch_k5_linear(c->att, c->rows_alloc, w.w_o, M, d, d, nullptr, false, nullptr, c->partial, kSplitsO, st);
+      e = launch_k5_linear(c->att, c->rows_alloc, w.w_o, M, d, d, nullptr, false, nullptr, c->partial, so, st);
     if (e == cudaSuccess)
-      e = launch_k7_add_layernorm(xin, c->partial, kSplitsO, w.b_o, w.ln1_g, w.ln1_b, x1, M, d, 1e-5f, st);
+      e = launch_k7_add_layernorm(xin, c->partial, so, w.b_o, w.ln1_g, w.ln1_b, x1, M, d, 1e-5f, st);
     if (e == cudaSuccess) e = launch_k5_linear(x1, c->rows_alloc, w.w_1, M, dff, d, w.b_1, true, c->h, nullptr, 1, st);
     if (e == cudaSuccess)
-      e = launch_k5_linear(c->h, c->rows_alloc, w.w_2, M, d, dff, nullptr, false, nullptr, c->partial, kSplitsF, st);
+      e = launch_k5_linear(c->h, c->rows_alloc, w.w_2, M, d, dff, nullptr, false, nullptr, c->partial, sf, st);
     if (e == cudaSuccess)
-      e = launch_k7_add_layernorm(x1, c->partial, kSplitsF, w.b_2, w.ln2_g, w.ln2_b, x2, M, d, 1e-5f, st);
+      e = launch_k7_add_layernorm(x1, c->partial, sf, w.b_2, w.ln2_g, w.ln2_b, x2, M, d, 1e-5f, st);
     xin = x2;
   }
   return e;

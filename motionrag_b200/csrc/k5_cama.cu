@@ -21,10 +21,17 @@
 
 namespace mrag {
 
-constexpr int kGemmBM = 128, kGemmBN = 128, kGemmStages = 6, kGemmThreads = 192;
-constexpr uint32_t kGemmABytes = kGemmBM * kBK * 2, kGemmBBytes = kGemmBN * kBK * 2;
-constexpr uint32_t kGemmStageBytes = kGemmABytes + kGemmBBytes;
-constexpr uint32_t kGemmSmem = kGemmStages * kGemmStageBytes + 256 + 1024;
+constexpr int kGemmBM = 128, kGemmThreads = 192;
+constexpr uint32_t kGemmABytes = kGemmBM * kBK * 2;
+// BN = 128 by default; BN = 64 doubles the CTA count when a GEMM would otherwise leave most SMs idle.
+// STAGES = 6 (one CTA per SM) for grids of at most one wave; STAGES = 3 lets two CTAs share an SM so
+// that one tile's epilogue overlaps the other's main loop when there are several waves of tiles.
+template <int BN, int STAGES>
+struct GemmCfg {
+  static constexpr uint32_t kBBytes = BN * kBK * 2;
+  static constexpr uint32_t kStageBytes = kGemmABytes + kBBytes;
+  static constexpr uint32_t kSmem = STAGES * kStageBytes + 256 + 1024;
+};
 
 struct GemmArgs {
   int M, N, K;          // C[M,N] = A[M,K] W[N,K]^T ; K multiple of 64, N multiple of 128
@@ -37,9 +44,13 @@ struct GemmArgs {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
     k5_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                      const GemmArgs g) {
+  constexpr uint32_t kGemmStageBytes = GemmCfg<BN, STAGES>::kStageBytes;
+  constexpr int kGemmBN = BN;
+  constexpr int kGemmStages = STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
@@ -65,7 +76,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     mbar_init(tfull_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -161,160 +172,294 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<BN>(tmem_base);
   }
 }
 
 // ---- K6: block-causal attention, head_dim 64 ---------------------------------------------------
-// grid (b * heads, groups); block 128 threads. Group g attends to keys of groups 0..g.
+// grid (b * heads, groups, 32-row blocks of a group). Group g attends to the keys of groups 0..g
+// (get_mask), so there is no mask inside a CTA apart from the padding of the last 64-key chunk.
 // qkv [M, 3*d] bf16 (q | k | v, head h at columns h*64 inside each third), out [M, d] bf16.
+// The shapes (25 query rows x <= 250 keys x 64 dims per CTA) are far below a tcgen05 tile (M >= 64
+// per instruction, one issuing thread, TMEM round trips), so this kernel uses warp-level
+// mma.sync.m16n8k16 bf16 with fp32 accumulation: 4 warps = 2 query tiles of 16 rows x 2 key-chunk
+// parities; each warp walks its 64-key chunks with an online softmax (scores and the running
+// output never leave registers; P is re-used as the A operand of P V straight from the score
+// accumulators), the two parities are merged through shared memory at the end. K and V rows of the
+// visible prefix are staged once per CTA with cp.async as bf16, rows padded to 144 B so the
+// B-fragment loads (32-bit for K, ldmatrix.trans for V) are bank-conflict free.
 constexpr int kAttnThreads = 128;
 constexpr int kHeadDim = 64;
-constexpr int kKeyStride = 66;  // bf16 elements per staged key/value row: 33 words -> conflict-free
+constexpr int kKVStride = 72;   // bf16 elements per staged K / V row
+constexpr int kKeyChunk = 64;
+constexpr int kAttnMaxT = 704;  // staged K + V of the longest prefix must fit in shared memory
 
-__global__ void __launch_bounds__(kAttnThreads)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 3)
     k6_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
-                        int d_model, int heads, int group_tokens, float scale) {
+                        int d_model, int heads, int group_tokens, float scale_log2e) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  const int bh = blockIdx.x, g = blockIdx.y;
+  const int bh = blockIdx.x;
   const int b = bh / heads, h = bh % heads;
-  const int nk = (g + 1) * group_tokens;  // visible keys
-  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* vs = ks + size_t(nk) * kKeyStride;
-  float* probs = reinterpret_cast<float*>(vs + size_t(nk) * kKeyStride);  // [4 warps][nk]
-  float* qs = probs + 4 * nk;                                              // [4 warps][64]
+  const int g = int(gridDim.y) - 1 - int(blockIdx.y);  // longest key prefixes first
+  const int nk = (g + 1) * group_tokens;               // visible keys
+  const int n_chunks = (nk + kKeyChunk - 1) / kKeyChunk;
+  const int rows_pad = n_chunks * kKeyChunk;
+  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem_attn);  // [rows_pad][72]
+  __nv_bfloat16* vs = ks + size_t(rows_pad) * kKVStride;            // [rows_pad][72]
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int quad = lane >> 2, qlane = lane & 3;
   const size_t row_stride = size_t(3) * d_model;
   const __nv_bfloat16* base = qkv + size_t(b) * T * row_stride;
-  // stage K and V rows of this head: 64 bf16 = 128 B per row, 4-byte words
-  for (int i = tid; i < nk * 32; i += kAttnThreads) {
-    const int r = i >> 5, w = i & 31;
-    const uint32_t kw = *reinterpret_cast<const uint32_t*>(base + size_t(r) * row_stride + d_model + h * kHeadDim + 2 * w);
-    const uint32_t vw = *reinterpret_cast<const uint32_t*>(base + size_t(r) * row_stride + 2 * d_model + h * kHeadDim + 2 * w);
-    *reinterpret_cast<uint32_t*>(ks + size_t(r) * kKeyStride + 2 * w) = kw;
-    *reinterpret_cast<uint32_t*>(vs + size_t(r) * kKeyStride + 2 * w) = vw;
+
+  // stage K and V rows of this head (16-byte pieces); rows of the last chunk beyond nk are zeroed
+  // (their scores are masked, but 0 * garbage must not produce NaN in P V)
+  for (int i = tid; i < rows_pad * 8; i += kAttnThreads) {
+    const int r = i >> 3, c = i & 7;
+    __nv_bfloat16* dk = ks + size_t(r) * kKVStride + 8 * c;
+    __nv_bfloat16* dv = vs + size_t(r) * kKVStride + 8 * c;
+    if (r < nk) {
+      const __nv_bfloat16* src = base + size_t(r) * row_stride + h * kHeadDim + 8 * c;
+      cp_async_16(dk, src + d_model);
+      cp_async_16(dv, src + 2 * d_model);
+    } else {
+      *reinterpret_cast<uint4*>(dk) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dv) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  // query fragments (A operand, 16 rows x 64 dims) straight from global while the copies fly
+  const int mt = warp & 1, par = warp >> 1;
+  const int r0 = int(blockIdx.z) * 32 + mt * 16 + quad, r1 = r0 + 8;
+  const bool valid0 = r0 < group_tokens, valid1 = r1 < group_tokens;
+  const __nv_bfloat16* q0 = base + size_t(g * group_tokens + (valid0 ? r0 : 0)) * row_stride + h * kHeadDim;
+  const __nv_bfloat16* q1 = base + size_t(g * group_tokens + (valid1 ? r1 : 0)) * row_stride + h * kHeadDim;
+  uint32_t qa[4][4];
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    const int col = 16 * kt + 2 * qlane;
+    qa[kt][0] = valid0 ? __ldg(reinterpret_cast<const uint32_t*>(q0 + col)) : 0u;
+    qa[kt][1] = valid1 ? __ldg(reinterpret_cast<const uint32_t*>(q1 + col)) : 0u;
+    qa[kt][2] = valid0 ? __ldg(reinterpret_cast<const uint32_t*>(q0 + col + 8)) : 0u;
+    qa[kt][3] = valid1 ? __ldg(reinterpret_cast<const uint32_t*>(q1 + col + 8)) : 0u;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // running max / per-lane partial sums of rows r0, r1
+  const uint32_t vs_u32 = smem_u32(vs);
+  for (int ch = par; ch < n_chunks; ch += 2) {
+    const int key0 = ch * kKeyChunk;
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const __nv_bfloat16* kp = ks + size_t(key0 + 8 * j + quad) * kKVStride + 2 * qlane;
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt)
+        mma_bf16_16816(s[j], qa[kt], *reinterpret_cast<const uint32_t*>(kp + 16 * kt),
+                       *reinterpret_cast<const uint32_t*>(kp + 16 * kt + 8));
+    }
+    if (key0 + kKeyChunk > nk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int key = key0 + 8 * j + 2 * qlane;
+        if (key >= nk) s[j][0] = s[j][2] = -INFINITY;
+        if (key + 1 >= nk) s[j][1] = s[j][3] = -INFINITY;
+      }
+    }
+    float c0 = -INFINITY, c1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c0 = fmaxf(c0, fmaxf(s[j][0], s[j][1]));
+      c1 = fmaxf(c1, fmaxf(s[j][2], s[j][3]));
+    }
+    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1));
+    c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1));
+    c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
+    const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);  // finite: every chunk holds a visible key
+    const float a0 = exp2f((m0 - n0) * scale_log2e), a1 = exp2f((m1 - n1) * scale_log2e);
+    m0 = n0;
+    m1 = n1;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = exp2f((s[j][0] - m0) * scale_log2e);
+      s[j][1] = exp2f((s[j][1] - m0) * scale_log2e);
+      s[j][2] = exp2f((s[j][2] - m1) * scale_log2e);
+      s[j][3] = exp2f((s[j][3] - m1) * scale_log2e);
+      rs0 += s[j][0] + s[j][1];
+      rs1 += s[j][2] + s[j][3];
+    }
+    l0 = l0 * a0 + rs0;
+    l1 = l1 * a1 + rs1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= a0;
+      o[j][1] *= a0;
+      o[j][2] *= a1;
+      o[j][3] *= a1;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+      uint32_t pa[4];
+      pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      const uint32_t vrow = vs_u32 + uint32_t((key0 + 16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * kKVStride +
+                                              8 * (lane >> 4)) * 2u;
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {  // 16 output dims per step
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, vrow + uint32_t(16 * jp) * 2u);
+        mma_bf16_16816(o[2 * jp], pa, vb[0], vb[1]);
+        mma_bf16_16816(o[2 * jp + 1], pa, vb[2], vb[3]);
+      }
+    }
+  }
+
+  // merge the two key parities: warps 2, 3 park (o, m, l) in shared memory (K is no longer needed)
+  __syncthreads();
+  float* xch = reinterpret_cast<float*>(smem_attn) + mt * (36 * 32);
+  if (par == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xch[(4 * j + e) * 32 + lane] = o[j][e];
+    xch[32 * 32 + lane] = m0;
+    xch[33 * 32 + lane] = m1;
+    xch[34 * 32 + lane] = l0;
+    xch[35 * 32 + lane] = l1;
   }
   __syncthreads();
-  float* my_p = probs + warp * nk;
-  float* my_q = qs + warp * kHeadDim;
-  for (int qi = warp; qi < group_tokens; qi += 4) {
-    const int t = g * group_tokens + qi;
-    const uint32_t qw = *reinterpret_cast<const uint32_t*>(base + size_t(t) * row_stride + h * kHeadDim + 2 * lane);
-    my_q[2 * lane] = bf16lo_to_f32(qw) * scale;
-    my_q[2 * lane + 1] = bf16hi_to_f32(qw) * scale;
-    __syncwarp();
-    // scores: lane owns keys lane, lane+32, ...
-    float mx = -INFINITY;
-    for (int k0 = lane; k0 < nk; k0 += 32) {
-      const __nv_bfloat16* kr = ks + size_t(k0) * kKeyStride;
-      float s = 0.f;
+  if (par == 0) {
+    const float pm0 = xch[32 * 32 + lane], pm1 = xch[33 * 32 + lane];
+    const float t0 = fmaxf(m0, pm0), t1 = fmaxf(m1, pm1);
+    const float f0 = exp2f((m0 - t0) * scale_log2e), g0 = exp2f((pm0 - t0) * scale_log2e);
+    const float f1 = exp2f((m1 - t1) * scale_log2e), g1 = exp2f((pm1 - t1) * scale_log2e);
+    l0 = l0 * f0 + xch[34 * 32 + lane] * g0;
+    l1 = l1 * f1 + xch[35 * 32 + lane] * g1;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    __nv_bfloat16* o0 = out + (size_t(b) * T + g * group_tokens + r0) * d_model + h * kHeadDim + 2 * qlane;
+    __nv_bfloat16* o1 = out + (size_t(b) * T + g * group_tokens + r1) * d_model + h * kHeadDim + 2 * qlane;
 #pragma unroll
-      for (int w = 0; w < 32; ++w) {
-        const uint32_t kw = *reinterpret_cast<const uint32_t*>(kr + 2 * w);
-        s = fmaf(my_q[2 * w], bf16lo_to_f32(kw), s);
-        s = fmaf(my_q[2 * w + 1], bf16hi_to_f32(kw), s);
-      }
-      my_p[k0] = s;
-      mx = fmaxf(mx, s);
+    for (int j = 0; j < 8; ++j) {
+      const float x0 = (o[j][0] * f0 + xch[(4 * j + 0) * 32 + lane] * g0) * i0;
+      const float x1 = (o[j][1] * f0 + xch[(4 * j + 1) * 32 + lane] * g0) * i0;
+      const float y0 = (o[j][2] * f1 + xch[(4 * j + 2) * 32 + lane] * g1) * i1;
+      const float y1 = (o[j][3] * f1 + xch[(4 * j + 3) * 32 + lane] * g1) * i1;
+      if (valid0) *reinterpret_cast<uint32_t*>(o0 + 8 * j) = pack_bf16x2(x0, x1);
+      if (valid1) *reinterpret_cast<uint32_t*>(o1 + 8 * j) = pack_bf16x2(y0, y1);
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    float sum = 0.f;
-    for (int k0 = lane; k0 < nk; k0 += 32) {
-      const float p = __expf(my_p[k0] - mx);
-      my_p[k0] = p;
-      sum += p;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-    __syncwarp();
-    // output: lane owns dims 2*lane, 2*lane+1
-    float o0 = 0.f, o1 = 0.f;
-    for (int k0 = 0; k0 < nk; ++k0) {
-      const float p = my_p[k0];
-      const uint32_t vw = *reinterpret_cast<const uint32_t*>(vs + size_t(k0) * kKeyStride + 2 * lane);
-      o0 = fmaf(p, bf16lo_to_f32(vw), o0);
-      o1 = fmaf(p, bf16hi_to_f32(vw), o1);
-    }
-    const float inv = 1.f / sum;
-    const __nv_bfloat162 r = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-    *reinterpret_cast<__nv_bfloat162*>(out + (size_t(b) * T + t) * d_model + h * kHeadDim + 2 * lane) = r;
-    __syncwarp();
   }
 }
 
 // ---- K7: y = LayerNorm(resid + sum_s partial[s] + bias) * gamma + beta ---------------------------
-// one warp per row; d multiple of 256 (8 elements per lane per pass)
-__global__ void __launch_bounds__(256)
+// one CTA of d/8 threads per row, 8 elements per thread; every load of a thread (residual, bias,
+// `splits` partial sums, gamma, beta) is independent and issued up front, the two reductions go
+// through warp shuffles + one shared-memory hop.
+constexpr int kMaxSplits = 8;
+
+__device__ __forceinline__ float block_sum(float v, float* red, int warp, int lane, int nwarps) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < nwarps; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(128)
     k7_add_layernorm_kernel(const __nv_bfloat16* __restrict__ resid, const float* __restrict__ partial,
                             int splits, const __nv_bfloat16* __restrict__ bias,
                             const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                             __nv_bfloat16* __restrict__ out, int M, int d, float eps) {
+  __shared__ float red[4];
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int lane = threadIdx.x & 31;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= M) return;
-  constexpr int MAXV = 4;  // d <= 1024: 4 passes of 8 elements per lane
-  float x[MAXV][8];
-  const int passes = d / 256;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int row = blockIdx.x;
+  const int c = tid * 8;
+  const uint4 rv = *reinterpret_cast<const uint4*>(resid + size_t(row) * d + c);
+  const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + c));
+  const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c));
+  const uint4 ev = __ldg(reinterpret_cast<const uint4*>(beta + c));
+  float4 pa[kMaxSplits], pb[kMaxSplits];
+#pragma unroll
+  for (int s = 0; s < kMaxSplits; ++s) {
+    if (s < splits) {
+      const float4* pp = reinterpret_cast<const float4*>(partial + (size_t(s) * M + row) * d + c);
+      pa[s] = pp[0];
+      pb[s] = pp[1];
+    }
+  }
+  const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+  float x[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    x[2 * j] = bf16lo_to_f32(rw[j]) + bf16lo_to_f32(bw[j]);
+    x[2 * j + 1] = bf16hi_to_f32(rw[j]) + bf16hi_to_f32(bw[j]);
+  }
+#pragma unroll
+  for (int s = 0; s < kMaxSplits; ++s) {
+    if (s < splits) {
+      x[0] += pa[s].x; x[1] += pa[s].y; x[2] += pa[s].z; x[3] += pa[s].w;
+      x[4] += pb[s].x; x[5] += pb[s].y; x[6] += pb[s].z; x[7] += pb[s].w;
+    }
+  }
   float s1 = 0.f;
 #pragma unroll
-  for (int p = 0; p < MAXV; ++p) {
-    if (p >= passes) break;
-    const int c = p * 256 + lane * 8;
-    const uint4 rv = *reinterpret_cast<const uint4*>(resid + size_t(row) * d + c);
-    const uint4 bv = *reinterpret_cast<const uint4*>(bias + c);
-    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      x[p][2 * j] = bf16lo_to_f32(rw[j]) + bf16lo_to_f32(bw[j]);
-      x[p][2 * j + 1] = bf16hi_to_f32(rw[j]) + bf16hi_to_f32(bw[j]);
-    }
-    for (int s = 0; s < splits; ++s) {
-      const float4* pp = reinterpret_cast<const float4*>(partial + (size_t(s) * M + row) * d + c);
-      const float4 a = pp[0], b = pp[1];
-      x[p][0] += a.x; x[p][1] += a.y; x[p][2] += a.z; x[p][3] += a.w;
-      x[p][4] += b.x; x[p][5] += b.y; x[p][6] += b.z; x[p][7] += b.w;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s1 += x[p][j];
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-  const float mean = s1 / d;
+  for (int j = 0; j < 8; ++j) s1 += x[j];
+  const float mean = block_sum(s1, red, warp, lane, nwarps) / d;
   float s2 = 0.f;
 #pragma unroll
-  for (int p = 0; p < MAXV; ++p) {
-    if (p >= passes) break;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float t = x[p][j] - mean;
-      s2 = fmaf(t, t, s2);
-    }
+  for (int j = 0; j < 8; ++j) {
+    const float t = x[j] - mean;
+    s2 = fmaf(t, t, s2);
   }
+  const float rstd = rsqrtf(block_sum(s2, red, warp, lane, nwarps) / d + eps);
+  const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ew[4] = {ev.x, ev.y, ev.z, ev.w};
+  uint32_t o[4];
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-  const float rstd = rsqrtf(s2 / d + eps);
-#pragma unroll
-  for (int p = 0; p < MAXV; ++p) {
-    if (p >= passes) break;
-    const int c = p * 256 + lane * 8;
-    const uint4 gv = *reinterpret_cast<const uint4*>(gamma + c);
-    const uint4 ev = *reinterpret_cast<const uint4*>(beta + c);
-    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ew[4] = {ev.x, ev.y, ev.z, ev.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = (x[p][2 * j] - mean) * rstd * bf16lo_to_f32(gw[j]) + bf16lo_to_f32(ew[j]);
-      const float b = (x[p][2 * j + 1] - mean) * rstd * bf16hi_to_f32(gw[j]) + bf16hi_to_f32(ew[j]);
-      const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
-      o[j] = *reinterpret_cast<const uint32_t*>(&r);
-    }
-    *reinterpret_cast<uint4*>(out + size_t(row) * d + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  for (int j = 0; j < 4; ++j) {
+    const float a = (x[2 * j] - mean) * rstd * bf16lo_to_f32(gw[j]) + bf16lo_to_f32(ew[j]);
+    const float b = (x[2 * j + 1] - mean) * rstd * bf16hi_to_f32(gw[j]) + bf16hi_to_f32(ew[j]);
+    const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+    o[j] = *reinterpret_cast<const uint32_t*>(&r);
   }
+  *reinterpret_cast<uint4*>(out + size_t(row) * d + c) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -332,12 +477,27 @@ static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, size_t smem
   return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
+template <int BN, int STAGES>
+static cudaError_t launch_k5_bn(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmArgs& g, int splits,
+                                cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k5_linear_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(GemmCfg<BN, STAGES>::kSmem));
+  if (e != cudaSuccess) return e;
+  void* args[] = {const_cast<CUtensorMap*>(&tm_a), const_cast<CUtensorMap*>(&tm_w), const_cast<GemmArgs*>(&g)};
+  return launch_pdl(reinterpret_cast<const void*>(k5_linear_kernel<BN, STAGES>),
+                    dim3(unsigned(g.N / BN), unsigned((g.M + kGemmBM - 1) / kGemmBM), unsigned(splits)),
+                    dim3(kGemmThreads), GemmCfg<BN, STAGES>::kSmem, st, args);
+}
+
 cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w_bf16, int M, int N, int K,
                              const void* bias, bool gelu, void* out_bf16, float* partial, int splits,
                              cudaStream_t st) {
-  if (N % kGemmBN != 0 || K % kBK != 0 || M < 1 || splits < 1) return cudaErrorInvalidValue;
+  if (N % 128 != 0 || K % kBK != 0 || M < 1 || splits < 1) return cudaErrorInvalidValue;
+  const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  const int ctas128 = (N / 128) * m_tiles * splits;
+  const int bn = (ctas128 < 120) ? 64 : 128;  // fill the 148 SMs when tiles are few
   CUtensorMap tm_a, tm_w;
-  if (!make_tmap(&tm_a, a_bf16, a_rows_alloc, K, kGemmBM) || !make_tmap(&tm_w, w_bf16, N, K, kGemmBN))
+  if (!make_tmap(&tm_a, a_bf16, a_rows_alloc, K, kGemmBM) || !make_tmap(&tm_w, w_bf16, N, K, bn))
     return cudaErrorInvalidValue;
   GemmArgs g;
   g.M = M;
@@ -349,27 +509,26 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   g.gelu = gelu ? 1 : 0;
   g.out = static_cast<__nv_bfloat16*>(out_bf16);
   g.partial = partial;
-  cudaError_t e = cudaFuncSetAttribute(k5_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmem));
-  if (e != cudaSuccess) return e;
-  void* args[] = {&tm_a, &tm_w, &g};
-  e = launch_pdl(reinterpret_cast<const void*>(k5_linear_kernel),
-                 dim3(unsigned(N / kGemmBN), unsigned((M + kGemmBM - 1) / kGemmBM), unsigned(splits)),
-                 dim3(kGemmThreads), kGemmSmem, st, args);
+  cudaError_t e = bn == 64        ? launch_k5_bn<64, 6>(tm_a, tm_w, g, splits, st)
+                  : ctas128 > 148 ? launch_k5_bn<128, 3>(tm_a, tm_w, g, splits, st)
+                                  : launch_k5_bn<128, 6>(tm_a, tm_w, g, splits, st);
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_model, int heads,
                                 int groups, int group_tokens, cudaStream_t st) {
-  if (d_model != heads * kHeadDim || groups * group_tokens != T) return cudaErrorInvalidValue;
-  const size_t smem = size_t(2) * T * kKeyStride * 2 + size_t(4) * T * 4 + 4 * kHeadDim * 4;
+  if (d_model != heads * kHeadDim || groups * group_tokens != T || T > kAttnMaxT) return cudaErrorInvalidValue;
+  const int rows_pad = (T + kKeyChunk - 1) / kKeyChunk * kKeyChunk;
+  const size_t smem = size_t(rows_pad) * kKVStride * 2 * 2;
   cudaError_t e = cudaFuncSetAttribute(k6_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  float scale = 1.f / sqrtf(float(kHeadDim));
-  void* args[] = {&q, &o, &T, &d_model, &heads, &group_tokens, &scale};
-  e = launch_pdl(reinterpret_cast<const void*>(k6_attention_kernel), dim3(unsigned(b * heads), unsigned(groups)),
+  float scale_log2e = 1.4426950408889634f / sqrtf(float(kHeadDim));
+  void* args[] = {&q, &o, &T, &d_model, &heads, &group_tokens, &scale_log2e};
+  e = launch_pdl(reinterpret_cast<const void*>(k6_attention_kernel),
+                 dim3(unsigned(b * heads), unsigned(groups), unsigned((group_tokens + 31) / 32)),
                  dim3(kAttnThreads), smem, st, args);
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
@@ -378,15 +537,15 @@ cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_
 cudaError_t launch_k7_add_layernorm(const void* resid, const float* partial, int splits, const void* bias,
                                     const void* gamma, const void* beta, void* out, int M, int d, float eps,
                                     cudaStream_t st) {
-  if (d % 256 != 0 || d > 1024) return cudaErrorInvalidValue;
+  if (d % 256 != 0 || d > 1024 || splits > kMaxSplits) return cudaErrorInvalidValue;
   const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(resid);
   const __nv_bfloat16* bi = static_cast<const __nv_bfloat16*>(bias);
   const __nv_bfloat16* ga = static_cast<const __nv_bfloat16*>(gamma);
   const __nv_bfloat16* be = static_cast<const __nv_bfloat16*>(beta);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   void* args[] = {&r, &partial, &splits, &bi, &ga, &be, &o, &M, &d, &eps};
-  cudaError_t e = launch_pdl(reinterpret_cast<const void*>(k7_add_layernorm_kernel), dim3(unsigned((M * 32 + 255) / 256)),
-                             dim3(256), 0, st, args);
+  cudaError_t e = launch_pdl(reinterpret_cast<const void*>(k7_add_layernorm_kernel), dim3(unsigned(M)),
+                             dim3(unsigned(d / 8)), 0, st, args);
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -138,31 +138,78 @@ class MotionContext:
         return gather_context(self.table, ref_index, self.sos, self.uncond_row, self.pos_table,
                               condition_emb, out)
 
+    def build_from_features(self, ref_features: torch.Tensor, condition_emb: torch.Tensor | None = None,
+                            out: torch.Tensor | None = None) -> torch.Tensor:
+        """Same `x` from already-materialised reference features (`batch['ref_features']`,
+        [b, K, L, C] in similarity order, 0 = most similar) instead of table rows: the batch itself
+        is the table and slot (i, k) reads row i*K + k — still one K4 launch."""
+        if ref_features.ndim != 4 or tuple(ref_features.shape[2:]) != (self.table.L, self.table.Cdim):
+            raise ValueError(f"ref_features must be [b, K, {self.table.L}, {self.table.Cdim}]")
+        b, K = ref_features.shape[:2]
+        dt, dev = self.table.local.dtype, self.table.device
+        feats = ref_features.detach().to(dev, dt).reshape(b * K, self.table.L, self.table.Cdim).contiguous()
+        idx = torch.arange(b * K, dtype=torch.int64, device=dev).view(b, K)
+        return gather_context(FeatureTable(feats), idx, self.sos, self.uncond_row, self.pos_table, condition_emb, out)
+
     def uncond_action_emb(self, b: int) -> torch.Tensor:
         """predict()'s CFG branch (module.py:327-329): encode_vision(zeros)[:, 0] per sample."""
         return self.uncond_row[None].expand(b, -1, -1)
 
 
-def attach(model, ctx: MotionContext):
+def attach(model, ctx: MotionContext, transformer=None):
     """Teach a reference ActionTransformer to take `batch['ref_index']` ([b, K] int64 row ids
-    from retrieval) instead of `batch['ref_videos']` for inference (`return_loss=False`),
+    from retrieval) or `batch['ref_features']` ([b, K, L, C] features in similarity order) instead
+    of `batch['ref_videos']` for inference (`return_loss=False`),
     producing the same prediction tensor as module.py:292-315 with encode_vision of the K
     references replaced by the table gather. The condition embedding is still computed by the
     model's own encode_condition from `batch['ref_images']` ([b, K+1, C, H, W], refs flipped +
-    target first frame, as batch_forward builds them at :321)."""
+    target first frame, as batch_forward builds them at :321).
+
+    transformer: optionally a `CamaTransformer` built from `model.transformer`; the context is then
+    gathered straight into its input buffer and the 4-layer forward runs on libmrag kernels
+    (bf16 tables only). `predict` (module.py:325-331) is patched the same way: the CFG "uncond" rows
+    come from the stored uncond row instead of encoding an all-zero clip."""
     orig = model.batch_forward
+    orig_predict = getattr(model, 'predict', None)
+    if transformer is not None and ctx.table.local.dtype != torch.bfloat16:
+        raise ValueError("the libmrag transformer consumes a bf16 feature table")
 
     def batch_forward(batch, return_loss: bool = True, ignore_ref_loss: bool = False):
-        if 'ref_index' not in batch:
+        if 'ref_index' not in batch and 'ref_features' not in batch:
             return orig(batch, return_loss, ignore_ref_loss)
         if return_loss:
             raise NotImplementedError("the table-backed path serves inference (predict); "
                                       "training losses need the target clip's own features")
         cond = model.encode_condition(batch['ref_images']) if 'ref_images' in batch else batch.get('condition_emb')
-        x = ctx.build(batch['ref_index'], cond)
-        K = batch['ref_index'].shape[1]
-        pred = model.transformer(x, ctx.get_mask(K + 1, ctx.table.L))
+        by_index = 'ref_index' in batch
+        b, K = (batch['ref_index'] if by_index else batch['ref_features']).shape[:2]
+
+        def build(out=None):
+            if by_index:
+                return ctx.build(batch['ref_index'], cond, out=out)
+            return ctx.build_from_features(batch['ref_features'], cond, out=out)
+
+        if transformer is None:
+            x = build()
+            pred = model.transformer(x, ctx.get_mask(K + 1, ctx.table.L))
+        else:
+            if (K + 1, ctx.table.L) != (transformer.groups, transformer.group_tokens):
+                raise ValueError(f"transformer was built for {transformer.groups} groups of "
+                                 f"{transformer.group_tokens} tokens, got {K + 1} x {ctx.table.L}")
+            build(out=transformer.input_view(b))
+            pred = transformer.forward(b=b)
         return pred.reshape(pred.shape[0], K + 1, ctx.table.L, -1)
 
+    def predict(batch, do_classifier_free_guidance: bool = False):
+        if 'ref_index' not in batch and 'ref_features' not in batch:
+            if orig_predict is None:
+                raise AttributeError("the wrapped model has no predict() for the video path")
+            return orig_predict(batch, do_classifier_free_guidance)
+        action_emb = batch_forward(batch, return_loss=False)[:, -1]
+        if do_classifier_free_guidance:
+            action_emb = torch.cat([ctx.uncond_action_emb(action_emb.shape[0]).to(action_emb.dtype), action_emb], dim=0)
+        return action_emb
+
     model.batch_forward = batch_forward
+    model.predict = predict
     return model

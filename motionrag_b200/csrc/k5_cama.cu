@@ -17,6 +17,8 @@
 // tcgen05.ld epilogue), tile 128 x 128, one tile (and one K split) per CTA. The residual path
 // stays in fp32 until the LayerNorm (torch rounds the projection to bf16 first), so results are
 // at least as close to an fp32 evaluation as torch's own bf16 path.
+#include <cstdlib>
+
 #include "k2_common.cuh"
 
 namespace mrag {
@@ -495,7 +497,11 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   if (N % 128 != 0 || K % kBK != 0 || M < 1 || splits < 1) return cudaErrorInvalidValue;
   const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
   const int ctas128 = (N / 128) * m_tiles * splits;
-  const int bn = (ctas128 < 120) ? 64 : 128;  // fill the 148 SMs when tiles are few
+  int bn = (ctas128 < 120) ? 64 : 128;  // fill the 148 SMs when tiles are few
+  if (const char* v = getenv("MRAG_K5_BN")) {  // tuning knob (scripts/cama_gemm_bench.py)
+    const int o = atoi(v);
+    if (o == 64 || o == 128) bn = o;
+  }
   CUtensorMap tm_a, tm_w;
   if (!make_tmap(&tm_a, a_bf16, a_rows_alloc, K, kGemmBM) || !make_tmap(&tm_w, w_bf16, N, K, bn))
     return cudaErrorInvalidValue;

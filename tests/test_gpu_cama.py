@@ -96,3 +96,51 @@ def test_unsupported_shapes_are_loud(libmrag):
     layer = nn.TransformerEncoderLayer(256, 4, 512, 0.0, "relu", batch_first=True)
     with pytest.raises(ValueError, match="gelu"):
         CamaTransformer(nn.TransformerEncoder(layer, 1), groups=2, group_tokens=4)
+
+
+def test_attach_with_libmrag_transformer_and_cfg_predict(libmrag):
+    """Row f-1 end to end: retrieval row ids -> K4 gather into the transformer's own input buffer ->
+    K5/K6/K7 forward -> ActionTransformer.predict's slice and CFG concat (module.py:325-331)."""
+    from motionrag_b200 import CamaTransformer, FeatureTable, MotionContext, attach
+    L, C, K, b, n = 25, 1024, 9, 3, 64
+    g = torch.Generator().manual_seed(5)
+    table = torch.randn(n, L, C, generator=g).bfloat16()
+    sos = (torch.randn(1, L, C, generator=g) / 32).bfloat16()
+    un = torch.randn(L, C, generator=g).bfloat16()
+    cond = torch.randn(b, (K + 1) * L, C, generator=g).bfloat16()
+    idx = torch.randint(0, n, (b, K), generator=g)
+    idx[2, 0] = -1
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.transformer = _encoder(C, 16, 4096, 4, seed=11)
+
+        def encode_condition(self, images):
+            return images
+
+        def batch_forward(self, batch, return_loss=True, ignore_ref_loss=False):
+            raise AssertionError("video path")
+
+        def predict(self, batch, do_classifier_free_guidance=False):
+            raise AssertionError("video path")
+
+    model = Model().eval()
+    ctx = MotionContext(FeatureTable(table.cuda()), sos, un, pe_max_length=256)
+    cama = CamaTransformer(model.transformer, groups=K + 1, group_tokens=L, max_batch=4, device=0)
+    x = cc.context_restatement(cc.gather_restatement(table, idx, un), sos, cc.sinusoid_table(256, C), cond.clone())
+    with torch.no_grad():
+        want = model.transformer(x.float(), cc.block_causal_mask(K + 1, L))[:, -L:]     # fp32 oracle
+    attach(model, ctx, transformer=cama)
+    batch = {"ref_index": idx.cuda(), "ref_images": cond.cuda()}
+    got = model.predict(batch)
+    assert torch.equal(cama.input_view(b).cpu(), x)            # the gather wrote the transformer's input in place
+    assert got.shape == (b, L, C)
+    err = (got.float().cpu() - want).abs()
+    assert float(err.max()) < 6e-2 and float(err.mean()) < 6e-3, (float(err.max()), float(err.mean()))
+    both = model.predict(batch, do_classifier_free_guidance=True)
+    assert both.shape == (2 * b, L, C)
+    assert torch.equal(both[b:], got) and torch.equal(both[:b].cpu(), un[None].expand(b, -1, -1))
+    with pytest.raises(ValueError, match="groups"):
+        model.batch_forward({"ref_index": idx[:, :4].cuda(), "ref_images": cond[:, :5 * L].cuda()}, return_loss=False)
+    cama.close()

@@ -123,3 +123,8 @@ def test_attach_drives_a_cama_style_transformer_from_row_ids(libmrag):
     assert torch.equal(pred.reshape(b, -1, C), want)       # same x, same mask -> same bits
     with pytest.raises(NotImplementedError):
         model.batch_forward({"ref_index": idx.cuda()}, return_loss=True)
+    # batch['ref_features'] (SURVEY §8b face 2): the same x from materialised features
+    feats = cc.gather_restatement(table, idx, un)                      # [b, K, L, C], -1 -> uncond row
+    with torch.no_grad():
+        pred2 = model.batch_forward({"ref_features": feats.cuda(), "ref_images": cond.cuda()}, return_loss=False)
+    assert torch.equal(pred2, pred)

@@ -10,6 +10,7 @@ from ._cabi import MragError, launch_count  # noqa: F401
 from .cama import CamaTransformer  # noqa: F401
 from .context import (MotionContext, attach, block_causal_mask, gather_context, select_refs,  # noqa: F401
                       sinusoid_table)
+from .features import FeatureTableWriter, build_feature_table, load_feature_rows  # noqa: F401
 from .parallel import (PeerExchange, ShardedRetriever, alloc_feature_block, open_peer_tables,  # noqa: F401
                        shard_range)
 from .rag import RAGDatabase, save_table  # noqa: F401

@@ -114,3 +114,45 @@ def test_select_refs_follows_get_ref_videos_semantics():
     i, d = select_refs(big, torch.zeros(1000, 4), 4, uncond_video_ratio=0.25, generator=g)
     frac = float((i == -1).float().mean())
     assert 0.2 < frac < 0.3 and bool((d[i == -1] == 1.0).all()) and bool((i[i >= 0] == big[i >= 0]).all())
+
+
+def test_feature_table_builder_round_trip(tmp_path):
+    """Row f-5: encode_vision driven over (row ids, clips) batches -> row-aligned bf16 table; rows never
+    written (failed decodes) and the CFG branch share the encode_vision(zeros) row (module.py:327-329)."""
+    from motionrag_b200 import build_feature_table, load_feature_rows
+    L, C, n = 5, 64, 37
+
+    class Model:
+        calls = 0
+
+        def encode_vision(self, videos):                      # [b, k, T, C, H, W] -> [b, k, L, C]
+            Model.calls += 1
+            b, k = videos.shape[:2]
+            m = videos.float().mean(dim=(2, 3, 4, 5))           # a deterministic function of the clip
+            return (m[..., None, None] + torch.arange(L)[:, None] * 0.5 + torch.arange(C)[None] * 0.01 + 7.0).expand(b, k, L, C)
+
+    g = torch.Generator().manual_seed(0)
+    clips = torch.randn(n, 4, 3, 8, 8, generator=g)
+    order = torch.randperm(n, generator=g)
+    skipped = {3, 20}                                           # unreadable clips
+
+    def batches():
+        ids = [int(i) for i in order if int(i) not in skipped]
+        for lo in range(0, len(ids), 6):
+            sel = torch.tensor(ids[lo:lo + 6])
+            yield sel, clips[sel]
+
+    meta = build_feature_table(Model(), batches(), n, tmp_path / "feat", tokens=L, width=C, device="cpu")
+    assert meta["missing_rows"] == 2 and meta["n_rows"] == n
+    feats, uncond, meta2 = load_feature_rows(tmp_path / "feat")
+    assert feats.dtype == torch.bfloat16 and tuple(feats.shape) == (n, L, C) and meta2 == meta
+    want = Model().encode_vision(clips[:, None])[:, 0].bfloat16()
+    want_un = Model().encode_vision(torch.zeros(1, 1, 4, 3, 8, 8))[0, 0].bfloat16()
+    assert torch.equal(uncond, want_un)
+    for r in range(n):
+        assert torch.equal(feats[r], want_un if r in skipped else want[r]), r
+    part, _, _ = load_feature_rows(tmp_path / "feat", rows=(10, 25))       # a shard
+    assert torch.equal(part, feats[10:25])
+    with pytest.raises(IndexError):
+        from motionrag_b200 import FeatureTableWriter
+        FeatureTableWriter(tmp_path / "bad", 4, L, C).write([9], torch.zeros(1, L, C))

@@ -37,6 +37,7 @@ WORKLOADS = {
     "c3q4096": (10_000_000, 4096, "clustered", "10M-entry DB row-sharded, 4096-query batch"),
     "c4": (1_000_000, 16, "clustered", "1M-entry DB, 16-query batch + gather into CAMA context [16,250,1024] bf16"),
     "c1q4": (1_000_000, 4, "clustered", "1M-entry DB, 4 queries per step (one padded tensor tile at the HBM rate)"),
+    "c1s": (125_000, 1, "clustered", "125k-entry DB, single query (the per-GPU shard of c1 at 8 GPUs; tuning aid)"),
     "c1f": (1_000_000, 1, "clustered", "1M-entry DB, single query, fp32 master rows streamed (4 B/elt, ranking exact in fp32)"),
 }
 PATHS = {"c1f": "stream_f32"}

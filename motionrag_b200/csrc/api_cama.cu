@@ -94,6 +94,9 @@ int mrag_cama_create(int32_t n_layers, const mrag_cama_layer* layers, int32_t d_
     return api_fail(MRAG_ERR_UNSUPPORTED,
                     "kernels are built for head_dim 64, d_model in {256,512,768,1024} and d_ff %% 512 == 0 "
                     "(got d_model %d, heads %d, d_ff %d)", d_model, n_heads, d_ff);
+  if (int64_t(groups) * group_tokens > 704)
+    return api_fail(MRAG_ERR_UNSUPPORTED, "sequence of %lld tokens: the attention kernel stages K and V of the whole "
+                    "sequence in shared memory (at most 704 tokens)", (long long)(int64_t(groups) * group_tokens));
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     cudaGetLastError();

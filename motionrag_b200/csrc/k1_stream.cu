@@ -233,7 +233,8 @@ static cudaError_t launch_one(const void* db, int64_t n_rows, const float* queri
     }
   }
   if constexpr (D == 768 && Q == 1) return launch_cfg<T, D, Q, F ? 2 : 6, 2>(db, n_rows, queries, cand, kc, grid, st);
-  return launch_cfg<T, D, Q, F ? 2 : 4, F ? 2 : 3>(db, n_rows, queries, cand, kc, grid, st);
+  // bf16 with 3-4 queries or 1024-d rows: 4 rows in flight per warp do not fit 80 registers without spilling
+  return launch_cfg<T, D, Q, F ? 2 : 4, (F || Q >= 3 || D >= 1024) ? 2 : 3>(db, n_rows, queries, cand, kc, grid, st);
 }
 
 template <typename T, int D>
@@ -265,9 +266,9 @@ bool k1_supported(int dim, int nq) {
 }
 
 int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count) {
-  // the headline shape (768-d, one query) has tuned variants; other shapes use (2,2) / (4,3)
+  // the headline shape (768-d, one query) has tuned variants; other shapes use (2,2) / (4,3 or 2)
   K1Variant v = (dim == 768 && nq == 1) ? k1_variant(elt_bytes)
-                                        : (elt_bytes == 4 ? K1Variant{2, 2} : K1Variant{4, 3});
+                                        : (elt_bytes == 4 ? K1Variant{2, 2} : K1Variant{4, (nq >= 3 || dim >= 1024) ? 2 : 3});
   const int64_t quantum = int64_t(kK1Warps) * v.r;
   // one resident wave; small tables get fewer CTAs
   int64_t want = (n_rows + quantum - 1) / quantum;

@@ -59,7 +59,7 @@ class EmbeddingStore:
         h = C.c_void_p()
         check(self._lib.mrag_store_create(self.dim, int(capacity_rows), self.device.index, C.byref(h)))
         self._h = h
-        self._ws: torch.Tensor | None = None
+        self._ws: dict[int, torch.Tensor] = {}   # scratch per CUDA stream: searches on different streams may overlap
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -196,8 +196,10 @@ class EmbeddingStore:
         if certify:
             out_margin = torch.empty(nq, dtype=torch.float32, device=self.device)
             p.out_margin = out_margin.data_ptr()
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        stream = _stream_ptr(self.device)
+        ws = self._ws.get(stream.value or 0)
+        if ws is None or ws.numel() < need:
+            ws = self._ws[stream.value or 0] = torch.empty(need, dtype=torch.uint8, device=self.device)
         if out is None:
             out = SearchResult(torch.empty((nq, k), dtype=torch.float32, device=self.device),
                                torch.empty((nq, k), dtype=torch.int64, device=self.device),
@@ -205,8 +207,7 @@ class EmbeddingStore:
         args = (self._h, C.c_void_p(queries.data_ptr()), nq, C.byref(p),
                 C.c_void_p(exclude_group.data_ptr()) if exclude_group is not None else None,
                 C.c_void_p(out.distance.data_ptr()), C.c_void_p(out.index.data_ptr()),
-                C.c_void_p(out.group.data_ptr()), C.c_void_p(self._ws.data_ptr()), self._ws.numel(),
-                _stream_ptr(self.device))
+                C.c_void_p(out.group.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), stream)
         if exchange is not None:   # row-sharded: cross-GPU merge fused into the last kernel
             check(self._lib.mrag_search_sharded(*args[:-1], C.byref(exchange), args[-1]))
         elif timings is None:

@@ -93,6 +93,8 @@ def test_unsupported_shapes_are_loud(libmrag):
     enc = _encoder(192, 2, 512, 1, seed=0)                            # head_dim 96
     with pytest.raises(MragError, match="head_dim 64"):
         CamaTransformer(enc, groups=2, group_tokens=4, max_batch=1)
+    with pytest.raises(MragError, match="704 tokens"):
+        CamaTransformer(_encoder(256, 4, 512, 1, seed=0), groups=40, group_tokens=25, max_batch=1)
     layer = nn.TransformerEncoderLayer(256, 4, 512, 0.0, "relu", batch_first=True)
     with pytest.raises(ValueError, match="gelu"):
         CamaTransformer(nn.TransformerEncoder(layer, 1), groups=2, group_tokens=4)

@@ -446,3 +446,25 @@ def test_10m_table_properties_single_gpu(libmrag):
             assert torch.allclose(one.distance, big.distance[:3], rtol=1e-3, atol=1e-6)
         assert torch.equal(one.index[:, 0], src[:3])
     st.close()
+
+
+def test_searches_on_different_streams_do_not_share_scratch(case):
+    """SURVEY §8b ownership: the store is immutable after upload, so searches issued on different
+    streams may overlap; each stream gets its own candidate/threshold scratch."""
+    store = case["store"]
+    qa = torch.from_numpy(case["q"][:64]).cuda()
+    qb = torch.from_numpy(case["q"][64:128]).cuda()
+    want_a, want_b = store.search(qa, 12, path="tensor_bf16"), store.search(qb, 12, path="stream_bf16")
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    got = []
+    for _ in range(10):                      # interleave so the kernels of both streams overlap
+        with torch.cuda.stream(s1):
+            ra = store.search(qa, 12, path="tensor_bf16")
+        with torch.cuda.stream(s2):
+            rb = store.search(qb, 12, path="stream_bf16")
+        got.append((ra, rb))
+    torch.cuda.synchronize()
+    for ra, rb in got:
+        assert torch.equal(ra.index, want_a.index) and torch.equal(ra.distance, want_a.distance)
+        assert torch.equal(rb.index, want_b.index) and torch.equal(rb.distance, want_b.distance)

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/mrag.h"
@@ -42,6 +43,24 @@ int pick_splits(int M, int N, int max_splits) {
   return s;
 }
 
+// bf16-output GEMMs (QKV, FFN1) with less than a wave of 128 x 128 tiles: split K inside a cluster
+// (k5_linear_kernel<.., REDUCE>) as far as the 2 x 148 co-resident CTAs allow
+int pick_cluster_splits(int M, int N, int K) {
+  static const int max_s = [] {
+    const char* e = getenv("MRAG_K5_REDUCE_MAX");  // tuning knob: 1 disables
+    const int v = e ? atoi(e) : 4;
+    return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
+  }();
+  const int tiles = ((M + 127) / 128) * (N / 128);
+  // measured (scripts/cama_bench.py, MRAG_K5_REDUCE_MAX sweep): with the <= 64 tiles of one sample the
+  // 128 x 64-tile form without clusters is as fast (186 vs 190 us per forward); from two samples on the
+  // cluster form avoids a second wave of 128 x 64 tiles (b = 2: 258 -> 237 us)
+  if (tiles >= 120 || tiles <= 64) return 1;
+  int s = 1;
+  while (s < max_s && tiles * s * 2 <= 296 && (K / 64) % (s * 2) == 0) s *= 2;
+  return s;
+}
+
 struct Guard {
   int prev = -1;
   explicit Guard(int dev) {
@@ -59,17 +78,18 @@ cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
   const void* xin = c->x_in;
   cudaError_t e = cudaSuccess;
   const int so = pick_splits(M, d, kSplitsO), sf = pick_splits(M, d, kSplitsF);
+  const int sq = pick_cluster_splits(M, 3 * d, d), s1 = pick_cluster_splits(M, dff, d);
   for (int l = 0; l < c->n_layers && e == cudaSuccess; ++l) {
     const mrag_cama_layer& w = c->layers[l];
     void* x1 = c->x_a;
     void* x2 = (l == c->n_layers - 1) ? c->y_out : c->x_b;
-    e = launch_k5_linear(xin, c->rows_alloc, w.w_qkv, M, 3 * d, d, w.b_qkv, false, c->qkv, nullptr, 1, st);
+    e = launch_k5_linear(xin, c->rows_alloc, w.w_qkv, M, 3 * d, d, w.b_qkv, false, c->qkv, nullptr, sq, st);
     if (e == cudaSuccess) e = launch_k6_attention(c->qkv, c->att, b, c->T, d, c->heads, c->groups, c->gtok, st);
     if (e == cudaSuccess)
       e = launch_k5_linear(c->att, c->rows_alloc, w.w_o, M, d, d, nullptr, false, nullptr, c->partial, so, st);
     if (e == cudaSuccess)
       e = launch_k7_add_layernorm(xin, c->partial, so, w.b_o, w.ln1_g, w.ln1_b, x1, M, d, 1e-5f, st);
-    if (e == cudaSuccess) e = launch_k5_linear(x1, c->rows_alloc, w.w_1, M, dff, d, w.b_1, true, c->h, nullptr, 1, st);
+    if (e == cudaSuccess) e = launch_k5_linear(x1, c->rows_alloc, w.w_1, M, dff, d, w.b_1, true, c->h, nullptr, s1, st);
     if (e == cudaSuccess)
       e = launch_k5_linear(c->h, c->rows_alloc, w.w_2, M, d, dff, nullptr, false, nullptr, c->partial, sf, st);
     if (e == cudaSuccess)

@@ -46,13 +46,33 @@ struct GemmArgs {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int STAGES>
+// REDUCE: the grid.z K splits of a tile form one thread-block cluster and their fp32 partial tiles are
+// summed on chip: every CTA parks its TMEM accumulator in its own shared memory, then CTA r of the
+// cluster sums rows [r*128/S, (r+1)*128/S) over the S tiles through distributed shared memory (fixed
+// order, so results are deterministic) and writes the final bf16 (+bias, +GELU) — no fp32 round trip
+// through HBM. Used when M is small: each CTA then walks only K/S of the reduction dimension, which
+// shortens the TMA -> MMA latency chain that bounds a GEMM of less than one wave of tiles.
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta_rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(remote)
+               : "memory");
+  return v;
+}
+
+template <int BN, int STAGES, bool REDUCE>
 __global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
     k5_linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                      const GemmArgs g) {
   constexpr uint32_t kGemmStageBytes = GemmCfg<BN, STAGES>::kStageBytes;
   constexpr int kGemmBN = BN;
   constexpr int kGemmStages = STAGES;
+  constexpr int kStgStride = BN + 4;  // floats per parked accumulator row (bank-conflict-free float4 rows)
+  static_assert(!REDUCE || kGemmBM * kStgStride * 4 <= STAGES * GemmCfg<BN, STAGES>::kStageBytes,
+                "parked accumulator tile must fit in the pipeline stages");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
@@ -139,7 +159,15 @@ __global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
       tmem_ld_32x32(t_addr + c * 32, v);
       tmem_ld_wait();
       const int n0 = n_tile * kGemmBN + c * 32;
-      if (m < g.M) {
+      if constexpr (REDUCE) {
+        // the pipeline stages are idle once tfull has fired (every MMA has read its operands)
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(smem) +
+                                                size_t(quarter * 32 + lane) * kStgStride + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      } else if (m < g.M) {
         if (g.out != nullptr) {
           uint32_t packed[16];
 #pragma unroll
@@ -169,6 +197,50 @@ __global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
         }
       }
     }
+  }
+  if constexpr (REDUCE) {
+    __syncwarp();        // the producer / MMA lanes rejoin their warps before the aligned cluster barrier
+    cluster_sync_all();  // every CTA of the cluster has parked its partial tile
+    const uint32_t S = gridDim.z, rank = cluster_ctarank();
+    const int rows_per = kGemmBM / int(S);
+    const uint32_t stg_u32 = smem_u32(smem);
+    for (int u = threadIdx.x; u < rows_per * (BN / 4); u += kGemmThreads) {
+      const int r = int(rank) * rows_per + u / (BN / 4), c4 = u % (BN / 4);
+      const uint32_t addr = stg_u32 + uint32_t(r * kStgStride + 4 * c4) * 4u;
+      float4 acc = ld_dsmem_v4(addr, 0);
+      for (uint32_t sidx = 1; sidx < S; ++sidx) {
+        const float4 t = ld_dsmem_v4(addr, sidx);
+        acc.x += t.x;
+        acc.y += t.y;
+        acc.z += t.z;
+        acc.w += t.w;
+      }
+      const int m = m_tile * kGemmBM + r;
+      if (m < g.M) {
+        const int n0 = n_tile * BN + 4 * c4;
+        if (g.out != nullptr) {
+          if (g.bias != nullptr) {
+            const uint2 bw = *reinterpret_cast<const uint2*>(g.bias + n0);
+            acc.x += bf16lo_to_f32(bw.x);
+            acc.y += bf16hi_to_f32(bw.x);
+            acc.z += bf16lo_to_f32(bw.y);
+            acc.w += bf16hi_to_f32(bw.y);
+          }
+          if (g.gelu) {
+            acc.x = gelu_erf(acc.x);
+            acc.y = gelu_erf(acc.y);
+            acc.z = gelu_erf(acc.z);
+            acc.w = gelu_erf(acc.w);
+          }
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x, acc.y), hi = __floats2bfloat162_rn(acc.z, acc.w);
+          *reinterpret_cast<uint2*>(g.out + size_t(m) * g.N + n0) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        } else {
+          *reinterpret_cast<float4*>(g.partial + size_t(m) * g.N + n0) = acc;  // one reduced partial
+        }
+      }
+    }
+    cluster_sync_all();  // nobody leaves while a peer may still read its tile
   }
   tc_fence_before();
   __syncthreads();
@@ -465,30 +537,38 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args,
+                              unsigned cluster_z = 1) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_z > 1) {  // the K splits of one tile (grid.z) share a cluster
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 1;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = cluster_z;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool REDUCE = false>
 static cudaError_t launch_k5_bn(const CUtensorMap& tm_a, const CUtensorMap& tm_w, const GemmArgs& g, int splits,
                                 cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(k5_linear_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(GemmCfg<BN, STAGES>::kSmem));
+  cudaError_t e = cudaFuncSetAttribute(k5_linear_kernel<BN, STAGES, REDUCE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, int(GemmCfg<BN, STAGES>::kSmem));
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<CUtensorMap*>(&tm_a), const_cast<CUtensorMap*>(&tm_w), const_cast<GemmArgs*>(&g)};
-  return launch_pdl(reinterpret_cast<const void*>(k5_linear_kernel<BN, STAGES>),
+  return launch_pdl(reinterpret_cast<const void*>(k5_linear_kernel<BN, STAGES, REDUCE>),
                     dim3(unsigned(g.N / BN), unsigned((g.M + kGemmBM - 1) / kGemmBM), unsigned(splits)),
-                    dim3(kGemmThreads), GemmCfg<BN, STAGES>::kSmem, st, args);
+                    dim3(kGemmThreads), GemmCfg<BN, STAGES>::kSmem, st, args, REDUCE ? unsigned(splits) : 1u);
 }
 
 cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w_bf16, int M, int N, int K,
@@ -497,10 +577,11 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   if (N % 128 != 0 || K % kBK != 0 || M < 1 || splits < 1) return cudaErrorInvalidValue;
   const int m_tiles = (M + kGemmBM - 1) / kGemmBM;
   const int ctas128 = (N / 128) * m_tiles * splits;
-  int bn = (ctas128 < 120) ? 64 : 128;  // fill the 148 SMs when tiles are few
+  const bool reduce = out_bf16 != nullptr && splits > 1;
+  int bn = (ctas128 < 120 && !reduce) ? 64 : 128;  // fill the 148 SMs when tiles are few
   if (const char* v = getenv("MRAG_K5_BN")) {  // tuning knob (scripts/cama_gemm_bench.py)
     const int o = atoi(v);
-    if (o == 64 || o == 128) bn = o;
+    if ((o == 64 || o == 128) && !reduce) bn = o;
   }
   CUtensorMap tm_a, tm_w;
   if (!make_tmap(&tm_a, a_bf16, a_rows_alloc, K, kGemmBM) || !make_tmap(&tm_w, w_bf16, N, K, bn))
@@ -515,9 +596,16 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   g.gelu = gelu ? 1 : 0;
   g.out = static_cast<__nv_bfloat16*>(out_bf16);
   g.partial = partial;
-  cudaError_t e = bn == 64        ? launch_k5_bn<64, 6>(tm_a, tm_w, g, splits, st)
-                  : ctas128 > 148 ? launch_k5_bn<128, 3>(tm_a, tm_w, g, splits, st)
-                                  : launch_k5_bn<128, 6>(tm_a, tm_w, g, splits, st);
+  cudaError_t e;
+  if (reduce) {  // bf16 output of a split-K GEMM: sum the splits inside a cluster (128-wide tiles, two CTAs per SM)
+    if (splits > 8 || (splits & (splits - 1)) != 0) return cudaErrorInvalidValue;
+    e = launch_k5_bn<128, 3, true>(tm_a, tm_w, g, splits, st);
+  } else {
+    // ring depth measured at b = 1 (whole forward): 3 stages 227 us, 4: 192 us, 6: 186 us, 8: 188 us
+    e = bn == 64        ? launch_k5_bn<64, 6>(tm_a, tm_w, g, splits, st)
+        : ctas128 > 148 ? launch_k5_bn<128, 3>(tm_a, tm_w, g, splits, st)
+                        : launch_k5_bn<128, 6>(tm_a, tm_w, g, splits, st);
+  }
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }

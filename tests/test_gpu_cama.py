@@ -32,6 +32,30 @@ def test_linear_matches_fp32_matmul(libmrag, M, N, K, bias, gelu, splits):
         assert torch.equal(got.cpu(), want.bfloat16()) or (got.float().cpu() - want).abs().max() < 2e-2
 
 
+@pytest.mark.parametrize("M,N,K,bias,gelu,splits", [(250, 3072, 1024, True, False, 4), (250, 4096, 1024, True, True, 4),
+                                                    (500, 3072, 1024, True, False, 2), (77, 256, 512, False, True, 8),
+                                                    (250, 1024, 4096, True, False, 8)])
+def test_linear_with_cluster_reduced_split_k(libmrag, M, N, K, bias, gelu, splits):
+    """bf16 output of a split-K GEMM: the splits are summed through distributed shared memory in a fixed
+    order, so the result equals the unsplit kernel's up to fp32 summation order — and is deterministic."""
+    from motionrag_b200.cama import linear
+    g = torch.Generator().manual_seed(M + N + K + splits)
+    a = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    b = torch.randn(N, generator=g).bfloat16().cuda() if bias else None
+    want = a.float() @ w.float().T
+    if bias:
+        want = want + b.float()
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    got = linear(a, w, b, gelu, splits, cluster_reduce=True)
+    again = linear(a, w, b, gelu, splits, cluster_reduce=True)
+    assert torch.equal(got, again)
+    assert (got.float() - want).abs().max() < 2e-2
+    unsplit = linear(a, w, b, gelu, 1)
+    assert (got.float() - unsplit.float()).abs().max() <= 2 ** -6 * max(1.0, float(want.abs().max()))   # <= 1 bf16 ulp
+
+
 def _encoder(d, heads, dff, layers, seed):
     torch.manual_seed(seed)
     layer = nn.TransformerEncoderLayer(d, heads, dff, 0.0, "gelu", batch_first=True, norm_first=False, bias=True)
@@ -45,7 +69,7 @@ def _encoder(d, heads, dff, layers, seed):
 
 
 @pytest.mark.parametrize("b,G,L,d,heads,dff,layers", [(1, 10, 25, 1024, 16, 4096, 4), (3, 10, 25, 1024, 16, 4096, 4),
-                                                      (2, 4, 5, 256, 4, 512, 2)])
+                                                      (2, 4, 5, 256, 4, 512, 2), (2, 3, 40, 512, 8, 1024, 2)])
 def test_forward_matches_reference_encoder(libmrag, b, G, L, d, heads, dff, layers):
     """Reference configuration (configs/cogvideox/MotionRAG_open.yml:253-267) and a small one."""
     from motionrag_b200 import CamaTransformer

@@ -422,15 +422,30 @@ class RAGDatabase:
             out.extend(self._records(dist, idx, select))
         return out
 
-    def retrieve_for_annotations(self, annotations: list[dict], ref_video_num: int,
-                                 batch: int = 4096) -> list[dict]:
-        """The `rag_text` branch of VideoDataModule.prepare_annotations
-        (src/data/datamodule.py:231-236, 264-265) as one batched call: k = ref_video_num + 3,
-        `where video != "<own video>"`, select video/start_sec/end_sec; attaches `ref_videos`."""
-        vec = np.stack([np.asarray(a['text_embedding'], dtype=np.float32) for a in annotations])
-        wheres = [f'video != "{a["video"]}"' for a in annotations]
-        results = self.search_batch(vec, top_k=ref_video_num + 3, where=wheres,
-                                    select=['video', 'start_sec', 'end_sec'], batch=batch)
+    def retrieve_for_annotations(self, annotations: list[dict], ref_video_num: int, batch: int = 4096,
+                                 ref_video_type: str = "rag_text", save_path=None) -> list[dict]:
+        """The retrieval branches of VideoDataModule.prepare_annotations
+        (src/data/datamodule.py:231-245, 257-268) without the spawn pool.
+
+        `rag_text`: one batched scan per `batch` annotations — k = ref_video_num + 3,
+        `where video != "<own video>"`, select video/start_sec/end_sec. `rag_text_image`: the
+        two-stage search with top_k = (2*ref_video_num + 3, ref_video_num) per annotation (not
+        batched: no shipped config uses it). The records are attached as `anno['ref_videos']` and,
+        like the reference (:268), the list is written with torch.save when `save_path` is given."""
+        if ref_video_type == "rag_text":
+            vec = np.stack([np.asarray(a['text_embedding'], dtype=np.float32) for a in annotations])
+            wheres = [f'video != "{a["video"]}"' for a in annotations]
+            results = self.search_batch(vec, top_k=ref_video_num + 3, where=wheres,
+                                        select=['video', 'start_sec', 'end_sec'], batch=batch)
+        elif ref_video_type == "rag_text_image":
+            results = [self.text_image_search(a['text_embedding'], a['image_embedding'],
+                                              top_k=(ref_video_num * 2 + 3, ref_video_num),
+                                              where=f'video != "{a["video"]}"',
+                                              select=['video', 'start_sec', 'end_sec']) for a in annotations]
+        else:
+            raise ValueError("Invalid ref_video_type.")   # 'gt' / 'random' never touch the database
         for anno, r in zip(annotations, results):
             anno['ref_videos'] = r
+        if save_path is not None:
+            torch.save(annotations, save_path)
         return annotations

@@ -79,6 +79,25 @@ def test_batched_fast_path_equals_per_query_calls(libmrag, table):
         _same(o["ref_videos"], single)
 
 
+def test_annotation_cache_file_and_text_image_branch(libmrag, table, tmp_path):
+    """prepare_annotations writes the annotated list with torch.save (datamodule.py:268); the
+    `rag_text_image` branch uses top_k = (2K+3, K) per annotation (:239-245)."""
+    from motionrag_b200 import RAGDatabase
+    db = RAGDatabase(None, None, 'cuda', columns=table)
+    annos = [{"video": table["video"][j], "text_embedding": table["text_embedding"][j] * 4,
+              "image_embedding": table["image_embedding"][j] * 2} for j in (5, 50, 500)]
+    out = db.retrieve_for_annotations([dict(a) for a in annos], 9, save_path=tmp_path / "annos.pt")
+    cached = torch.load(tmp_path / "annos.pt", weights_only=False)
+    assert [a["ref_videos"] for a in cached] == [a["ref_videos"] for a in out]
+    out2 = db.retrieve_for_annotations([dict(a) for a in annos], 4, ref_video_type="rag_text_image")
+    for a, o in zip(annos, out2):
+        want = db.text_image_search(a["text_embedding"], a["image_embedding"], top_k=(11, 4),
+                                    where=f'video != "{a["video"]}"', select=['video', 'start_sec', 'end_sec'])
+        assert o["ref_videos"] == want and len(want) == 4 and all(r["video"] != a["video"] for r in want)
+    with pytest.raises(ValueError, match="Invalid ref_video_type"):
+        db.retrieve_for_annotations(annos, 9, ref_video_type="gt")
+
+
 def test_text_image_two_stage(libmrag, table):
     """src/data/rag.py:101-130 / datamodule.py:239-245: text top-(2K+3), then image top-K."""
     from motionrag_b200 import RAGDatabase

@@ -70,3 +70,37 @@ def check_retrieval(got_dist: np.ndarray, got_idx: np.ndarray, ref_dist: np.ndar
         near += 1
     return {"queries": int(got_idx.shape[0]), "positions": int(valid.sum()), "index_mismatches": int(diff.sum()),
             "near_tie_positions": int(near), "max_rel_score_err": max_rel}
+
+
+def replay_reference_class(factory, golden_json, rel: float = 1e-5) -> int:
+    """Replays tests/golden/rag_reference_class.json — recorded from the reference's REAL RAGDatabase
+    class (src/data/rag.py) run over the LanceDB stand-in, see oracle/make_golden.py — against the class
+    `factory(table_columns)` returns: same rows in the same order, same keys, same container type per
+    output_format, `_distance` within `rel`, same ValueError. Returns the number of calls replayed."""
+    import json
+    import math
+    from . import make_golden as mg
+    gold = json.loads(open(golden_json).read())
+    table = mg.rag_class_table(**gold["table"])
+    for entry in gold["calls"]:
+        call, want = entry["call"], entry["result"]
+        kw = mg.rag_class_kwargs(table, call)
+        db = factory(table)
+        if "raises" in want:
+            try:
+                getattr(db, call["method"])(**kw)
+            except ValueError as e:
+                assert want["message"] in str(e), (call, str(e))
+            else:
+                raise AssertionError(f"{call}: expected ValueError({want['message']!r})")
+            continue
+        got = mg.rag_class_summary(getattr(db, call["method"])(**kw))
+        assert got["kind"] == want["kind"] and got["keys"] == want["keys"], (call, got["kind"], got["keys"])
+        assert len(got["records"]) == len(want["records"]), (call, len(got["records"]), len(want["records"]))
+        for g, w in zip(got["records"], want["records"]):
+            for key, val in w.items():
+                if key == "_distance":
+                    assert math.isclose(g[key], val, rel_tol=rel, abs_tol=1e-6), (call, g[key], val)
+                else:
+                    assert g[key] == val, (call, key, g[key], val)
+    return len(gold["calls"])

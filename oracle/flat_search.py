@@ -170,7 +170,9 @@ class OracleRAGDatabase:
             values = np.asarray(self.columns[col])
             row_group = (values == val).astype(np.int64)  # group 1 = excluded value
             exclude = np.array([1])
-        dist, idx = flat_search(self.db, np.asarray(vector, dtype=np.float32)[None], top_k,
+        column = vector_column_name or self.vector_column
+        mat = self.db if column == self.vector_column else np.asarray(self.columns[column], dtype=np.float32)
+        dist, idx = flat_search(mat, np.asarray(vector, dtype=np.float32)[None], top_k,
                                 self.metric, row_group, exclude, self.prefilter)
         cols = select if select is not None else [c for c in self.columns]
         recs = []
@@ -186,6 +188,23 @@ class OracleRAGDatabase:
                     refine_factor=30, output_format="dict"):
         return self.vector_search(text, "text_embedding", top_k, table, where, select, nprobes,
                                   refine_factor, output_format)
+
+
+    def image_search(self, image_embedding, top_k=10, table=None, where=None, select=None, nprobes=50,
+                     refine_factor=30, output_format="dict"):
+        return self.vector_search(image_embedding, "image_embedding", top_k, table, where, select, nprobes,
+                                  refine_factor, output_format)
+
+    def text_image_search(self, text, image_embedding, top_k=(20, 10), table=None, where=None, select=None,
+                          nprobes=50, refine_factor=30, output_format="dict"):
+        """src/data/rag.py:101-130: text top-k0 (with the where clause), the hits become a temporary
+        table, image top-k1 inside it (no where clause on the second stage)."""
+        db = self if table is None else table
+        first = db.vector_search(text, "text_embedding", top_k[0], None, where, None, nprobes, refine_factor)
+        if not first:
+            return self.format_result([], output_format)
+        tmp = OracleRAGDatabase({c: np.asarray([r[c] for r in first]) for c in first[0]}, metric=self.metric)
+        return tmp.image_search(image_embedding, top_k[1], None, None, select, nprobes, refine_factor, output_format)
 
 
 def _py(v):

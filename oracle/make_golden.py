@@ -6,6 +6,9 @@ Run in the build container (the only place /root/reference exists):
 cama_context_{bf16,f32}.npz   inputs + the (x, mask) captured from the reference's REAL
                               ActionTransformer.batch_forward (oracle/cama_context.py) —
                               these pin the gather/context kernel to the reference itself.
+rag_reference_class.json      what the reference's REAL RAGDatabase class (src/data/rag.py) returns for
+                              the calls prepare_annotations makes (and the other public methods), run
+                              over the LanceDB stand-in oracle/fake_lancedb.py.
 retrieval_small.npz           seeded database / queries / group ids with the oracle's own
                               answers for l2 / cosine / dot, post- and pre-filter. LanceDB is
                               not installable here, so these pin the oracle against
@@ -68,12 +71,104 @@ def make_retrieval(name="retrieval_small.npz", n=2000, dim=256, nq=16, k=12, see
     np.savez_compressed(OUT / name, **out)
 
 
+def rag_class_table(n=1500, dim=256, seed=21) -> dict:
+    """The in-memory RAG table (schema of tools/build_rag_database.py:35-45) behind
+    rag_reference_class.json; tests rebuild it from the same seed."""
+    rng = np.random.default_rng(seed)
+    cent = flat_search.normalise_rows(rng.standard_normal((24, dim)).astype(np.float32))
+    emb = flat_search.normalise_rows(cent[rng.integers(0, 24, n)] +
+                                     0.4 / np.sqrt(dim) * rng.standard_normal((n, dim)).astype(np.float32))
+    img = flat_search.normalise_rows(rng.standard_normal((n, dim)).astype(np.float32))
+    return {"text": np.array([f"caption {j}" for j in range(n)]), "text_embedding": emb, "image_embedding": img,
+            "id": np.arange(n), "uid": np.array([f"u{j}" for j in range(n)]), "dataset": np.array(["openvid"] * n),
+            "video": np.array([f"clip_{j // 3:05d}.mp4" for j in range(n)]),
+            "start_sec": (np.arange(n) % 3) * 2.0, "end_sec": (np.arange(n) % 3) * 2.0 + 2.0}
+
+
+def rag_class_calls(table: dict) -> list[dict]:
+    """The calls recorded in rag_reference_class.json: (method, kwargs) with array arguments given
+    as (column, row, scale) so that the file stays small and tests can rebuild them."""
+    calls = []
+    for j in (5, 77, 640, 1201, 1499):       # the prepare_annotations pattern, datamodule.py:231-236
+        calls.append({"method": "text_search", "text": ("text_embedding", j, 7.5), "top_k": 12,
+                      "where": f'video != "{table["video"][j]}"', "select": ["video", "start_sec", "end_sec"]})
+    calls.append({"method": "text_search", "text": ("text_embedding", 33, 1.0)})                     # all defaults
+    calls.append({"method": "text_search", "text": ("text_embedding", 34, 2.0), "top_k": 5, "select": ["id", "uid"],
+                  "output_format": "list"})
+    calls.append({"method": "text_search", "text": ("text_embedding", 35, 2.0), "top_k": 4, "select": ["id", "video"],
+                  "output_format": "pandas"})
+    calls.append({"method": "text_search", "text": ("text_embedding", 36, 2.0), "top_k": 4, "select": ["id", "dataset"],
+                  "output_format": "pyarrow"})
+    calls.append({"method": "vector_search", "vector": ("image_embedding", 90, 3.0), "vector_column_name": "image_embedding",
+                  "top_k": 6, "select": ["id"]})
+    calls.append({"method": "image_search", "image_embedding": ("image_embedding", 91, 0.5), "top_k": 3,
+                  "where": f'video != "{table["video"][91]}"', "select": ["id", "video"]})
+    for j in (100, 900):                      # datamodule.py:239-245 with K = 9
+        calls.append({"method": "text_image_search", "text": ("text_embedding", j, 4.0),
+                      "image_embedding": ("image_embedding", j, 2.0), "top_k": (21, 9),
+                      "where": f'video != "{table["video"][j]}"', "select": ["video", "start_sec", "end_sec"]})
+    calls.append({"method": "text_image_search", "text": ("text_embedding", 7, 1.0),
+                  "image_embedding": ("image_embedding", 8, 1.0), "top_k": (6, 3), "select": ["id"]})
+    calls.append({"method": "text_search", "text": ("text_embedding", 1, 1.0), "output_format": "csv"})  # ValueError
+    return calls
+
+
+def rag_class_kwargs(table: dict, call: dict) -> dict:
+    kw = {k: v for k, v in call.items() if k != "method"}
+    for key in ("text", "vector", "image_embedding"):
+        if key in kw:
+            col, row, scale = kw[key]
+            kw[key] = (table[col][row] * np.float32(scale)).astype(np.float32)
+    if "top_k" in kw and isinstance(kw["top_k"], list):
+        kw["top_k"] = tuple(kw["top_k"])
+    return kw
+
+
+def rag_class_summary(result) -> dict:
+    """A JSON-able digest of what a RAGDatabase call returned, whatever the output format."""
+    import pandas as pd
+    import pyarrow as pa
+    if isinstance(result, pd.DataFrame):
+        kind, recs = "pandas", result.to_dict("records")
+    elif isinstance(result, pa.Table):
+        kind, recs = "pyarrow", result.to_pylist()
+    else:
+        kind, recs = "list", list(result)
+    out = {"kind": kind, "keys": sorted(recs[0]) if recs else [], "records": []}
+    for r in recs:
+        out["records"].append({k: (float(v) if isinstance(v, (float, np.floating)) else
+                                   int(v) if isinstance(v, (int, np.integer)) else
+                                   v if isinstance(v, str) else None)      # vectors are not stored
+                               for k, v in r.items()})
+    return out
+
+
+def make_rag_class(name="rag_reference_class.json"):
+    """Runs the reference's REAL RAGDatabase class (src/data/rag.py, unmodified) over the LanceDB
+    stand-in of oracle/fake_lancedb.py and records what it returns: pins argument plumbing, column
+    selection, the two-stage text->image search and result formatting of the drop-in class."""
+    import json
+    from . import fake_lancedb
+    table = rag_class_table()
+    ref = fake_lancedb.reference_rag_database(table)
+    recorded = []
+    for call in rag_class_calls(table):
+        kw = rag_class_kwargs(table, call)
+        try:
+            res = rag_class_summary(getattr(ref, call["method"])(**kw))
+        except ValueError as e:
+            res = {"raises": "ValueError", "message": str(e)}
+        recorded.append({"call": call, "result": res})
+    (OUT / name).write_text(json.dumps({"table": {"n": 1500, "dim": 256, "seed": 21}, "calls": recorded}, indent=1))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
+    make_rag_class()
     make_cama(torch.bfloat16, "cama_context_bf16.npz")
     make_cama(torch.float32, "cama_context_f32.npz")
     make_retrieval()
-    for f in sorted(OUT.glob("*.npz")):
+    for f in sorted(OUT.glob("*.npz")) + sorted(OUT.glob("*.json")):
         print(f, f.stat().st_size, "bytes")
 
 

@@ -123,3 +123,15 @@ def test_on_disk_table_and_pickle_roundtrip(libmrag, table, tmp_path):
     assert [x["id"] for x in db2.text_search(small["text_embedding"][10], top_k=3, select=["id"])] == [x["id"] for x in r]
     with pytest.raises(TypeError):
         pickle.dumps(RAGDatabase(None, None, columns=small))
+
+
+def test_drop_in_class_matches_the_reference_class_recording(libmrag, golden_dir):
+    """motionrag_b200.RAGDatabase replays every call recorded from the reference's REAL RAGDatabase
+    class (src/data/rag.py run over oracle/fake_lancedb.py): same rows in the same order, same keys,
+    same container type per output_format, distances within 1e-3, same ValueError."""
+    from motionrag_b200 import RAGDatabase
+    from oracle import compare
+    cache = {}
+    n = compare.replay_reference_class(lambda t: cache.setdefault(id(t), RAGDatabase(None, None, 'cuda', columns=t)),
+                                       golden_dir / "rag_reference_class.json", rel=1e-3)
+    assert n >= 15

@@ -162,3 +162,13 @@ def test_gather_restatement_uncond_for_missing():
     un = -torch.ones(2, 3)
     out = cc.gather_restatement(table, torch.tensor([[5, -1, 0]]), un)
     assert torch.equal(out[0, 0], table[5]) and torch.equal(out[0, 1], un) and torch.equal(out[0, 2], table[0])
+
+
+def test_oracle_class_matches_the_reference_class_recording(golden_dir):
+    """OracleRAGDatabase (the restated class) == the reference's own class on the same engine."""
+    from oracle import flat_search as fs
+    cache = {}
+    from oracle import compare
+    n = compare.replay_reference_class(lambda t: cache.setdefault(id(t), fs.OracleRAGDatabase(t)),
+                                       golden_dir / "rag_reference_class.json")
+    assert n >= 15

@@ -99,10 +99,10 @@ class CamaTransformer:
 
 
 def linear(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, gelu: bool = False,
-           splits: int = 1, cluster_reduce: bool = False) -> torch.Tensor:
+           splits: int = 1, cluster_reduce: bool = False, partial: bool = False) -> torch.Tensor:
     """The K5 GEMM on its own: a [M,K] bf16, weight [N,K] bf16 -> bf16 [M,N] (splits == 1, or
     cluster_reduce: the K splits are summed on chip inside a thread-block cluster) or fp32 partial sums
-    [splits, M, N]."""
+    [splits, M, N] (always when partial=True)."""
     lib = _cabi.load()
     M, K = a.shape
     N = weight.shape[0]
@@ -113,7 +113,7 @@ def linear(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
         pad = torch.zeros((128, K), dtype=a.dtype, device=dev)
         pad[:M] = a
         a, rows_alloc = pad, 128
-    if splits == 1 or cluster_reduce:
+    if (splits == 1 and not partial) or cluster_reduce:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
         part = None
     else:

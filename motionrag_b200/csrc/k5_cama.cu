@@ -250,6 +250,178 @@ __global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
   }
 }
 
+// ---- K5p: persistent form of K5 for GEMMs of several waves of tiles -----------------------------
+// One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so the CTAs of one
+// round share A tiles in L2). Two 128-column TMEM accumulators: the MMA thread starts the k-loop of
+// tile i+1 while the eight epilogue warps (two per TMEM lane quarter, 64 columns each) drain tile i —
+// bias / erf-GELU / bf16 packing no longer sits on the tensor pipe's critical path. The TMA producer
+// runs ahead across tile boundaries through the same 6-stage ring. bf16 output or one fp32 partial.
+constexpr int kPersEpiWarps = 8;
+constexpr int kPersThreads = 64 + 32 * kPersEpiWarps;
+// BN = 256 halves the L2 -> shared-memory bytes per flop (the bound of 128 x 128 tiles at ~0.65 PF/s):
+// 48 KB per k-block for a 128 x 256 x 64 MMA block, 4 stages, both accumulators fill the 512 TMEM columns
+template <int BN>
+struct PersCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr uint32_t kStageBytes = kGemmABytes + BN * kBK * 2;
+  static constexpr uint32_t kSmem = kStages * kStageBytes + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kPersThreads, 1)
+    k5_linear_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                                const GemmArgs g, int m_tiles, int n_tiles) {
+  constexpr int kPersBN = BN, kPersStages = PersCfg<BN>::kStages;
+  constexpr uint32_t kPersStageBytes = PersCfg<BN>::kStageBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPersStages * kPersStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kPersStages;
+  uint64_t* tfull_bar = bars + 2 * kPersStages;       // [2] accumulator ready
+  uint64_t* tempty_bar = bars + 2 * kPersStages + 2;  // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPersStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int total = m_tiles * n_tiles, kblocks = g.K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    for (int s = 0; s < kPersStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kPersEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * kPersBN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_a = policy_evict_last(), pol_w = policy_evict_normal();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m_tile = t / n_tiles, n_tile = t % n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kPersStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kPersStageBytes);
+          tma_load_2d(sa, &tm_a, &full_bar[stage], kb * kBK, m_tile * kGemmBM, pol_a);
+          tma_load_2d(sa + kGemmABytes, &tm_w, &full_bar[stage], kb * kBK, n_tile * kPersBN, pol_w);
+          if (++stage == kPersStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, kPersBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&tempty_bar[buf], ((i >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(buf * kPersBN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kPersStageBytes);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + kGemmABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_bf16(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kPersStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // epilogue warp: TMEM lane quarter = warp % 4 (hardware rule), column half by warp group
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    int i = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
+      const int m_tile = t / n_tiles, n_tile = t % n_tiles, buf = i & 1;
+      mbar_wait(&tfull_bar[buf], (i >> 1) & 1);
+      tc_fence_after();
+      constexpr int kColsPerWarp = kPersBN / 2, kBatches = kColsPerWarp / 64;
+      const uint32_t t_addr =
+          tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kPersBN + half * kColsPerWarp);
+      const int m = m_tile * kGemmBM + quarter * 32 + lane;
+#pragma unroll 1
+      for (int bt = 0; bt < kBatches; ++bt) {
+        uint32_t v[2][32];
+        tmem_ld_32x32(t_addr + bt * 64, v[0]);
+        tmem_ld_32x32(t_addr + bt * 64 + 32, v[1]);
+        tmem_ld_wait();
+        if (bt == kBatches - 1) {  // everything of this accumulator is in registers: release it now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        if (m < g.M) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int n0 = n_tile * kPersBN + half * kColsPerWarp + bt * 64 + c * 32;
+            if (g.out != nullptr) {
+              uint32_t packed[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float a = __uint_as_float(v[c][j]), b = __uint_as_float(v[c][j + 1]);
+                if (g.bias != nullptr) {
+                  const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(g.bias + n0 + j);
+                  a += __bfloat162float(bb.x);
+                  b += __bfloat162float(bb.y);
+                }
+                if (g.gelu) {
+                  a = gelu_erf(a);
+                  b = gelu_erf(b);
+                }
+                const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+                packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&r);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(m) * g.N + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            } else {
+              float4* dst = reinterpret_cast<float4*>(g.partial + size_t(m) * g.N + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(__uint_as_float(v[c][4 * j]), __uint_as_float(v[c][4 * j + 1]),
+                                     __uint_as_float(v[c][4 * j + 2]), __uint_as_float(v[c][4 * j + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * kPersBN>(tmem_base);
+  }
+}
+
 // ---- K6: block-causal attention, head_dim 64 ---------------------------------------------------
 // grid (b * heads, groups, 32-row blocks of a group). Group g attends to the keys of groups 0..g
 // (get_mask), so there is no mask inside a CTA apart from the padding of the last 64-key chunk.
@@ -597,7 +769,30 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   g.out = static_cast<__nv_bfloat16*>(out_bf16);
   g.partial = partial;
   cudaError_t e;
-  if (reduce) {  // bf16 output of a split-K GEMM: sum the splits inside a cluster (128-wide tiles, two CTAs per SM)
+  static const bool persistent_ok = [] {  // MRAG_K5_PERSISTENT=0 falls back to one tile per CTA (A/B runs)
+    const char* v = getenv("MRAG_K5_PERSISTENT");
+    return !(v && atoi(v) == 0);
+  }();
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // persistent kernel when the tile count makes >= 2 full rounds over the SMs (wave quantisation would
+  // otherwise cost more than the overlap gains): 128 x 256 tiles when they still do, else 128 x 128
+  const int tiles256 = (N % 256 == 0) ? (N / 256) * m_tiles : 0;
+  if (!reduce && splits == 1 && persistent_ok && (tiles256 >= 2 * sms || ctas128 >= 2 * sms)) {
+    const bool wide = tiles256 >= 2 * sms;
+    const int pbn = wide ? 256 : 128;
+    if (!make_tmap(&tm_w, w_bf16, N, K, pbn)) return cudaErrorInvalidValue;
+    const void* fn = wide ? reinterpret_cast<const void*>(k5_linear_persistent_kernel<256>)
+                          : reinterpret_cast<const void*>(k5_linear_persistent_kernel<128>);
+    const uint32_t smem = wide ? PersCfg<256>::kSmem : PersCfg<128>::kSmem;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    int mt = m_tiles, nt = N / pbn;
+    const int total = mt * nt;
+    void* args[] = {&tm_a, &tm_w, &g, &mt, &nt};
+    e = launch_pdl(fn, dim3(unsigned(total < sms ? total : sms)), dim3(kPersThreads), smem, st, args);
+  } else if (reduce) {  // bf16 output of a split-K GEMM: sum the splits inside a cluster (128-wide tiles, two CTAs per SM)
     if (splits > 8 || (splits & (splits - 1)) != 0) return cudaErrorInvalidValue;
     e = launch_k5_bn<128, 3, true>(tm_a, tm_w, g, splits, st);
   } else {

@@ -56,6 +56,32 @@ def test_linear_with_cluster_reduced_split_k(libmrag, M, N, K, bias, gelu, split
     assert (got.float() - unsplit.float()).abs().max() <= 2 ** -6 * max(1.0, float(want.abs().max()))   # <= 1 bf16 ulp
 
 
+@pytest.mark.parametrize("M,N,K,bias,gelu,partial", [(4000, 4096, 1024, True, True, False),      # 128 x 256 tiles
+                                                     (4000, 3072, 1024, True, False, False),
+                                                     (6000, 2048, 256, False, False, True),
+                                                     (12803, 384, 128, True, False, False),       # 128 x 128 tiles
+                                                     (12803, 384, 192, False, False, True),
+                                                     (2500, 1024, 4096, False, False, True)])      # one tile per CTA
+def test_persistent_linear_for_many_tiles(libmrag, M, N, K, bias, gelu, partial):
+    """More than one wave of 128 x 128 tiles runs the persistent kernel (double-buffered TMEM accumulators)."""
+    from motionrag_b200.cama import linear
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().cuda()
+    b = torch.randn(N, generator=g).bfloat16().cuda() if bias else None
+    want = a.float() @ w.float().T
+    got = linear(a, w, b, gelu, 1, partial=partial)
+    if partial:
+        assert tuple(got.shape) == (1, M, N) and torch.allclose(got[0], want, rtol=1e-4, atol=1e-4)
+        return
+    if bias:
+        want = want + b.float()
+    if gelu:
+        want = torch.nn.functional.gelu(want)
+    assert (got.float() - want).abs().max() < 2e-2
+    assert torch.equal(got, linear(a, w, b, gelu, 1))
+
+
 def _encoder(d, heads, dff, layers, seed):
     torch.manual_seed(seed)
     layer = nn.TransformerEncoderLayer(d, heads, dff, 0.0, "gelu", batch_first=True, norm_first=False, bias=True)

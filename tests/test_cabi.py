@@ -89,3 +89,28 @@ def test_missing_library_is_an_error(tmp_path):
 def test_product_package_never_imports_the_oracle():
     for f in (ROOT / "motionrag_b200").rglob("*.py"):
         assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read_text(), re.M), f
+
+
+def _build_c_host(tmp_path):
+    from motionrag_b200 import _cabi
+    exe = tmp_path / "search_host"
+    r = subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", str(ROOT / "tests" / "c_host" / "search_host.c"),
+                        "-I", str(ROOT / "include"), "-L", str(_cabi.LIB_PATH.parent), "-lmrag", "-lm",
+                        f"-Wl,-rpath,{_cabi.LIB_PATH.parent}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_pure_c_host_links_and_fails_loudly_without_gpu(libmrag, tmp_path):
+    """include/mrag.h + libmrag.so are enough for a host in another language: a C99 program links
+    against them; with no GPU the library refuses with MRAG_ERR_DEVICE instead of computing on the CPU."""
+    r = subprocess.run([str(_build_c_host(tmp_path))], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 3 and "no CPU path" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+def test_pure_c_host_search_matches_brute_force(libmrag, tmp_path):
+    r = subprocess.run([str(_build_c_host(tmp_path))], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "0 mismatches" in r.stdout

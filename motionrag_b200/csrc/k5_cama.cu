@@ -422,6 +422,175 @@ __global__ void __launch_bounds__(kPersThreads, 1)
   }
 }
 
+// ---- K5 pair form: 256 x 256 tiles on a CTA pair (cta_group::2) ------------------------------------
+// The persistent kernel above is bound by the L2 -> shared-memory path (128 x 256 tiles: 48 KB per
+// 128 x 256 x 64 MMA block). Two CTAs of a cluster share one M = 256 x N = 256 MMA stream instead: each
+// stages its own 128 rows of A and 128 of the 256 rows of the W tile (32 KB per k-block and SM for the
+// same flops, 6 stages), the leader's single thread issues tcgen05.mma.cta_group::2, commits are
+// multicast to both CTAs, and each CTA drains the 128 x 256 accumulator of its own rows with eight
+// epilogue warps while the next tile accumulates in the other half of TMEM. Same structure as the
+// CTA-pair scan kernel (k2_batch2.cu). Tiles: (256-row pair, 256-column block), n fastest.
+constexpr int kPairBN = 256, kPairStages = 6;
+constexpr uint32_t kPairStageBytes = kGemmABytes + (kPairBN / 2) * kBK * 2;  // 16 KB A + 16 KB half of W
+constexpr uint32_t kPairSmem = kPairStages * kPairStageBytes + 256 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersThreads, 1)
+    k5_linear_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                          const GemmArgs g, int m_pairs, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes);
+  uint64_t* full_bar = bars;                          // [stages] used in the leader only
+  uint64_t* empty_bar = bars + kPairStages;           // [stages] each CTA its own (multicast commit)
+  uint64_t* tfull_bar = bars + 2 * kPairStages;       // [2]      each CTA its own (multicast commit)
+  uint64_t* tempty_bar = bars + 2 * kPairStages + 2;  // [2]      used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairStages + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;");
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int total = m_pairs * n_tiles, kblocks = g.K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader producer's arrive.expect_tx (+ the bytes of both CTAs)
+      mbar_init(&empty_bar[s], 1);  // one multicast commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 2 * kPersEpiWarps);  // epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<2 * kPairBN>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers exist before anything is signalled remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_a = policy_evict_last(), pol_w = policy_evict_normal();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair_id; t < total; t += n_pairs) {
+        const int m_pair = t / n_tiles, n_tile = t % n_tiles;
+        const int a_row0 = (m_pair * 2 + int(cta_rank)) * kGemmBM;
+        const int w_row0 = n_tile * kPairBN + int(cta_rank) * (kPairBN / 2);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kPairStageBytes;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          tma_load_2d_pair(sa, &tm_a, &full_bar[stage], kb * kBK, a_row0, pol_a);
+          tma_load_2d_pair(sa + kGemmABytes, &tm_w, &full_bar[stage], kb * kBK, w_row0, pol_w);
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kGemmBM, kPairBN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int i = 0;
+      for (int t = pair_id; t < total; t += n_pairs, ++i) {
+        const int buf = i & 1;
+        mbar_wait(&tempty_bar[buf], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(buf * kPairBN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+          const uint64_t da = umma_desc_k_sw128(sa);
+          const uint64_t db = umma_desc_k_sw128(sa + kGemmABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_bf16_pair(d_tmem, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    int i = 0;
+    for (int t = pair_id; t < total; t += n_pairs, ++i) {
+      const int m_pair = t / n_tiles, n_tile = t % n_tiles, buf = i & 1;
+      mbar_wait(&tfull_bar[buf], (i >> 1) & 1);
+      tc_fence_after();
+      constexpr int kColsPerWarp = kPairBN / 2;
+      const uint32_t t_addr =
+          tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kPairBN + half * kColsPerWarp);
+      const int m = (m_pair * 2 + int(cta_rank)) * kGemmBM + quarter * 32 + lane;
+#pragma unroll 1
+      for (int bt = 0; bt < kColsPerWarp / 64; ++bt) {
+        uint32_t v[2][32];
+        tmem_ld_32x32(t_addr + bt * 64, v[0]);
+        tmem_ld_32x32(t_addr + bt * 64 + 32, v[1]);
+        tmem_ld_wait();
+        if (bt == kColsPerWarp / 64 - 1) {  // accumulator fully in registers: hand it back to the leader's MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tempty_bar[buf], 0);
+        }
+        if (m < g.M) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int n0 = n_tile * kPairBN + half * kColsPerWarp + bt * 64 + c * 32;
+            if (g.out != nullptr) {
+              uint32_t packed[16];
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float a = __uint_as_float(v[c][j]), b = __uint_as_float(v[c][j + 1]);
+                if (g.bias != nullptr) {
+                  const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(g.bias + n0 + j);
+                  a += __bfloat162float(bb.x);
+                  b += __bfloat162float(bb.y);
+                }
+                if (g.gelu) {
+                  a = gelu_erf(a);
+                  b = gelu_erf(b);
+                }
+                const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+                packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&r);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(m) * g.N + n0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            } else {
+              float4* dst = reinterpret_cast<float4*>(g.partial + size_t(m) * g.N + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(__uint_as_float(v[c][4 * j]), __uint_as_float(v[c][4 * j + 1]),
+                                     __uint_as_float(v[c][4 * j + 2]), __uint_as_float(v[c][4 * j + 3]));
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves while the pair's MMAs / remote arrives may still land
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair<2 * kPairBN>(tmem_base);
+  }
+}
+
 // ---- K6: block-causal attention, head_dim 64 ---------------------------------------------------
 // grid (b * heads, groups, 32-row blocks of a group). Group g attends to the keys of groups 0..g
 // (get_mask), so there is no mask inside a CTA apart from the padding of the last 64-key chunk.
@@ -779,7 +948,22 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   // persistent kernel when the tile count makes >= 2 full rounds over the SMs (wave quantisation would
   // otherwise cost more than the overlap gains): 128 x 256 tiles when they still do, else 128 x 128
   const int tiles256 = (N % 256 == 0) ? (N / 256) * m_tiles : 0;
-  if (!reduce && splits == 1 && persistent_ok && (tiles256 >= 2 * sms || ctas128 >= 2 * sms)) {
+  static const bool pair_ok = [] {  // MRAG_K5_PAIR=0 keeps the single-CTA persistent kernel (A/B runs)
+    const char* v = getenv("MRAG_K5_PAIR");
+    return !(v && atoi(v) == 0);
+  }();
+  const int m_pairs = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int pair_tiles = (N % kPairBN == 0) ? (N / kPairBN) * m_pairs : 0;
+  if (!reduce && splits == 1 && persistent_ok && pair_ok && pair_tiles >= 2 * (sms / 2)) {
+    if (!make_tmap(&tm_w, w_bf16, N, K, kPairBN / 2)) return cudaErrorInvalidValue;
+    e = cudaFuncSetAttribute(k5_linear_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPairSmem));
+    if (e != cudaSuccess) return e;
+    int mp = m_pairs, nt = N / kPairBN;
+    const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    void* args[] = {&tm_a, &tm_w, &g, &mp, &nt};
+    e = launch_pdl(reinterpret_cast<const void*>(k5_linear_pair_kernel), dim3(unsigned(2 * pairs)),
+                   dim3(kPersThreads), kPairSmem, st, args);
+  } else if (!reduce && splits == 1 && persistent_ok && (tiles256 >= 2 * sms || ctas128 >= 2 * sms)) {
     const bool wide = tiles256 >= 2 * sms;
     const int pbn = wide ? 256 : 128;
     if (!make_tmap(&tm_w, w_bf16, N, K, pbn)) return cudaErrorInvalidValue;

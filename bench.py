@@ -422,7 +422,7 @@ def run_ours(args):
         cama = m.CamaTransformer(enc, groups=K_REF + 1, group_tokens=L_TOK, max_batch=16, device=dev.index or 0)
         T = (K_REF + 1) * L_TOK
         res = {"workload": "CAMA forward: 4 layers, d_model 1024, 16 heads, d_ff 4096, 250 tokens, bf16, CUDA-graph replay",
-               "kernels": "k5_linear_kernel (tcgen05), k6_attention_kernel, k7_add_layernorm_kernel; 28 launches/forward"}
+               "kernels": "k5_linear_kernel / k5_linear_pair_kernel (tcgen05), k6_attention_kernel, k7_add_layernorm_kernel; 28 launches/forward"}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for b in (1, 16):
             cama.input_view(b).normal_()

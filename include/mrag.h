@@ -237,7 +237,8 @@ MRAG_API int mrag_cama_io(const mrag_cama* c, void** x_in_dev, void** y_out_dev)
  * the 7*n_layers launch chain is captured once per b and replayed as one CUDA graph */
 MRAG_API int mrag_cama_forward(mrag_cama* c, int32_t b, int32_t use_graph, void* stream);
 /* the GEMM building block on its own (tests / profiling): C[M,N] = A[M,K] W[N,K]^T (+bias)(gelu) to
- * bf16, or fp32 partial sums [splits][M,N] when out_bf16_dev is NULL; N %% 128 == 0, K %% 64 == 0 */
+ * bf16 (splits > 1: split-K summed inside a thread-block cluster, splits a power of two <= 8), or fp32
+ * partial sums [splits][M,N] when out_bf16_dev is NULL; N %% 128 == 0, K %% 64 == 0, splits | K/64 */
 MRAG_API int mrag_linear(const void* a_dev, int32_t a_rows_alloc, const void* w_dev, int32_t M, int32_t N,
                          int32_t K, const void* bias_dev, int32_t gelu, void* out_bf16_dev,
                          float* partial_dev, int32_t splits, void* stream);

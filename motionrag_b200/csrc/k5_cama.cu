@@ -14,9 +14,13 @@
 //                          x2  = LN2(x1 + p + b2)      K7
 // K5 is a tcgen05 GEMM built from the same parts as the retrieval scan K2 (TMA ring of
 // SWIZZLE_128B k-blocks -> single-thread tcgen05.mma with the accumulator in TMEM ->
-// tcgen05.ld epilogue), tile 128 x 128, one tile (and one K split) per CTA. The residual path
-// stays in fp32 until the LayerNorm (torch rounds the projection to bf16 first), so results are
-// at least as close to an fp32 evaluation as torch's own bf16 path.
+// tcgen05.ld epilogue). Four forms, chosen per launch by launch_k5_linear from the tile count:
+//   k5_linear_kernel<BN,STAGES,false>   one 128 x BN tile and one K split per CTA (less than ~2 rounds of tiles)
+//   k5_linear_kernel<128,3,true>        K splits of a tile = one cluster, partials summed through DSMEM
+//   k5_linear_persistent_kernel<BN>     one CTA per SM walks the tiles, two TMEM accumulators (N % 256 != 0)
+//   k5_linear_pair_kernel               the same on a CTA pair: cta_group::2, 256 x 256 tiles (N % 256 == 0)
+// The residual path stays in fp32 until the LayerNorm (torch rounds the projection to bf16 first), so
+// results are at least as close to an fp32 evaluation as torch's own bf16 path.
 #include <cstdlib>
 
 #include "k2_common.cuh"

@@ -83,8 +83,9 @@ cudaError_t launch_k4_gather(const void* const* shard_ptrs, int nshards, int64_t
                              int C, int dtype, cudaStream_t st);
 
 // K5/K6/K7: CAMA transformer pieces (k5_cama.cu) ------------------------------------------------
-// C[M,N] = A[M,K] W[N,K]^T (+bias)(gelu) -> bf16 `out`, or fp32 partial sums [splits][M,N] when out
-// is null. a_rows_alloc = rows the A buffer really has (>= M rounded up to 128).
+// C[M,N] = A[M,K] W[N,K]^T (+bias)(gelu) -> bf16 `out` (splits > 1: the K splits are summed on chip
+// inside a thread-block cluster), or fp32 partial sums [splits][M,N] when out is null.
+// a_rows_alloc = rows the A buffer really has (TMA zero-fills tile rows beyond it).
 cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w_bf16, int M, int N, int K,
                              const void* bias, bool gelu, void* out_bf16, float* partial, int splits,
                              cudaStream_t st);

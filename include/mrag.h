@@ -181,6 +181,15 @@ MRAG_API int mrag_search_host(const mrag_store* s, const float* queries_host, in
                      float* out_dist_host, int64_t* out_idx_host, int32_t* out_group_host,
                      void* stream);
 
+/* ---- second stage of RAGDatabase.text_image_search (src/data/rag.py:118-128): the reference puts
+ *      the text hits into a temporary table and runs the image search inside it. Here: exact
+ *      distances (store metric formulas, fp32) of the candidate rows cand_idx_dev [nq, kc] (kc <= 64,
+ *      -1 = no candidate) of `s` (the image-embedding store) against queries_dev [nq, dim]; outputs
+ *      [nq, k_out] ascending by (distance, position in the candidate list), unused = (+inf, -1). */
+MRAG_API int mrag_rescore_rows(const mrag_store* s, const float* queries_dev, int32_t nq,
+                      const int64_t* cand_idx_dev, int32_t kc, int32_t metric, int32_t k_out,
+                      float* out_dist_dev, int64_t* out_idx_dev, void* stream);
+
 /* ---- cross-shard merge of per-shard results (after the all-gather of [nshards, nq, k]) ----
  * Shard g's [nq, k_in] block of every field starts shard_stride_bytes * g after the field's
  * base pointer (0 = dense [nshards, nq, k_in] arrays); this lets one packed per-rank record

@@ -81,6 +81,8 @@ SIGNATURES = {
                                     C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mrag_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrag_rescore_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrag_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),

@@ -602,6 +602,21 @@ int mrag_search_host(const mrag_store* s, const float* queries_host, int32_t nq,
   return MRAG_OK;
 }
 
+int mrag_rescore_rows(const mrag_store* s, const float* queries_dev, int32_t nq, const int64_t* cand_idx_dev,
+                      int32_t kc, int32_t metric, int32_t k_out, float* out_dist_dev, int64_t* out_idx_dev,
+                      void* stream) {
+  if (!s || !queries_dev || !cand_idx_dev || !out_dist_dev || !out_idx_dev)
+    return fail(MRAG_ERR_ARG, "null store or device buffer");
+  if (nq < 1 || kc < 1 || kc > 64 || k_out < 1 || k_out > 64 || metric < 0 || metric > 2)
+    return fail(MRAG_ERR_ARG, "need nq >= 1, 1 <= kc <= 64, 1 <= k_out <= 64 (got nq %d kc %d k_out %d)", nq, kc,
+                k_out);
+  if (s->n_rows < 1) return fail(MRAG_ERR_ARG, "store is empty");
+  DeviceGuard guard(s->device);
+  CK(launch_k3_rescore_rows(s->rows_f32, s->n_rows, s->dim, queries_dev, nq, cand_idx_dev, kc, metric, k_out,
+                            out_dist_dev, out_idx_dev, static_cast<cudaStream_t>(stream)));
+  return MRAG_OK;
+}
+
 int mrag_merge_topk(const float* cand_dist_dev, const int64_t* cand_idx_dev,
                     const int32_t* cand_group_dev, int64_t shard_stride_bytes, int32_t nshards,
                     int32_t nq, int32_t k_in,

@@ -474,6 +474,76 @@ cudaError_t launch_k3_merge_rerank(const uint64_t* cand, int n_runs, int run_len
   return le != cudaSuccess ? le : cudaGetLastError();
 }
 
+// ---- second stage of text_image_search: exact distances of given rows --------------------------
+// The reference materialises the text hits as a temporary table and runs the image search inside it
+// (src/data/rag.py:118-128). Here the candidate row ids of every query stay on the device and one
+// block per query scores them against the image-embedding store: warp per candidate, the fp32
+// formulas of the re-rank above, ties -> earlier candidate (= lower row of the temporary table).
+constexpr int kMaxRescore = 64;
+
+__global__ void __launch_bounds__(256)
+    k3_rescore_rows_kernel(const float* __restrict__ db, int64_t n_rows, int dim, const float* __restrict__ queries,
+                           const int64_t* __restrict__ cand_idx, int kc, int metric, int k_out,
+                           float* __restrict__ out_dist, int64_t* __restrict__ out_idx) {
+  __shared__ uint64_t keys[kMaxRescore], sorted[kMaxRescore];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = blockIdx.x;
+  if (tid < kMaxRescore) keys[tid] = kEmptyKey;
+  __syncthreads();
+  const float4* qv = reinterpret_cast<const float4*>(queries + int64_t(q) * dim);
+  const int nv = dim >> 2;
+  for (int c = warp; c < kc; c += 8) {
+    const int64_t row = cand_idx[int64_t(q) * kc + c];
+    if (row < 0 || row >= n_rows) continue;  // warp-uniform
+    const float4* dv = reinterpret_cast<const float4*>(db + row * dim);
+    float l2 = 0.f, dot = 0.f, qq = 0.f, dd = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+      const float4 a = qv[i];
+      const float4 b = dv[i];
+      float t;
+      t = a.x - b.x; l2 = fmaf(t, t, l2);
+      t = a.y - b.y; l2 = fmaf(t, t, l2);
+      t = a.z - b.z; l2 = fmaf(t, t, l2);
+      t = a.w - b.w; l2 = fmaf(t, t, l2);
+      dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot);
+      dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+      qq = fmaf(a.x, a.x, qq); qq = fmaf(a.y, a.y, qq);
+      qq = fmaf(a.z, a.z, qq); qq = fmaf(a.w, a.w, qq);
+      dd = fmaf(b.x, b.x, dd); dd = fmaf(b.y, b.y, dd);
+      dd = fmaf(b.z, b.z, dd); dd = fmaf(b.w, b.w, dd);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      l2 += __shfl_xor_sync(0xffffffffu, l2, off);
+      dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      qq += __shfl_xor_sync(0xffffffffu, qq, off);
+      dd += __shfl_xor_sync(0xffffffffu, dd, off);
+    }
+    float dist;
+    if (metric == 0) dist = l2;
+    else if (metric == 1) dist = 1.f - dot / fmaxf(sqrtf(qq) * sqrtf(dd), 1e-30f);
+    else dist = 1.f - dot;
+    if (lane == 0) keys[c] = (uint64_t(f32_to_ordered(dist)) << 32) | uint32_t(c);
+  }
+  rank_sort_smem(keys, sorted, kMaxRescore, tid, 256);
+  for (int j = tid; j < k_out; j += 256) {
+    const uint64_t key = j < kMaxRescore ? sorted[j] : kEmptyKey;
+    const bool ok = key != kEmptyKey;
+    out_dist[int64_t(q) * k_out + j] = ok ? ordered_to_f32(uint32_t(key >> 32)) : INFINITY;
+    out_idx[int64_t(q) * k_out + j] = ok ? cand_idx[int64_t(q) * kc + int(uint32_t(key))] : -1;
+  }
+}
+
+cudaError_t launch_k3_rescore_rows(const float* db_f32, int64_t n_rows, int dim, const float* queries, int nq,
+                                   const int64_t* cand_idx, int kc, int metric, int k_out, float* out_dist,
+                                   int64_t* out_idx, cudaStream_t st) {
+  if (kc < 1 || kc > kMaxRescore || k_out < 1 || k_out > kMaxRescore || (dim & 3) != 0) return cudaErrorInvalidValue;
+  k3_rescore_rows_kernel<<<nq, 256, 0, st>>>(db_f32, n_rows, dim, queries, cand_idx, kc, metric, k_out, out_dist,
+                                             out_idx);
+  note_launch();
+  return cudaGetLastError();
+}
+
 // ---- cross-shard merge ----------------------------------------------------------------------
 // Shard g's [nq][k_in] block of each field sits `stride` elements (of that field's type) after
 // the base pointer; each shard's list is already sorted by (distance, index) and shards are

@@ -82,6 +82,12 @@ cudaError_t launch_k4_gather(const void* const* shard_ptrs, int nshards, int64_t
                              const void* pe, const void* cond, void* out, int b, int K, int L,
                              int C, int dtype, cudaStream_t st);
 
+// exact fp32 distances of the given rows (second stage of text_image_search): cand_idx [nq][kc] (-1 = none),
+// outputs [nq][k_out] sorted by (distance, candidate position)
+cudaError_t launch_k3_rescore_rows(const float* db_f32, int64_t n_rows, int dim, const float* queries, int nq,
+                                   const int64_t* cand_idx, int kc, int metric, int k_out, float* out_dist,
+                                   int64_t* out_idx, cudaStream_t st);
+
 // K5/K6/K7: CAMA transformer pieces (k5_cama.cu) ------------------------------------------------
 // C[M,N] = A[M,K] W[N,K]^T (+bias)(gelu) -> bf16 `out` (splits > 1: the K splits are summed on chip
 // inside a thread-block cluster), or fp32 partial sums [splits][M,N] when out is null.

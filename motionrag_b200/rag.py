@@ -26,6 +26,12 @@ import torch
 from .store import EmbeddingStore
 
 VECTOR_COLUMNS = ("text_embedding", "image_embedding")
+def _as_2d(v):
+    """One vector (ndarray / Tensor / list) as a [1, dim] float32 array."""
+    a = np.asarray(v.detach().float().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
+    return a[None] if a.ndim == 1 else a
+
+
 _WHERE = re.compile(r'^\s*(\w+)\s*!=\s*(["\'])((?:(?!\2).)*)\2\s*$')
 
 
@@ -384,27 +390,37 @@ class RAGDatabase:
                           refine_factor: int = 30,
                           output_format: Literal["pandas", "pyarrow", "dict"] = 'dict'):
         """src/data/rag.py:101-130: text top-k0, then image-embedding top-k1 inside that
-        candidate set (the reference materialises a temporary table; here the k0 candidate rows
-        become a temporary HBM store searched by the same kernels)."""
+        candidate set (the reference materialises a temporary table; here the k0 candidate rows are
+        scored against the image column by one kernel, see text_image_search_batch)."""
         db = self if table is None else table
-        _, idx0, single = db._search(text, "text_embedding", top_k[0], where, refine_factor)
-        if not single:
+        texts = [text] if isinstance(text, str) else _as_2d(text)
+        if len(texts) != 1:
             raise ValueError("text_image_search takes one query at a time, like the reference")
-        rows = idx0[0][idx0[0] >= 0]
-        if rows.size == 0:
-            return self.format_result([], output_format)
-        img = np.ascontiguousarray(np.asarray(db._vectors["image_embedding"])[rows], dtype=np.float32)
-        tmp = EmbeddingStore(img.shape[1], img.shape[0], self.device)
-        try:
-            tmp.append(img, normalise=False)
-            q, _ = self._as_queries(image_embedding)
-            r2 = tmp.search(q, int(min(top_k[1], 32)), metric=self.metric, path="stream_f32")
-            d2 = r2.distance.cpu().numpy()
-            i2 = r2.index.cpu().numpy()
-        finally:
-            tmp.close()
-        i2g = np.where(i2 >= 0, rows[np.clip(i2, 0, len(rows) - 1)], -1)
-        return self.format_result(db._records(d2, i2g, select)[0], output_format)
+        res = db.text_image_search_batch(texts, _as_2d(image_embedding), top_k, where, select, refine_factor)
+        return self.format_result(res[0], output_format)
+
+    def text_image_search_batch(self, texts, image_embeddings, top_k: tuple[int, int] = (20, 10),
+                                where: Sequence[str | None] | str | None = None, select: list[str] | None = None,
+                                refine_factor: int = 30, batch: int = 4096) -> list[list[dict]]:
+        """The two-stage search for many queries at once: one text scan per `batch` queries (k0 hits
+        each, with the where clause), then ONE kernel that scores every query's k0 candidate rows
+        against the image-embedding column in fp32 and keeps the best k1 (mrag_rescore_rows) — the
+        candidate rows play the part of the reference's temporary table (src/data/rag.py:118-128)."""
+        k0, k1 = int(top_k[0]), int(top_k[1])
+        q_t, _ = self._as_queries(texts)
+        q_i, _ = self._as_queries(image_embeddings)
+        if q_t.shape[0] != q_i.shape[0]:
+            raise ValueError("need one image embedding per text query")
+        img = self._store("image_embedding")
+        wheres = None if where is None else ([where] * q_t.shape[0] if isinstance(where, str) else list(where))
+        out: list[list[dict]] = []
+        for s in range(0, q_t.shape[0], batch):
+            w = None if wheres is None else wheres[s:s + batch]
+            _, idx0, _ = self._search(q_t[s:s + batch], "text_embedding", k0, w, refine_factor)
+            cand = torch.from_numpy(np.ascontiguousarray(idx0)).to(self.device)
+            d1, i1 = img.rescore(q_i[s:s + batch].contiguous(), cand, min(k1, 64), self.metric)
+            out.extend(self._records(d1.cpu().numpy(), i1.cpu().numpy(), select))
+        return out
 
     # -- batched fast path (replaces the spawn pool of datamodule.py:257-262) -----------------------
     def search_batch(self, vectors, top_k: int = 10, where: Sequence[str | None] | str | None = None,
@@ -429,8 +445,8 @@ class RAGDatabase:
 
         `rag_text`: one batched scan per `batch` annotations — k = ref_video_num + 3,
         `where video != "<own video>"`, select video/start_sec/end_sec. `rag_text_image`: the
-        two-stage search with top_k = (2*ref_video_num + 3, ref_video_num) per annotation (not
-        batched: no shipped config uses it). The records are attached as `anno['ref_videos']` and,
+        two-stage search with top_k = (2*ref_video_num + 3, ref_video_num), batched the same way
+        (text scan, then one kernel scoring each annotation's candidates against the image column). The records are attached as `anno['ref_videos']` and,
         like the reference (:268), the list is written with torch.save when `save_path` is given."""
         if ref_video_type == "rag_text":
             vec = np.stack([np.asarray(a['text_embedding'], dtype=np.float32) for a in annotations])
@@ -438,10 +454,11 @@ class RAGDatabase:
             results = self.search_batch(vec, top_k=ref_video_num + 3, where=wheres,
                                         select=['video', 'start_sec', 'end_sec'], batch=batch)
         elif ref_video_type == "rag_text_image":
-            results = [self.text_image_search(a['text_embedding'], a['image_embedding'],
-                                              top_k=(ref_video_num * 2 + 3, ref_video_num),
-                                              where=f'video != "{a["video"]}"',
-                                              select=['video', 'start_sec', 'end_sec']) for a in annotations]
+            results = self.text_image_search_batch(
+                np.stack([np.asarray(a['text_embedding'], dtype=np.float32) for a in annotations]),
+                np.stack([np.asarray(a['image_embedding'], dtype=np.float32) for a in annotations]),
+                top_k=(ref_video_num * 2 + 3, ref_video_num), where=[f'video != "{a["video"]}"' for a in annotations],
+                select=['video', 'start_sec', 'end_sec'], batch=batch)
         else:
             raise ValueError("Invalid ref_video_type.")   # 'gt' / 'random' never touch the database
         for anno, r in zip(annotations, results):

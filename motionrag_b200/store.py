@@ -220,6 +220,26 @@ class EmbeddingStore:
             out.margin = out_margin
         return out
 
+    def rescore(self, queries: torch.Tensor, cand_index: torch.Tensor, k_out: int, metric: str = "l2"):
+        """Exact fp32 distances of the rows `cand_index` [nq, kc] (int64, -1 = none, kc <= 64) of this
+        store against `queries` [nq, dim]: the second stage of text_image_search
+        (src/data/rag.py:118-128) with the candidate rows as the 'temporary table'. Returns
+        (distance f32 [nq, k_out], index i64 [nq, k_out]) sorted by (distance, candidate position)."""
+        if queries.device != self.device or queries.dtype != torch.float32 or not queries.is_contiguous():
+            raise ValueError("queries must be a contiguous float32 tensor on the store's device")
+        if cand_index.device != self.device or cand_index.dtype != torch.int64 or cand_index.ndim != 2 \
+                or cand_index.shape[0] != queries.shape[0]:
+            raise ValueError("cand_index must be int64 [nq, kc] on the store's device")
+        cand_index = cand_index.contiguous()
+        nq, kc = cand_index.shape
+        dist = torch.empty((nq, k_out), dtype=torch.float32, device=self.device)
+        idx = torch.empty((nq, k_out), dtype=torch.int64, device=self.device)
+        check(self._lib.mrag_rescore_rows(self._h, C.c_void_p(queries.data_ptr()), nq,
+                                          C.c_void_p(cand_index.data_ptr()), kc, METRIC[metric], int(k_out),
+                                          C.c_void_p(dist.data_ptr()), C.c_void_p(idx.data_ptr()),
+                                          _stream_ptr(self.device)))
+        return dist, idx
+
     def search_host(self, queries: np.ndarray, k: int, *, metric: str = "l2", path: str = "auto",
                     refine: int = 0, exclude_group: np.ndarray | None = None,
                     filter_mode: str = "post", index_base: int = 0, certify: bool = False):

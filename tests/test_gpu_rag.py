@@ -112,6 +112,32 @@ def test_text_image_two_stage(libmrag, table):
     np.testing.assert_allclose([r["_distance"] for r in got], d1[0], rtol=1e-3)
 
 
+def test_text_image_batch_equals_single_calls_and_oracle(libmrag, table):
+    """Batched two-stage search (one text scan + mrag_rescore_rows) == per-query calls == the oracle class."""
+    from motionrag_b200 import RAGDatabase
+    db = RAGDatabase(None, None, 'cuda', columns=table)
+    ora = fs.OracleRAGDatabase(table)
+    rows = [3, 250, 1999, 4000, 5999]
+    texts = np.stack([table["text_embedding"][j] * 5 for j in rows]).astype(np.float32)
+    imgs = np.stack([table["image_embedding"][(j * 7) % 6000] * 2 for j in rows]).astype(np.float32)
+    wheres = [f'video != "{table["video"][j]}"' for j in rows]
+    got = db.text_image_search_batch(texts, imgs, top_k=(21, 9), where=wheres, select=['id', 'video'])
+    for j, t, im, w, g in zip(rows, texts, imgs, wheres, got):
+        _same(g, db.text_image_search(t, im, top_k=(21, 9), where=w, select=['id', 'video']))
+        _same(g, ora.text_image_search(t, im, top_k=(21, 9), where=w, select=['id', 'video']))
+        assert len(g) == 9 and all(r["video"] != table["video"][j] for r in g)
+    # raw kernel: candidates with holes, k_out larger than the candidate count
+    st = db._store("image_embedding")
+    cand = torch.tensor([[5, -1, 17, 5999, -1, 42]], dtype=torch.int64, device="cuda")
+    q = torch.from_numpy(imgs[:1]).cuda()
+    d, i = st.rescore(q, cand, 8)
+    want = sorted(((float(((imgs[0] - table["image_embedding"][r]) ** 2).sum()), p, r)
+                   for p, r in enumerate([5, -1, 17, 5999, -1, 42]) if r >= 0))
+    assert i[0].tolist() == [r for _, _, r in want] + [-1] * 4
+    np.testing.assert_allclose(d[0, :4].cpu().numpy(), [x for x, _, _ in want], rtol=1e-5)
+    assert torch.isinf(d[0, 4:]).all()
+
+
 def test_on_disk_table_and_pickle_roundtrip(libmrag, table, tmp_path):
     import pickle
     from motionrag_b200 import RAGDatabase, save_table

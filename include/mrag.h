@@ -65,7 +65,8 @@ typedef enum mrag_path {
 typedef enum mrag_filter {
   MRAG_FILTER_NONE = 0,
   MRAG_FILTER_POST = 1, /* LanceDB 0.14 default: k nearest first, then drop excluded rows (<= k results) */
-  MRAG_FILTER_PRE = 2   /* drop excluded rows first, then k nearest */
+  MRAG_FILTER_PRE = 2   /* drop excluded rows first, then k nearest; the filter runs on the k + 32 (<= 64)
+                           nearest candidates, so it is exact while no more than 32 of them are excluded */
 } mrag_filter;
 
 typedef struct mrag_store mrag_store; /* opaque: HBM-resident, row-major, immutable between appends */

@@ -155,6 +155,9 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
       // top-`rerank` by scan score, which the exactness certificate (out_margin) relies on
       pl.rerank = refine > 32 ? 32 : refine;
     }
+    // a pre-filter drops candidates AFTER the selection: re-rank k + 32 of them (no certificate is
+    // defined for this mode), so up to 32 excluded rows among the nearest still leave k results
+    if (p->filter_mode == MRAG_FILTER_PRE) pl.rerank = (p->k + 32 > 64) ? 64 : p->k + 32;
     pl.k1_grid = k1_grid(s->n_rows, f32 ? 4 : 2, s->dim, nq < 4 ? nq : 4, s->sm_count);
     pl.cands_per_query = pl.k1_grid * pl.kc;
   } else if (path == MRAG_PATH_TENSOR_BF16) {
@@ -166,6 +169,7 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
     const char* kc_env = getenv("MRAG_K2_KC");
     pl.kc = (p->k <= 12 && p->filter_mode != MRAG_FILTER_PRE && !(kc_env && atoi(kc_env) == 32)) ? 16 : 32;
     pl.rerank = refine > pl.kc ? pl.kc : refine;
+    if (p->filter_mode == MRAG_FILTER_PRE) pl.rerank = (p->k + 32 > 64) ? 64 : p->k + 32;  // see the streaming branch
     // more than one query tile: the CTA-pair kernel (M = 256 per cluster); MRAG_K2_SINGLE=1
     // forces the single-CTA kernel for A/B measurements
     const char* force = getenv("MRAG_K2_SINGLE");

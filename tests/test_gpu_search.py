@@ -468,3 +468,42 @@ def test_searches_on_different_streams_do_not_share_scratch(case):
     for ra, rb in got:
         assert torch.equal(ra.index, want_a.index) and torch.equal(ra.distance, want_a.distance)
         assert torch.equal(rb.index, want_b.index) and torch.equal(rb.distance, want_b.distance)
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_random_configurations_match_oracle(seed):
+    """Seeded random draws over table size, width, batch size, k, scan path, metric and filter mode
+    (ragged against every tile size; small tables, groups that swallow whole result lists)."""
+    from motionrag_b200 import EmbeddingStore
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([1, 7, 40, 255, 256, 257, 1000, 2999]))
+    dim = int(rng.choice([256, 768]))
+    path = str(rng.choice(["stream_f32", "stream_bf16", "tensor_bf16"]))
+    nq = int(rng.integers(1, 5)) if path.startswith("stream") and rng.random() < 0.7 else int(rng.choice([1, 5, 9, 127, 128, 129, 140]))
+    k = int(rng.choice([1, 3, 12, 20, 32]))
+    metric = str(rng.choice(["l2", "l2", "cosine", "dot"]))
+    filt = str(rng.choice(["none", "post", "pre"]))
+    cent = fs.normalise_rows(rng.standard_normal((8, dim)).astype(np.float32))
+    db = fs.normalise_rows(cent[rng.integers(0, 8, n)] + 0.5 / np.sqrt(dim) * rng.standard_normal((n, dim)).astype(np.float32))
+    src = rng.integers(0, n, nq)
+    q = ((db[src] + 0.1 / np.sqrt(dim) * rng.standard_normal((nq, dim))) * rng.uniform(0.5, 20, (nq, 1))).astype(np.float32)
+    # 50: one group can swallow a whole post-filtered top-k. A PRE-filter is exact while the excluded rows
+    # among the re-ranked candidates leave k of them (documented limit), i.e. for video-sized groups.
+    group_size = int(rng.choice([1, 3, 50])) if filt != "pre" else int(rng.choice([1, 3]))
+    groups = (np.arange(n) // group_size).astype(np.int32)
+    excl = groups[src].astype(np.int32)
+    excl[::3] = -1
+    st = EmbeddingStore(dim, n, 0)
+    st.append(db, normalise=False)
+    st.set_groups(groups)
+    ex_d = torch.from_numpy(excl).cuda() if filt != "none" else None
+    res = st.search(torch.from_numpy(q).cuda(), k, metric=metric, path=path, exclude_group=ex_d,
+                    filter_mode=filt if filt != "none" else "post")
+    rd, ri = fs.flat_search(db, q, k, metric, groups if filt != "none" else None, excl if filt != "none" else None,
+                            prefilter=(filt == "pre"))
+    got_i, got_d = res.index.cpu().numpy(), res.distance.cpu().numpy()
+    cfg = dict(n=n, dim=dim, path=path, nq=nq, k=k, metric=metric, filt=filt, group_size=group_size)
+    assert ((got_i >= 0).sum(-1) == (ri >= 0).sum(-1)).all(), cfg       # same number of results per query
+    rep = compare.check_retrieval(got_d, got_i, rd, ri, db, q, metric)
+    assert rep["index_mismatches"] == rep["near_tie_positions"], (cfg, rep)
+    st.close()

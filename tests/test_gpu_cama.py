@@ -235,3 +235,28 @@ print("launches", m.launch_count() - before)
     assert r.returncode == 0, r.stderr[-2000:]
     n = int(r.stdout.strip().split()[-1])
     assert n <= 8, n        # one kernel per forward (plus the capture pass), not 28
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_forward_random_shapes_match_reference_encoder(libmrag, seed):
+    """Seeded random transformer shapes inside the kernels' envelope (head_dim 64, d in {256..1024},
+    d_ff % 512 == 0, <= 704 tokens): same parity bar as the reference configuration."""
+    from motionrag_b200 import CamaTransformer
+    g = torch.Generator().manual_seed(900 + seed)
+    r = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    d = [256, 512, 768, 1024][r(0, 3)]
+    dff = 512 * r(1, 4)
+    layers, G, L, b = r(1, 3), r(1, 12), r(1, 40), r(1, 5)
+    while G * L > 704:
+        L -= 1
+    enc = _encoder(d, d // 64, dff, layers, seed=seed)
+    x = torch.randn(b, G * L, d, generator=g).bfloat16()
+    mask = cc.block_causal_mask(G, L)
+    with torch.no_grad():
+        want = enc(x.float(), mask)
+    cama = CamaTransformer(enc, groups=G, group_tokens=L, max_batch=b, device=0)
+    got = cama.forward(x.cuda()).float().cpu()
+    err = (got - want).abs()
+    cfg = dict(d=d, dff=dff, layers=layers, G=G, L=L, b=b)
+    assert float(err.max()) < 8e-2 and float(err.mean()) < 8e-3, (cfg, float(err.max()), float(err.mean()))
+    cama.close()

@@ -128,3 +128,28 @@ def test_attach_drives_a_cama_style_transformer_from_row_ids(libmrag):
     with torch.no_grad():
         pred2 = model.batch_forward({"ref_features": feats.cuda(), "ref_images": cond.cuda()}, return_loss=False)
     assert torch.equal(pred2, pred)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_gather_random_shapes_match_restatement(libmrag, seed):
+    """Seeded random (b, K, L, C, dtype, pe, cond, share of missing references): bit-exact."""
+    from motionrag_b200 import FeatureTable, MotionContext
+    g = torch.Generator().manual_seed(500 + seed)
+    r = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    b, K, L = r(1, 9), r(1, 12), r(1, 30)
+    C = [64, 128, 384, 1024][r(0, 3)]
+    dt = [torch.bfloat16, torch.float32][r(0, 1)]
+    with_pe, with_cond = bool(r(0, 1)), bool(r(0, 1))
+    n = r(1, 200)
+    table = torch.randn(n, L, C, generator=g).to(dt)
+    idx = torch.randint(0, n, (b, K), generator=g)
+    idx[torch.rand(b, K, generator=g) < 0.25] = -1
+    sos = (torch.randn(1, L, C, generator=g) / 8).to(dt)
+    un = torch.randn(L, C, generator=g).to(dt)
+    cond = torch.randn(b, (K + 1) * L, C, generator=g).to(dt) if with_cond else None
+    ctx = MotionContext(FeatureTable(table.cuda()), sos, un, pe_max_length=(K + 1) * L + 3 if with_pe else None)
+    x = ctx.build(idx.cuda(), cond.cuda() if with_cond else None)
+    want = cc.context_restatement(cc.gather_restatement(table, idx, un), sos,
+                                  cc.sinusoid_table((K + 1) * L + 3, C) if with_pe else None,
+                                  cond.clone() if with_cond else None)
+    assert torch.equal(x.cpu(), want), dict(b=b, K=K, L=L, C=C, dt=dt, pe=with_pe, cond=with_cond, n=n)

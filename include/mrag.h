@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MRAG_ABI_VERSION 2
+#define MRAG_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MRAG_API __attribute__((visibility("default")))
@@ -65,8 +65,8 @@ typedef enum mrag_path {
 typedef enum mrag_filter {
   MRAG_FILTER_NONE = 0,
   MRAG_FILTER_POST = 1, /* LanceDB 0.14 default: k nearest first, then drop excluded rows (<= k results) */
-  MRAG_FILTER_PRE = 2   /* drop excluded rows first, then k nearest; the filter runs on the k + 32 (<= 64)
-                           nearest candidates, so it is exact while no more than 32 of them are excluded */
+  MRAG_FILTER_PRE = 2   /* drop excluded rows first, then k nearest: applied inside the scan kernels (rows of
+                           the excluded group never enter a candidate list), exact for any group size */
 } mrag_filter;
 
 typedef struct mrag_store mrag_store; /* opaque: HBM-resident, row-major, immutable between appends */
@@ -81,10 +81,13 @@ typedef struct mrag_store_info {
   const void* rows_f32_dev;  /* [n_rows, dim] float32, L2-normalised when appended with normalise=1 */
   const void* rows_bf16_dev; /* [n_rows, dim] bfloat16 shadow of the same rows */
   const void* groups_dev;    /* [n_rows] int32 group id per row (video identity) or NULL */
-  float max_norm_deviation;  /* max over non-zero rows of | |row|^2 - 1 | as stored; searches with the
-                                l2 / cosine metric are refused above 1e-3 (the scan ranks by q.d) */
+  float max_norm_deviation;  /* max over non-zero rows of | |row|^2 - 1 | as stored. l2 searches rank by
+                                q.d - |d|^2 / 2 (exact squared-L2 order for ANY rows: the per-row term is added
+                                to the scan score whenever this exceeds fp32 normalisation noise or zero rows
+                                exist); cosine searches are refused above 1e-3 (they rank by q.d) */
   int32_t reserved;
   int64_t zero_rows;         /* all-zero rows (LanceDB on_bad_vectors='fill'); they score q.d = 0 */
+  const void* row_bias_dev;  /* [n_rows] float32: -|row|^2 / 2 of each row as stored */
 } mrag_store_info;
 
 typedef struct mrag_search_params {
@@ -96,14 +99,17 @@ typedef struct mrag_search_params {
   int32_t filter_mode; /* mrag_filter; needs store groups + exclude_group */
   int32_t reserved;
   int64_t index_base;  /* added to local row numbers in out_idx (row-sharded stores) */
-  /* optional output, float[nq] (device memory for mrag_search*, host memory for
-   * mrag_search_host; NULL = not wanted): exactness certificate of the bf16 scan paths.
-   *   margin = (true q.d of the k-th result - bf16 score of the weakest re-ranked candidate) / |q|
-   * Every row that was NOT re-ranked has a bf16 score <= that weakest candidate, and for unit
-   * rows |bf16 score - true q.d| <= eps |q| with eps = 2^-9 (STREAM_BF16: rows rounded) or
-   * 2^-8 (TENSOR_BF16: rows and queries rounded). Hence margin > eps proves the returned
-   * top-k is the exact fp32 top-k; otherwise re-issue that query with MRAG_PATH_STREAM_F32.
-   * +inf when everything was re-ranked; NaN for MRAG_FILTER_PRE and for sharded searches. */
+  /* optional output, float[nq] (device memory for mrag_search*, host memory for the *_host
+   * variants; NULL = not wanted): exactness certificate of the bf16 scan paths.
+   *   margin = (exact ranking score of the k-th result - scan score of the weakest re-ranked candidate) / |q|
+   * (ranking score = q.d, plus -|d|^2/2 for l2 on rows that are not unit-norm). Every row that was
+   * NOT re-ranked has a scan score <= that weakest candidate, and |scan score - exact score| <=
+   * eps |q| |d| with eps = 2^-9 (STREAM_BF16: rows rounded) or 2^-8 (TENSOR_BF16: rows and queries
+   * rounded). Hence margin > eps * max|d| proves the returned top-k is the exact fp32 top-k;
+   * otherwise re-issue that query with MRAG_PATH_STREAM_F32. +inf when every (eligible) row was
+   * re-ranked. Row-sharded searches report the margin of the GLOBAL result: the k-th result after
+   * the cross-GPU merge against the weakest re-ranked candidate of ANY shard (both travel in the
+   * exchange records). NaN only for a query whose peer exchange timed out. */
   float* out_margin;
 } mrag_search_params;
 
@@ -133,6 +139,8 @@ typedef struct mrag_plan_info {
   int64_t scan_bytes;      /* algorithmic bytes streamed by the scan kernel: n_rows*dim*elt */
   int64_t scan_flops;      /* algorithmic flops: 2*nq*n_rows*dim */
   size_t workspace_bytes;
+  int32_t fused_tail;      /* 1: single-query streaming scan whose last CTA runs the K3 body (one launch) */
+  int32_t row_bias;        /* 1: the per-row l2 term is added to the scan scores (rows not unit-norm) */
 } mrag_plan_info;
 /* validates (store, nq, params) and reports how the call would run, including the workspace
  * the caller must provide to mrag_search */
@@ -148,15 +156,20 @@ MRAG_API int mrag_search(const mrag_store* s, const float* queries_dev, int32_t 
 /* ---- row-sharded search with the cross-GPU merge fused into the last kernel -----------------
  * One process per GPU; every rank holds a contiguous row range (params.index_base = its first
  * global row) and an exchange buffer of mrag_exchange_bytes() zero-initialised bytes that all
- * peers have mapped (mrag_ipc_export/open). Each K3 block stores its shard's top-k straight into
- * every rank's buffer over NVLink, raises per-query flags and merges world*k candidates as
- * soon as the peers' flags arrive — no collective call and no extra launch. All ranks must
- * issue the same sequence of calls (same nq, k) with the same epoch = 1, 2, 3, ... */
+ * peers have mapped (mrag_ipc_export/open). The last kernel of the search (the K3 block of a query,
+ * or the last CTA of the single-query scan) stores its shard's top-k straight into every rank's
+ * buffer over NVLink, raises per-query flags and merges world*k candidates as soon as the peers'
+ * flags arrive — no collective call. Batches of more than 128 queries publish in K3 and wait +
+ * merge in a second small kernel, so that progress never depends on the order in which the
+ * hardware dispatches blocks. The flag wait is bounded (timeout_ms): a dead or desynchronised peer
+ * yields empty results for the affected queries and an error readable with mrag_store_poll_error,
+ * never a hung GPU. All ranks must issue the same sequence of calls (same nq, k) with the same
+ * epoch = 1, 2, 3, ...; a rank whose shard is empty still takes part (it publishes no rows). */
 typedef struct mrag_exchange {
   int32_t world, rank;     /* world <= 8 */
   int32_t nq_cap, k_cap;   /* capacity the buffers were sized for (k_cap <= 32) */
   uint32_t epoch;          /* call counter, identical on all ranks, starts at 1 */
-  int32_t reserved;
+  int32_t timeout_ms;      /* bound of the flag wait; 0 = default (10 s, env MRAG_XCHG_TIMEOUT_MS) */
   void* const* bufs_dev;   /* device array [world]: exchange-buffer base of every rank */
 } mrag_exchange;
 MRAG_API size_t mrag_exchange_bytes(int32_t world, int32_t nq_cap, int32_t k_cap);
@@ -165,6 +178,11 @@ MRAG_API int mrag_search_sharded(const mrag_store* s, const float* queries_dev, 
                 float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,
                 void* workspace_dev, size_t workspace_bytes, const mrag_exchange* xchg,
                 void* stream);
+
+/* device-side error word of the store (set by a peer exchange that timed out): *code_out = the
+ * word (0 = none), which is cleared; returns MRAG_ERR_CUDA with a message when it was set. Only
+ * meaningful once the stream the search ran on has been synchronised. */
+MRAG_API int mrag_store_poll_error(const mrag_store* s, int32_t* code_out);
 
 /* mrag_search bracketed by CUDA events on `stream`: *scan_ms_out = duration of the scan kernel
  * alone (K1 or K2), *total_ms_out = the whole call on the device. Synchronises the stream.
@@ -181,6 +199,13 @@ MRAG_API int mrag_search_host(const mrag_store* s, const float* queries_host, in
                      const mrag_search_params* p, const int32_t* exclude_group_host,
                      float* out_dist_host, int64_t* out_idx_host, int32_t* out_group_host,
                      void* stream);
+
+/* the row-sharded search with HOST buffers (small calls replay a captured CUDA graph whose last kernel
+ * contains the peer exchange; the epoch travels with the queries) */
+MRAG_API int mrag_search_sharded_host(const mrag_store* s, const float* queries_host, int32_t nq,
+                     const mrag_search_params* p, const int32_t* exclude_group_host,
+                     float* out_dist_host, int64_t* out_idx_host, int32_t* out_group_host,
+                     const mrag_exchange* xchg, void* stream);
 
 /* ---- second stage of RAGDatabase.text_image_search (src/data/rag.py:118-128): the reference puts
  *      the text hits into a temporary table and runs the image search inside it. Here: exact
@@ -208,7 +233,9 @@ MRAG_API int mrag_merge_topk(const float* cand_dist_dev, const int64_t* cand_idx
  *      (src/data/dataset.py:285-312, src/projects/condition/module.py:264-268, 298-301) ------
  * shard_ptrs_dev: device array of nshards pointers to [rows_per_shard, L, C] feature blocks
  *                 (local or peer-mapped); global row r lives in shard r / rows_per_shard.
- * ref_idx_dev [b, K] int64 in similarity order (0 = most similar), -1 = missing/dropped.
+ * ref_idx_dev [b, K] int64 in similarity order (0 = most similar), -1 = missing/dropped; an index
+ *                 >= n_rows_total (the rows the table really has) also selects the uncond row and is
+ *                 never dereferenced.
  * out [b, (K+1)*L, C]; group 0 = sos, group g>=1 = feature of reference rank K-g.
  * dtype: 0 = bfloat16, 1 = float32 (all feature-like tensors share it).
  * pe_dev [(K+1)*L, C] and cond_dev [b, (K+1)*L, C] may be NULL; when given the adds happen in
@@ -217,7 +244,7 @@ MRAG_API int mrag_gather_context(const void* const* shard_ptrs_dev, int32_t nsha
                         int64_t rows_per_shard, const int64_t* ref_idx_dev, const void* sos_dev,
                         const void* uncond_row_dev, const void* pe_dev, const void* cond_dev,
                         void* out_dev, int32_t b, int32_t K, int32_t L, int32_t C, int32_t dtype,
-                        void* stream);
+                        int64_t n_rows_total, void* stream);
 
 /* ---- CAMA causal motion transformer forward (consumer of the gathered context) ----
  * torch.nn.TransformerEncoder(num_layers, TransformerEncoderLayer(d_model, nhead, dim_feedforward,

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "libmrag.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums of include/mrag.h
 METRIC = {"l2": 0, "cosine": 1, "dot": 2}
@@ -33,7 +33,7 @@ class StoreInfo(C.Structure):
                 ("capacity_rows", C.c_int64), ("has_groups", C.c_int32), ("sm_count", C.c_int32),
                 ("rows_f32_dev", C.c_void_p), ("rows_bf16_dev", C.c_void_p),
                 ("groups_dev", C.c_void_p), ("max_norm_deviation", C.c_float), ("reserved", C.c_int32),
-                ("zero_rows", C.c_int64)]
+                ("zero_rows", C.c_int64), ("row_bias_dev", C.c_void_p)]
 
 
 class SearchParams(C.Structure):
@@ -46,12 +46,13 @@ class PlanInfo(C.Structure):
     _fields_ = [("path", C.c_int32), ("grid", C.c_int32), ("cands_per_query", C.c_int32),
                 ("rerank", C.c_int32), ("m_tiles", C.c_int32), ("n_tiles", C.c_int32),
                 ("chunks", C.c_int32), ("tiles_per_chunk", C.c_int32), ("scan_bytes", C.c_int64),
-                ("scan_flops", C.c_int64), ("workspace_bytes", C.c_size_t)]
+                ("scan_flops", C.c_int64), ("workspace_bytes", C.c_size_t), ("fused_tail", C.c_int32),
+                ("row_bias", C.c_int32)]
 
 
 class Exchange(C.Structure):
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("nq_cap", C.c_int32), ("k_cap", C.c_int32),
-                ("epoch", C.c_uint32), ("reserved", C.c_int32), ("bufs_dev", C.c_void_p)]
+                ("epoch", C.c_uint32), ("timeout_ms", C.c_int32), ("bufs_dev", C.c_void_p)]
 
 
 class CamaLayer(C.Structure):
@@ -69,6 +70,7 @@ SIGNATURES = {
     "mrag_store_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "mrag_store_set_groups": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "mrag_store_get_info": (C.c_int, [C.c_void_p, C.POINTER(StoreInfo)]),
+    "mrag_store_poll_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "mrag_search_plan": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.POINTER(PlanInfo)]),
     "mrag_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -81,6 +83,8 @@ SIGNATURES = {
                                     C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "mrag_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mrag_search_sharded_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SearchParams), C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Exchange), C.c_void_p]),
     "mrag_rescore_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "mrag_merge_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
@@ -88,7 +92,7 @@ SIGNATURES = {
                                   C.c_void_p]),
     "mrag_gather_context": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
-                                      C.c_int32, C.c_int32, C.c_void_p]),
+                                      C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
     "mrag_cama_create": (C.c_int, [C.c_int32, C.POINTER(CamaLayer), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "mrag_cama_destroy": (C.c_int, [C.c_void_p]),

@@ -46,16 +46,21 @@ def _ptr(t: torch.Tensor | None):
 
 def gather_context(table: FeatureTable, ref_index: torch.Tensor, sos: torch.Tensor,
                    uncond_row: torch.Tensor, pos_table: torch.Tensor | None = None,
-                   cond: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+                   cond: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                   validate: bool = False) -> torch.Tensor:
     """ref_index [b, K] int64 (similarity order, 0 = most similar, -1 = dropped/missing) ->
     x [b, (K+1)*L, C] in the table's dtype. sos [L, C] / [1, L, C]; uncond_row [L, C];
     pos_table [>= (K+1)*L, C] already in the table's dtype (the reference casts its fp32 table
-    with .type_as(x) before adding); cond [b, (K+1)*L, C]."""
+    with .type_as(x) before adding); cond [b, (K+1)*L, C]. An index >= table.n_rows is never
+    dereferenced (the kernel substitutes the uncond row); validate=True raises for one instead
+    (costs a device synchronisation)."""
     lib = _cabi.load()
     dev, dt = table.device, table.local.dtype
     if ref_index.device != dev or ref_index.dtype != torch.int64 or ref_index.ndim != 2:
         raise ValueError("ref_index must be an int64 [b, K] tensor on the table's device")
     ref_index = ref_index.contiguous()
+    if validate and ref_index.numel() and int(ref_index.max()) >= table.n_rows:
+        raise IndexError(f"ref_index holds row {int(ref_index.max())} but the feature table has {table.n_rows} rows")
     b, K = ref_index.shape
     L, Cd = table.L, table.Cdim
     n_tok = (K + 1) * L
@@ -86,7 +91,7 @@ def gather_context(table: FeatureTable, ref_index: torch.Tensor, sos: torch.Tens
     check(lib.mrag_gather_context(
         _ptr(table.shard_ptrs), table.n_shards, table.rows_per_shard, _ptr(ref_index), _ptr(sos),
         _ptr(uncond_row), _ptr(pos_table), _ptr(cond), _ptr(out), b, K, L, Cd,
-        0 if dt == torch.bfloat16 else 1, _stream_ptr(dev)))
+        0 if dt == torch.bfloat16 else 1, table.n_rows, _stream_ptr(dev)))
     return out
 
 

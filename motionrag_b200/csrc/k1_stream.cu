@@ -5,13 +5,14 @@
 // coalesced, L1-bypassing loads; one warp owns a row at a time (lane l holds the 16-byte
 // slices l, l+32, ...), dots are finished with a 5-step xor-shuffle, and each warp keeps a
 // running top-KC in registers (lane i = slot i) guarded by a warp-uniform threshold so the
-// score vector never leaves the SM. Per-CTA lists are merged with a shared-memory bitonic
-// sort and written as u64 keys (score descending, index ascending); K3 finishes the job.
+// score vector never leaves the SM. Per-CTA lists are merged (warp shuffle sort + binary-search
+// ranks) and written as u64 keys (score descending, index ascending). For a single query the last
+// CTA to finish then runs the K3 body itself (select, fp32 re-score, filter, cross-GPU exchange),
+// so the whole search is one launch; otherwise K3 follows as its own kernel.
 //
 // Algorithmic bytes: n_rows * dim * sizeof(T) per launch (T = float or bf16).
-#include <cstdlib>
-
 #include "common.cuh"
+#include "k3_body.cuh"
 #include "kernels.h"
 
 namespace mrag {
@@ -58,10 +59,35 @@ __device__ __forceinline__ bool worse(float sa, int ia, int la, float sb, int ib
   return la > lb;
 }
 
+// ascending bitonic sort of one u64 key per lane across the warp (registers + shuffles only)
+__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t key, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool up = (lane & k) == 0;     // this k-block sorts ascending
+      const bool lower = (lane & j) == 0;  // this lane keeps the smaller of the pair when ascending
+      const uint64_t lo = key < other ? key : other;
+      const uint64_t hi = key < other ? other : key;
+      key = (lower == up) ? lo : hi;
+    }
+  }
+  return key;
+}
+
+// shared memory of the fused tail exists only in the single-query instantiations
+template <int Q>
+struct K1TailSmem {};
+template <>
+struct K1TailSmem<1> {
+  K3Smem k3;
+};
+
 template <typename T, int D, int Q, int R, int MINB>
 __global__ void __launch_bounds__(kK1Threads, MINB)
     k1_stream_kernel(const T* __restrict__ db, int64_t n_rows, const float* __restrict__ queries,
-                     uint64_t* __restrict__ cand, int kc, int64_t rows_per_cta) {
+                     uint64_t* __restrict__ cand, int kc, int64_t rows_per_cta, const K1Extra ex) {
   constexpr int EPV = Elt<T>::kPerVec;        // elements per 16-byte vector
   constexpr int STEPS = D / (32 * EPV);       // vectors per lane per row
   constexpr int QV = (EPV == 4) ? 1 : 2;      // float4 query slices per database vector
@@ -69,12 +95,39 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
 
   // queries staged so that lane l's float4 slices are contiguous across lanes (conflict-free)
   __shared__ __align__(16) float q_s[Q * D];
-  __shared__ uint64_t merge_keys[kK1Threads];
+  __shared__ uint64_t merge_keys[kK1Threads];  // 8 sorted runs of 32 keys (one per warp)
+  __shared__ K1TailSmem<Q> tail;
+  __shared__ int is_last_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // programmatic dependent launch: let the (1-4 block) K3 grid become resident now; it parks
   // in griddepcontrol.wait until this grid has completed and its candidate keys are visible
   asm volatile("griddepcontrol.launch_dependents;");
+
+  const int64_t row0 = int64_t(blockIdx.x) * rows_per_cta;
+  const int64_t row1 = min(n_rows, row0 + rows_per_cta);
+  const uint4* __restrict__ dbv = reinterpret_cast<const uint4*>(db);
+  constexpr int VPR = D / EPV;  // vectors per row
+  const float* __restrict__ bias = ex.row_bias;
+
+  uint4 v[R][STEPS];
+  float bz[R];
+  // all loads of one step (R rows) are issued before any math: R * STEPS 128-bit loads in flight
+  auto load_rows = [&](int64_t base) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = min(base + r, n_rows - 1);  // clamp: tail rows are masked below
+      const uint4* p = dbv + row * VPR + lane;
+#pragma unroll
+      for (int j = 0; j < STEPS; ++j) v[r][j] = ld_stream_v4(p + j * 32);
+      bz[r] = (bias != nullptr) ? __ldg(bias + row) : 0.f;
+    }
+  };
+  int64_t base = row0 + int64_t(warp) * R;
+  // the first rows are requested before the queries are staged: the HBM latency of the first
+  // step overlaps the staging (matters for small shards, where a CTA runs only a few steps)
+  if (base < row1) load_rows(base);
+
   for (int e = tid; e < Q * D; e += kK1Threads) {
     int q = e / D, d = e % D;
     int vec = d / EPV, c = d % EPV;           // vec = step*32 + lane
@@ -83,6 +136,12 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
     int pos = ((step * QV + half) * 32 + ln) * 4 + cc;
     q_s[q * D + pos] = queries[e];
   }
+  // pre-filter (`video != own` applied BEFORE the top-k): rows of the excluded group never enter
+  // the lists, so they hold the best eligible rows whatever the size of the group
+  int excl[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+    excl[q] = (ex.row_group != nullptr && ex.exclude_group != nullptr) ? ex.exclude_group[q] : -1;
   __syncthreads();
 
   // warp-distributed running top-kc per query: lane i holds slot i
@@ -98,20 +157,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
     minlane[q] = kc - 1;
   }
 
-  const int64_t row0 = int64_t(blockIdx.x) * rows_per_cta;
-  const int64_t row1 = min(n_rows, row0 + rows_per_cta);
-  const uint4* __restrict__ dbv = reinterpret_cast<const uint4*>(db);
-  constexpr int VPR = D / EPV;  // vectors per row
-
-  for (int64_t base = row0 + int64_t(warp) * R; base < row1; base += int64_t(kK1Warps) * R) {
-    uint4 v[R][STEPS];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int64_t row = min(base + r, n_rows - 1);  // clamp: tail rows are masked below
-      const uint4* p = dbv + row * VPR + lane;
-#pragma unroll
-      for (int j = 0; j < STEPS; ++j) v[r][j] = ld_stream_v4(p + j * 32);
-    }
+  while (base < row1) {
     float acc[R][Q];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -134,6 +180,13 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
         }
       }
     }
+    float bcur[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) bcur[r] = bz[r];
+    const int64_t cur = base;
+    base += int64_t(kK1Warps) * R;
+    if (base < row1) load_rows(base);  // next step's loads fly while this step is reduced / inserted
+
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -141,18 +194,19 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
         float a = acc[r][q];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-        acc[r][q] = a;
+        acc[r][q] = a + bcur[r];
       }
 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int64_t row = base + r;
+      const int64_t row = cur + r;
       if (row < row1) {  // warp-uniform
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const float s = acc[r][q];
           // rows arrive in ascending order inside a warp, so an equal score never displaces
           if (s > thr[q]) {  // warp-uniform
+            if (excl[q] >= 0 && __ldg(ex.row_group + row) == excl[q]) continue;  // pre-filtered row
             if (lane == minlane[q]) {
               ls[q] = s;
               li[q] = int(row);
@@ -178,85 +232,100 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
     }
   }
 
-  // CTA merge: 8 warps x 32 slots -> sorted, keep the best kc
+  // CTA merge: every warp sorts its 32 slots with shuffles, then each key finds its rank among the
+  // 8 sorted runs by binary search (one barrier per query instead of a 36-round sorting network)
 #pragma unroll 1
   for (int q = 0; q < Q; ++q) {
+    const uint64_t mine = warp_sort_u64((lane < kc) ? make_sim_key(ls[q], li[q]) : kEmptyKey, lane);
+    __syncthreads();  // previous query's readers are done
+    merge_keys[tid] = mine;
     __syncthreads();
-    merge_keys[tid] = (lane < kc) ? make_sim_key(ls[q], li[q]) : kEmptyKey;
-    bitonic_sort_smem(merge_keys, kK1Threads, tid, kK1Threads);
-    if (tid < kc) cand[(int64_t(q) * gridDim.x + blockIdx.x) * kc + tid] = merge_keys[tid];
+    int rank = lane;
+#pragma unroll
+    for (int w = 0; w < kK1Warps; ++w) {
+      if (w == warp) continue;
+      const uint64_t* run = merge_keys + w * 32;
+      // keys are unique except the empty key: earlier warps win ties, so ranks stay distinct
+      int c = 0;
+      if (w < warp) {
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1)
+          if (run[c + st - 1] <= mine) c += st;
+        if (run[c] <= mine) c += 1;
+      } else {
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1)
+          if (run[c + st - 1] < mine) c += st;
+        if (run[c] < mine) c += 1;
+      }
+      rank += c;
+    }
+    if (rank < kc) cand[(int64_t(q) * gridDim.x + blockIdx.x) * kc + rank] = mine;
+  }
+
+  // fused tail (single query): the last CTA to finish selects, re-scores in fp32, filters and emits
+  // (and runs the cross-GPU exchange of a row-sharded store) — the whole search is ONE launch
+  if constexpr (Q == 1) {
+    if (ex.ticket != nullptr) {
+      __threadfence();  // this CTA's candidate keys are visible device-wide before the ticket
+      __syncthreads();
+      if (tid == 0) is_last_s = (atomicAdd(ex.ticket, 1) == int(gridDim.x) - 1) ? 1 : 0;
+      __syncthreads();
+      if (is_last_s) {
+        __threadfence();
+        k3_body<kK1Threads>(ex.k3, 0, tail.k3);
+        if (tid == 0) *ex.ticket = 0;  // re-armed for the next call / graph replay
+      }
+    }
   }
 }
 
 // ---- host side ------------------------------------------------------------------------------
-// (rows in flight per warp, resident CTAs per SM). Variant 0 is the shipped configuration;
-// MRAG_K1_VARIANT selects the others for tuning runs.
-struct K1Variant {
-  int r, minb;
-};
-static const K1Variant kVariantsF32[] = {{2, 2}, {4, 2}, {2, 3}, {2, 4}, {1, 4}, {3, 2}};
-static const K1Variant kVariantsBF16[] = {{6, 2}, {8, 2}, {4, 2}, {4, 4}, {2, 4}, {4, 3}};
-
-static int k1_variant_index() {
-  const char* e = getenv("MRAG_K1_VARIANT");
-  int v = e ? atoi(e) : 0;
-  return (v < 0 || v > 5) ? 0 : v;
-}
-static K1Variant k1_variant(int elt_bytes) {
-  return elt_bytes == 4 ? kVariantsF32[k1_variant_index()] : kVariantsBF16[k1_variant_index()];
-}
-
+// (rows in flight per warp, resident CTAs per SM), measured on B200 (profiles/r1_k1_*): fp32 (2, 2);
+// bf16 768-d single query (6, 2); other bf16 shapes 4 rows, 3 CTAs unless 3-4 queries or 1024-d rows
+// (4 rows in flight per warp do not fit 80 registers without spilling there)
 template <typename T, int D, int Q, int R, int MINB>
 static cudaError_t launch_cfg(const void* db, int64_t n_rows, const float* queries, uint64_t* cand,
-                              int kc, int grid, cudaStream_t st) {
+                              int kc, int grid, const K1Extra& ex, cudaStream_t st) {
   const int64_t quantum = int64_t(kK1Warps) * R;
   int64_t rows_per_cta = (n_rows + grid - 1) / grid;
   rows_per_cta = (rows_per_cta + quantum - 1) / quantum * quantum;
+  K1Extra e = ex;
+  if (Q != 1) e.ticket = nullptr;
   k1_stream_kernel<T, D, Q, R, MINB><<<grid, kK1Threads, 0, st>>>(
-      static_cast<const T*>(db), n_rows, queries, cand, kc, rows_per_cta);
+      static_cast<const T*>(db), n_rows, queries, cand, kc, rows_per_cta, e);
   note_launch();
   return cudaGetLastError();
 }
 
 template <typename T, int D, int Q>
 static cudaError_t launch_one(const void* db, int64_t n_rows, const float* queries, uint64_t* cand,
-                              int kc, int grid, cudaStream_t st) {
+                              int kc, int grid, const K1Extra& ex, cudaStream_t st) {
   constexpr bool F = sizeof(T) == 4;
-  if constexpr (D == 768 && Q == 1) {  // tuning variants exist for the headline shape only
-    switch (k1_variant_index()) {
-      case 1: return launch_cfg<T, D, Q, F ? 4 : 8, 2>(db, n_rows, queries, cand, kc, grid, st);
-      case 2: return launch_cfg<T, D, Q, F ? 2 : 4, F ? 3 : 2>(db, n_rows, queries, cand, kc, grid, st);
-      case 3: return launch_cfg<T, D, Q, F ? 2 : 4, 4>(db, n_rows, queries, cand, kc, grid, st);
-      case 4: return launch_cfg<T, D, Q, F ? 1 : 2, 4>(db, n_rows, queries, cand, kc, grid, st);
-      case 5: return launch_cfg<T, D, Q, F ? 3 : 4, F ? 2 : 3>(db, n_rows, queries, cand, kc, grid, st);
-      default: break;
-    }
-  }
-  if constexpr (D == 768 && Q == 1) return launch_cfg<T, D, Q, F ? 2 : 6, 2>(db, n_rows, queries, cand, kc, grid, st);
-  // bf16 with 3-4 queries or 1024-d rows: 4 rows in flight per warp do not fit 80 registers without spilling
-  return launch_cfg<T, D, Q, F ? 2 : 4, (F || Q >= 3 || D >= 1024) ? 2 : 3>(db, n_rows, queries, cand, kc, grid, st);
+  if constexpr (D == 768 && Q == 1) return launch_cfg<T, D, Q, F ? 2 : 6, 2>(db, n_rows, queries, cand, kc, grid, ex, st);
+  return launch_cfg<T, D, Q, F ? 2 : 4, (F || Q >= 3 || D >= 1024) ? 2 : 3>(db, n_rows, queries, cand, kc, grid, ex, st);
 }
 
 template <typename T, int D>
 static cudaError_t launch_q(const void* db, int64_t n_rows, const float* queries, int nq,
-                            uint64_t* cand, int kc, int grid, cudaStream_t st) {
+                            uint64_t* cand, int kc, int grid, const K1Extra& ex, cudaStream_t st) {
   switch (nq) {
-    case 1: return launch_one<T, D, 1>(db, n_rows, queries, cand, kc, grid, st);
-    case 2: return launch_one<T, D, 2>(db, n_rows, queries, cand, kc, grid, st);
-    case 3: return launch_one<T, D, 3>(db, n_rows, queries, cand, kc, grid, st);
-    case 4: return launch_one<T, D, 4>(db, n_rows, queries, cand, kc, grid, st);
+    case 1: return launch_one<T, D, 1>(db, n_rows, queries, cand, kc, grid, ex, st);
+    case 2: return launch_one<T, D, 2>(db, n_rows, queries, cand, kc, grid, ex, st);
+    case 3: return launch_one<T, D, 3>(db, n_rows, queries, cand, kc, grid, ex, st);
+    case 4: return launch_one<T, D, 4>(db, n_rows, queries, cand, kc, grid, ex, st);
     default: return cudaErrorInvalidValue;
   }
 }
 
 template <typename T>
 static cudaError_t launch_d(const void* db, int64_t n_rows, int dim, const float* queries, int nq,
-                            uint64_t* cand, int kc, int grid, cudaStream_t st) {
+                            uint64_t* cand, int kc, int grid, const K1Extra& ex, cudaStream_t st) {
   switch (dim) {
-    case 256: return launch_q<T, 256>(db, n_rows, queries, nq, cand, kc, grid, st);
-    case 512: return launch_q<T, 512>(db, n_rows, queries, nq, cand, kc, grid, st);
-    case 768: return launch_q<T, 768>(db, n_rows, queries, nq, cand, kc, grid, st);
-    case 1024: return launch_q<T, 1024>(db, n_rows, queries, nq, cand, kc, grid, st);
+    case 256: return launch_q<T, 256>(db, n_rows, queries, nq, cand, kc, grid, ex, st);
+    case 512: return launch_q<T, 512>(db, n_rows, queries, nq, cand, kc, grid, ex, st);
+    case 768: return launch_q<T, 768>(db, n_rows, queries, nq, cand, kc, grid, ex, st);
+    case 1024: return launch_q<T, 1024>(db, n_rows, queries, nq, cand, kc, grid, ex, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -266,21 +335,20 @@ bool k1_supported(int dim, int nq) {
 }
 
 int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count) {
-  // the headline shape (768-d, one query) has tuned variants; other shapes use (2,2) / (4,3 or 2)
-  K1Variant v = (dim == 768 && nq == 1) ? k1_variant(elt_bytes)
-                                        : (elt_bytes == 4 ? K1Variant{2, 2} : K1Variant{4, (nq >= 3 || dim >= 1024) ? 2 : 3});
-  const int64_t quantum = int64_t(kK1Warps) * v.r;
+  const int r = elt_bytes == 4 ? 2 : ((dim == 768 && nq == 1) ? 6 : 4);
+  const int minb = (dim == 768 && nq == 1) ? 2 : ((elt_bytes == 4 || nq >= 3 || dim >= 1024) ? 2 : 3);
+  const int64_t quantum = int64_t(kK1Warps) * r;
   // one resident wave; small tables get fewer CTAs
   int64_t want = (n_rows + quantum - 1) / quantum;
-  int64_t cap = int64_t(sm_count) * v.minb;
+  int64_t cap = int64_t(sm_count) * minb;
   return int(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
 cudaError_t launch_k1_stream(const void* db, int elt_bytes, int64_t n_rows, int dim,
                              const float* queries, int nq, uint64_t* cand, int kc, int grid,
-                             cudaStream_t st) {
-  if (elt_bytes == 4) return launch_d<float>(db, n_rows, dim, queries, nq, cand, kc, grid, st);
-  return launch_d<__nv_bfloat16>(db, n_rows, dim, queries, nq, cand, kc, grid, st);
+                             const K1Extra& ex, cudaStream_t st) {
+  if (elt_bytes == 4) return launch_d<float>(db, n_rows, dim, queries, nq, cand, kc, grid, ex, st);
+  return launch_d<__nv_bfloat16>(db, n_rows, dim, queries, nq, cand, kc, grid, ex, st);
 }
 
 }  // namespace mrag

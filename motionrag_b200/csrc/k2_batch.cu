@@ -36,7 +36,7 @@ struct K2Smem {
   static constexpr uint32_t kTotal = kBars + 256;
 };
 
-template <int SETS, int KC>
+template <int SETS, int KC, bool EXTRA>
 __global__ void __launch_bounds__(k2_threads(SETS), 1)
     k2_batch_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                     const K2Args a) {
@@ -154,6 +154,12 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
       top.reset();
       const bool live = q_row < a.nq;  // padding rows of the last query tile keep no state
       uint32_t* gthr_q = a.gthr + (live ? q_row : 0);
+      EpiExtra xe{nullptr, nullptr, -1};
+      if constexpr (EXTRA) {
+        xe.bias = a.ex.row_bias;
+        xe.groups = a.ex.row_group;
+        if (live && a.ex.row_group != nullptr && a.ex.exclude_group != nullptr) xe.excl = a.ex.exclude_group[q_row];
+      }
       for (int t = t0; t < t1; ++t, ++n) {
         const int acc = int(n & 1u);
         if (SETS == 2 && acc != set) continue;
@@ -162,7 +168,7 @@ __global__ void __launch_bounds__(k2_threads(SETS), 1)
         tc_fence_after();
         const long long t_busy = clk();
         const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc) * kBN;
-        epilogue_tile<SETS == 1, KC>(top, t_addr, int64_t(t) * kBN, a.n_rows, stg, lane, a.debug);
+        epilogue_tile<SETS == 1, KC, EXTRA>(top, t_addr, int64_t(t) * kBN, a.n_rows, stg, lane, a.debug, xe);
         if (live) top.publish(gthr_q);
         tc_fence_before();
         __syncwarp();
@@ -213,7 +219,7 @@ K2Plan k2_plan(int64_t n_rows, int nq, int sm_count) {
 
 cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* db_bf16,
                             int64_t db_rows_padded, int64_t n_rows, int dim, int nq,
-                            const K2Plan& plan, uint64_t* cand, uint32_t* gthr,
+                            const K2Plan& plan, uint64_t* cand, uint32_t* gthr, const K2Extra& ex,
                             cudaStream_t st) {
   CUtensorMap tm_q, tm_db;
   if (!make_tmap(&tm_q, q_bf16, q_rows_padded, dim, kBM) ||
@@ -226,6 +232,8 @@ cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* d
   k2_fill_args(a, plan);
   a.cand = cand;
   a.gthr = gthr;
+  a.ex = ex;
+  const bool extra = ex.row_bias != nullptr || (ex.row_group != nullptr && ex.exclude_group != nullptr);
   a.debug = k2_debug_mode();
   a.stats = k2_stats_alloc(plan.grid);
   const size_t smem = K2Smem::kTotal + 1024;
@@ -234,10 +242,8 @@ cudaError_t launch_k2_batch(const void* q_bf16, int q_rows_padded, const void* d
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e == cudaSuccess) kern<<<plan.grid, threads, smem, st>>>(tm_q, tm_db, a);
   };
-  if (plan.epi_sets == 2 && plan.kc == 16) go(k2_batch_kernel<2, 16>, k2_threads(2));
-  else if (plan.epi_sets == 2) go(k2_batch_kernel<2, 32>, k2_threads(2));
-  else if (plan.kc == 16) go(k2_batch_kernel<1, 16>, k2_threads(1));
-  else go(k2_batch_kernel<1, 32>, k2_threads(1));
+  if (plan.kc == 16) extra ? go(k2_batch_kernel<1, 16, true>, k2_threads(1)) : go(k2_batch_kernel<1, 16, false>, k2_threads(1));
+  else extra ? go(k2_batch_kernel<1, 32, true>, k2_threads(1)) : go(k2_batch_kernel<1, 32, false>, k2_threads(1));
   if (e != cudaSuccess) return e;
   note_launch();
   cudaError_t le = cudaGetLastError();

@@ -41,6 +41,7 @@ struct K2Args {
   // numbers are from the first epilogue warp)
   unsigned long long* stats;
   int debug;  // profiling only (MRAG_K2_DEBUG): 1 = epilogue skips TMEM reads, 2 = reads but never inserts
+  K2Extra ex;  // row bias / pre-filter (kernels instantiated with EXTRA only)
 };
 
 // Work assignment. "Fixed" units keep ONE query group for their whole life and walk a contiguous
@@ -195,14 +196,38 @@ struct TopList {
 // Fast path: one max-tree + one compare rejects the whole group (the common case once the
 // threshold is warm). Slow path, only for lanes that have a candidate: park the scores in this
 // warp's scratch (column-major per lane, conflict-free) and walk the hit mask.
-template <int KC>
+// EXTRA: a per-row bias (uniform 128-bit loads: every lane reads the same 32 floats) is added to
+// the scores before selection, and rows of the query's excluded group (`excl` >= 0) are dropped on
+// the insertion path (pre-filter) — both off the fast reject path's critical dependencies.
+struct EpiExtra {
+  const float* bias;
+  const int32_t* groups;
+  int excl;
+};
+template <int KC, bool EXTRA>
 __device__ __forceinline__ void process_group(TopList<KC>& top, const uint32_t (&v)[32], int col0,
-                                              bool ragged, int64_t n_rows, float* stg, int lane) {
+                                              bool ragged, int64_t n_rows, float* stg, int lane,
+                                              const EpiExtra& xe) {
   float f[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    f[j] = __uint_as_float(v[j]);
-    if (ragged && int64_t(col0) + j >= n_rows) f[j] = -INFINITY;  // rows past the table
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if constexpr (EXTRA) {
+    if (xe.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(xe.bias + col0);  // col0 % 32 == 0
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        f[4 * j + 0] += b.x;
+        f[4 * j + 1] += b.y;
+        f[4 * j + 2] += b.z;
+        f[4 * j + 3] += b.w;
+      }
+    }
+  }
+  if (ragged) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (int64_t(col0) + j >= n_rows) f[j] = -INFINITY;  // rows past the table
   }
   float m[16];
 #pragma unroll
@@ -222,6 +247,9 @@ __device__ __forceinline__ void process_group(TopList<KC>& top, const uint32_t (
       const int j = __ffs(hits) - 1;
       hits &= hits - 1;
       const float cv = stg[j * 32 + lane];
+      if constexpr (EXTRA) {
+        if (xe.excl >= 0 && __ldg(xe.groups + col0 + j) == xe.excl) continue;  // pre-filtered row
+      }
       if (cv > top.thr) top.insert(cv, col0 + j);
     }
   }
@@ -230,9 +258,10 @@ __device__ __forceinline__ void process_group(TopList<KC>& top, const uint32_t (
 // One 128 x 256 accumulator tile: this warp's 32 query rows (TMEM lanes) x 256 columns, read
 // 32 columns at a time with the next tcgen05.ld in flight while the current group is scanned;
 // thread = query row. `stg` is this warp's private [32][32] float scratch.
-template <bool DOUBLE_BUFFER, int KC>
+template <bool DOUBLE_BUFFER, int KC, bool EXTRA>
 __device__ __forceinline__ void epilogue_tile(TopList<KC>& top, uint32_t t_addr, int64_t row_base,
-                                              int64_t n_rows, float* stg, int lane, int debug) {
+                                              int64_t n_rows, float* stg, int lane, int debug,
+                                              const EpiExtra& xe) {
   if (debug == 1) return;
   if (debug == 2) top.thr = INFINITY;
   const bool ragged = row_base + kBN > n_rows;  // last tile: rows past the table are zero-filled
@@ -242,7 +271,7 @@ __device__ __forceinline__ void epilogue_tile(TopList<KC>& top, uint32_t t_addr,
       uint32_t v[32];
       tmem_ld_32x32(t_addr + c * 32, v);
       tmem_ld_wait();
-      process_group(top, v, int(row_base) + c * 32, ragged, n_rows, stg, lane);
+      process_group<KC, EXTRA>(top, v, int(row_base) + c * 32, ragged, n_rows, stg, lane, xe);
     }
     return;
   }
@@ -252,10 +281,10 @@ __device__ __forceinline__ void epilogue_tile(TopList<KC>& top, uint32_t t_addr,
   for (int c = 0; c < kBN / 32; c += 2) {
     tmem_ld_wait();
     tmem_ld_32x32(t_addr + (c + 1) * 32, vb);
-    process_group(top, va, int(row_base) + c * 32, ragged, n_rows, stg, lane);
+    process_group<KC, EXTRA>(top, va, int(row_base) + c * 32, ragged, n_rows, stg, lane, xe);
     tmem_ld_wait();
     if (c + 2 < kBN / 32) tmem_ld_32x32(t_addr + (c + 2) * 32, va);
-    process_group(top, vb, int(row_base) + (c + 1) * 32, ragged, n_rows, stg, lane);
+    process_group<KC, EXTRA>(top, vb, int(row_base) + (c + 1) * 32, ragged, n_rows, stg, lane, xe);
   }
 }
 
@@ -264,11 +293,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-inline int k2_epi_sets() {
-  const char* e = getenv("MRAG_K2_SETS");
-  const int v = e ? atoi(e) : 1;
-  return v == 2 ? 2 : 1;
-}
+inline int k2_epi_sets() { return 1; }  // (a second epilogue warp set measured no faster; removed)
 
 __device__ __forceinline__ long long clk() { return clock64(); }
 // mbar_wait that charges the waited cycles to `acc`
@@ -282,8 +307,8 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
 
 // host: allocate / print the stats buffer when MRAG_K2_STATS=1
 inline unsigned long long* k2_stats_alloc(int n_ctas) {
-  const char* e = getenv("MRAG_K2_STATS");
-  if (!e || e[0] != '1') return nullptr;
+  static const bool on = [] { const char* e = getenv("MRAG_K2_STATS"); return e && e[0] == '1'; }();
+  if (!on) return nullptr;
   unsigned long long* p = nullptr;
   if (cudaMalloc(&p, size_t(n_ctas) * 8 * 8) != cudaSuccess) return nullptr;
   cudaMemset(p, 0, size_t(n_ctas) * 8 * 8);
@@ -310,8 +335,8 @@ inline void k2_stats_report(unsigned long long* dev, int n_ctas, cudaStream_t st
 }
 
 inline int k2_debug_mode() {
-  const char* e = getenv("MRAG_K2_DEBUG");
-  return e ? atoi(e) : 0;
+  static const int mode = [] { const char* e = getenv("MRAG_K2_DEBUG"); return e ? atoi(e) : 0; }();
+  return mode;
 }
 
 inline EncodeTiledFn get_encode_fn() {

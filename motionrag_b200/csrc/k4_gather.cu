@@ -50,7 +50,7 @@ __device__ __forceinline__ uint4 add_vec(const uint4& a, const uint4& b) {
 template <bool BF16>
 __global__ void __launch_bounds__(kK4Threads)
     k4_gather_kernel(const void* const* __restrict__ shard_ptrs, int nshards,
-                     int64_t rows_per_shard, const int64_t* __restrict__ ref_idx,
+                     int64_t rows_per_shard, int64_t n_rows, const int64_t* __restrict__ ref_idx,
                      const uint4* __restrict__ sos, const uint4* __restrict__ uncond,
                      const uint4* __restrict__ pe, const uint4* __restrict__ cond,
                      uint4* __restrict__ out, int K, int vec_per_group) {
@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(kK4Threads)
   } else {
     const int64_t r = ref_idx[int64_t(bi) * K + (K - g)];
     const int64_t shard = (r >= 0) ? r / rows_per_shard : 0;
-    if (r < 0 || shard >= nshards) {
+    // -1 = dropped / missing reference; an index past the table (stale after the table changed, or
+    // inside the last shard's nominal range but beyond its rows) must never be dereferenced either
+    if (r < 0 || r >= n_rows || shard >= nshards) {
       src = uncond;
     } else {
       src = reinterpret_cast<const uint4*>(shard_ptrs[shard]) +
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(kK4Threads)
 }
 
 cudaError_t launch_k4_gather(const void* const* shard_ptrs, int nshards, int64_t rows_per_shard,
-                             const int64_t* ref_idx, const void* sos, const void* uncond,
+                             int64_t n_rows, const int64_t* ref_idx, const void* sos, const void* uncond,
                              const void* pe, const void* cond, void* out, int b, int K, int L,
                              int C, int dtype, cudaStream_t st) {
   const int elt = (dtype == 0) ? 2 : 4;
@@ -111,12 +113,12 @@ cudaError_t launch_k4_gather(const void* const* shard_ptrs, int nshards, int64_t
             unsigned((vec_per_group + kK4Threads * kK4Unroll - 1) / (kK4Threads * kK4Unroll)));
   auto a = [](const void* p) { return reinterpret_cast<const uint4*>(p); };
   if (dtype == 0)
-    k4_gather_kernel<true><<<grid, kK4Threads, 0, st>>>(shard_ptrs, nshards, rows_per_shard,
+    k4_gather_kernel<true><<<grid, kK4Threads, 0, st>>>(shard_ptrs, nshards, rows_per_shard, n_rows,
                                                         ref_idx, a(sos), a(uncond), a(pe), a(cond),
                                                         reinterpret_cast<uint4*>(out), K,
                                                         vec_per_group);
   else
-    k4_gather_kernel<false><<<grid, kK4Threads, 0, st>>>(shard_ptrs, nshards, rows_per_shard,
+    k4_gather_kernel<false><<<grid, kK4Threads, 0, st>>>(shard_ptrs, nshards, rows_per_shard, n_rows,
                                                          ref_idx, a(sos), a(uncond), a(pe), a(cond),
                                                          reinterpret_cast<uint4*>(out), K,
                                                          vec_per_group);

@@ -126,10 +126,22 @@ class PeerExchange:
         self.table = torch.tensor(ptrs, dtype=torch.int64, device=device)
         dist.barrier(group=group)   # every rank has zeroed and mapped before the first use
 
-    def next(self) -> "_cabi.Exchange":
+    def next(self, timeout_ms: int = 0) -> "_cabi.Exchange":
+        """Descriptor of the next call (epoch + 1). Every rank must issue the same call sequence;
+        validate anything that can fail locally BEFORE taking a descriptor."""
         self.epoch += 1
         return _cabi.Exchange(world=self.world, rank=self.rank, nq_cap=self.nq_cap, k_cap=self.k_cap,
-                              epoch=self.epoch, reserved=0, bufs_dev=self.table.data_ptr())
+                              epoch=self.epoch, timeout_ms=int(timeout_ms), bufs_dev=self.table.data_ptr())
+
+    def reset(self, group: dist.ProcessGroup | None = None) -> None:
+        """Collective re-synchronisation after a failed call (a timed-out exchange leaves the ranks'
+        epochs out of step): drain, zero every buffer, restart the epoch count."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+        self.buf.zero_()
+        self.epoch = 0
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
 
     def close(self) -> None:
         for p in getattr(self, "_opened", []):
@@ -157,30 +169,44 @@ class ShardedRetriever:
         self._bufs: dict[tuple[int, int], tuple[torch.Tensor, torch.Tensor]] = {}
 
     # default (product) implementations ------------------------------------------------------
-    def _cuda_search(self, queries, k, metric, path, refine, exclude_group, filter_mode, index_base, out):
+    def _cuda_search(self, queries, k, metric, path, refine, exclude_group, filter_mode, index_base, out,
+                     certify=False):
         return self.store.search(queries, k, metric=metric, path=path, refine=refine,
                                  exclude_group=exclude_group, filter_mode=filter_mode,
-                                 index_base=index_base, out=out)
+                                 index_base=index_base, out=out, certify=certify)
 
     @staticmethod
     def _cuda_merge(dist_v, idx_v, grp_v, k_out, exclude_group, filter_mode, stride):
         return merge_topk(dist_v, idx_v, grp_v, k_out, exclude_group, filter_mode, stride)
 
+    def _validate(self, nq: int, k: int, path: str) -> None:
+        """Everything that can fail on ONE rank only is checked before the exchange epoch moves, so
+        a bad call raises on every rank instead of leaving the others waiting for a peer."""
+        if nq < 1 or not (1 <= k <= 32):
+            raise ValueError(f"need nq >= 1 and 1 <= k <= 32 (got nq {nq}, k {k})")
+        if path not in ("auto", "stream_f32", "stream_bf16", "tensor_bf16"):
+            raise ValueError(f"unknown path {path!r}")
+        if path.startswith("stream") and self.store is not None and self.store.dim not in (256, 512, 768, 1024):
+            raise ValueError("streaming paths need dim in {256, 512, 768, 1024}")
+
     def search(self, queries: torch.Tensor, k: int, *, metric: str = "l2", path: str = "auto",
                refine: int = 0, exclude_group: torch.Tensor | None = None,
-               filter_mode: str = "post") -> SearchResult:
+               filter_mode: str = "post", certify: bool = False) -> SearchResult:
         """Same contract as EmbeddingStore.search, over the union of all shards. Every rank
-        passes the same queries and gets the same (global-index) result."""
+        passes the same queries and gets the same (global-index) result; with certify the
+        exactness margin of the GLOBAL result (see mrag.h) comes back in `.margin`."""
         if self.world == 1:   # one shard: the local search already is the answer (no exchange)
             return self._local_search(queries, k, metric, path, refine, exclude_group,
-                                      filter_mode if exclude_group is not None else "none", 0, None)
+                                      filter_mode if exclude_group is not None else "none", 0, None,
+                                      **({"certify": True} if certify else {}))
         nq = queries.shape[0]
+        self._validate(nq, k, path)
         if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
             return self.store.search(queries, k, metric=metric, path=path, refine=refine,
                                      exclude_group=exclude_group,
                                      filter_mode=filter_mode if exclude_group is not None else "none",
                                      index_base=self.rank * self.rows_per_shard,
-                                     exchange=self.exchange.next())
+                                     exchange=self.exchange.next(), certify=certify)
         lay = PackedLayout(nq, k)
         key = (nq, k)
         if key not in self._bufs:
@@ -191,13 +217,46 @@ class ShardedRetriever:
         local = SearchResult(d[0], i[0], g[0])
         # post-filter happens after the GLOBAL top-k; pre-filter can be applied per shard
         local_filter = "pre" if (filter_mode == "pre" and exclude_group is not None) else "none"
-        self._local_search(queries, k, metric, path, refine,
-                           exclude_group if local_filter == "pre" else None, local_filter,
-                           self.rank * self.rows_per_shard, local)
+        local = self._local_search(queries, k, metric, path, refine,
+                                   exclude_group if local_filter == "pre" else None, local_filter,
+                                   self.rank * self.rows_per_shard, local,
+                                   **({"certify": True} if certify else {}))
         dist.all_gather_into_tensor(recv, send, group=self.group)
         dv, gv, iv = lay.views(recv, self.world)
-        return self._merge(dv, iv, gv, k, exclude_group,
-                           filter_mode if exclude_group is not None else "none", lay.nbytes)
+        out = self._merge(dv, iv, gv, k, exclude_group,
+                          filter_mode if exclude_group is not None else "none", lay.nbytes)
+        if certify:
+            # the global k-th result is at least as good as any shard's own k-th, so the smallest
+            # per-shard margin is a (conservative) margin of the merged result
+            m = local.margin.contiguous()
+            allm = torch.empty(self.world * nq, dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(allm, m, group=self.group)
+            out.margin = allm.view(self.world, nq).amin(0)
+        return out
+
+    def search_host(self, queries, k: int, *, metric: str = "l2", path: str = "auto", refine: int = 0,
+                    exclude_group=None, filter_mode: str = "post", certify: bool = False):
+        """Host buffers in, host buffers out (numpy), every rank with the same queries: the
+        reference-facing entry of a row-sharded table. With a PeerExchange small calls replay ONE
+        captured graph per rank (H2D copy, scan, fused select / exchange / merge writing straight to
+        pinned host memory); otherwise it falls back to device tensors + the NCCL transport."""
+        import numpy as np
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        if self.world == 1:
+            return self.store.search_host(q, k, metric=metric, path=path, refine=refine,
+                                          exclude_group=exclude_group, filter_mode=filter_mode, certify=certify)
+        self._validate(nq, k, path)
+        if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
+            return self.store.search_host(q, k, metric=metric, path=path, refine=refine,
+                                          exclude_group=exclude_group, filter_mode=filter_mode,
+                                          index_base=self.rank * self.rows_per_shard, certify=certify,
+                                          exchange=self.exchange.next())
+        ex = None if exclude_group is None else torch.from_numpy(np.ascontiguousarray(exclude_group, dtype=np.int32)).to(self.device)
+        r = self.search(torch.from_numpy(q).to(self.device), k, metric=metric, path=path, refine=refine,
+                        exclude_group=ex, filter_mode=filter_mode, certify=certify)
+        out = (r.distance.cpu().numpy(), r.index.cpu().numpy(), r.group.cpu().numpy())
+        return out + ((r.margin.cpu().numpy(),) if certify else ())
 
 
 # --- peer-mapped feature tables ------------------------------------------------------------------

@@ -26,6 +26,13 @@ import torch
 from .store import EmbeddingStore
 
 VECTOR_COLUMNS = ("text_embedding", "image_embedding")
+
+
+def _as_column(v):
+    """Scalar columns are indexed with integer arrays: lists / tuples become numpy arrays."""
+    return v if isinstance(v, np.ndarray) else np.asarray(v)
+
+
 def _as_2d(v):
     """One vector (ndarray / Tensor / list) as a [1, dim] float32 array."""
     a = np.asarray(v.detach().float().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
@@ -80,10 +87,11 @@ class RAGDatabase:
         gte-base-en-v1.5 function), `metric` / `prefilter` (LanceDB 0.14 defaults: "l2", post-
         filter), `normalise` (L2-normalise rows on upload; the reference's tables already are),
         `path` (force a scan kernel: auto | stream_f32 | stream_bf16 | tensor_bf16), `recheck`
-        (what to do with the exactness margin of the bf16 scans, see mrag.h: "auto" re-runs a
-        host call of <= 4 queries on the fp32 master rows when its margin is below 6 sigma of
-        the bf16 rounding noise; "strict" does so for any batch whenever the margin does not
-        rigorously prove exactness; None never re-runs).
+        (what to do with the exactness margin every bf16 scan reports per query, see mrag.h: "auto"
+        re-runs a query on the fp32 master rows when its margin is below 6 sigma of the bf16
+        rounding noise; "strict" whenever the margin does not rigorously prove exactness; None never
+        asks for the margin. Applies to every batch size and to row-sharded tables;
+        `fp32_rechecks` counts the re-runs).
         """
         self.db_path, self.table_name = db_path, table_name
         self._ctor = dict(device=str(device), metric=metric, prefilter=prefilter, normalise=normalise,
@@ -103,21 +111,33 @@ class RAGDatabase:
         self._from_memory = columns is not None
         if columns is None:
             columns = self._load(Path(db_path) / table_name)
-        self._columns = {k: v for k, v in columns.items() if k not in VECTOR_COLUMNS}
+        self._columns = {k: _as_column(v) for k, v in columns.items() if k not in VECTOR_COLUMNS}
         self._vectors = {k: columns[k] for k in VECTOR_COLUMNS if k in columns}
         if not self._vectors:
             raise ValueError("table has no vector column (text_embedding / image_embedding)")
         self._stores: dict[str, EmbeddingStore] = {}
         self._normalise = normalise
+        self._retriever = None
+        self._init_caches()
+        self.table = self  # reference attribute name (rag.py:14); `table=` arguments accept it
+
+    def _init_caches(self) -> None:
         self._group_col: str | None = None
         self._group_ids: dict[str, dict] = {}
-        self.table = self  # reference attribute name (rag.py:14); `table=` arguments accept it
+        self._thr_cache: dict[tuple, float] = {}
+        self._where_cache: dict[str, tuple[str, int]] = {}   # SQL string -> (column, group id)
+        self._col_lists: dict[str, list] = {}                # scalar columns as Python lists (record building)
 
     @classmethod
     def from_store(cls, store: EmbeddingStore, columns: dict, vector_column: str = "text_embedding",
-                   **kw) -> "RAGDatabase":
+                   retriever=None, **kw) -> "RAGDatabase":
         """Wrap an already HBM-resident store (e.g. generated on device) with its scalar
-        columns; the vector column is then not available to `select` on the host side."""
+        columns; the vector column is then not available to `select` on the host side.
+
+        retriever: a `parallel.ShardedRetriever` over a row-sharded table (one process per GPU, `store`
+        = this rank's shard). `columns` then cover ALL rows of the table (scalar metadata lives on the
+        host of every rank), every rank calls the same method with the same arguments, and every rank
+        gets the same records; searches go through the retriever's host-buffer entry."""
         self = object.__new__(cls)
         self.db_path = self.table_name = None
         self._ctor, self.embed_fn = {}, kw.get("embed_fn")
@@ -127,11 +147,12 @@ class RAGDatabase:
         self.fp32_rechecks = 0
         self.device = store.device
         self._from_memory = True
-        self._columns = {k: v for k, v in columns.items() if k not in VECTOR_COLUMNS}
+        self._columns = {k: _as_column(v) for k, v in columns.items() if k not in VECTOR_COLUMNS}
         self._vectors = {vector_column: _DeviceColumn(store)}
         self._stores = {vector_column: store}
         self._normalise = False
-        self._group_col, self._group_ids = None, {}
+        self._retriever = retriever
+        self._init_caches()
         self.table = self
         return self
 
@@ -149,6 +170,8 @@ class RAGDatabase:
         return cols
 
     def __len__(self) -> int:
+        if self._retriever is not None and self._columns:
+            return int(len(next(iter(self._columns.values()))))
         return int(next(iter(self._vectors.values())).shape[0])
 
     def _store(self, column: str) -> EmbeddingStore:
@@ -180,7 +203,11 @@ class RAGDatabase:
         g = self._groups_for(column)
         if self._group_col != column:
             for st in self._stores.values():
-                st.set_groups(g["ids"])
+                ids = g["ids"]
+                if self._retriever is not None and self._retriever.world > 1:   # this rank's rows only
+                    lo = self._retriever.rank * self._retriever.rows_per_shard
+                    ids = ids[lo:lo + len(st)]
+                st.set_groups(ids)
             self._group_col = column
         return g
 
@@ -215,6 +242,36 @@ class RAGDatabase:
         else:
             raise ValueError(f'Invalid format: {format}')
 
+    def _as_host_queries(self, vector) -> tuple[np.ndarray, bool]:
+        """Any accepted query form -> (contiguous float32 [nq, dim] host array, was it a single vector)."""
+        if isinstance(vector, np.ndarray):
+            q = vector if vector.dtype == np.float32 else vector.astype(np.float32)
+        elif isinstance(vector, torch.Tensor):
+            q = vector.detach().to(torch.float32).cpu().numpy()
+        else:
+            if isinstance(vector, str) or (isinstance(vector, (list, tuple)) and vector and isinstance(vector[0], str)):
+                if self.embed_fn is None:
+                    raise NotImplementedError(
+                        "text queries need an embed_fn (the reference lets LanceDB run gte-base-en-v1.5; "
+                        "src/data/datamodule.py:296-304 always passes precomputed vectors)")
+                was_str = isinstance(vector, str)
+                vector = self.embed_fn(vector)
+                if isinstance(vector, torch.Tensor):
+                    vector = vector.detach().to(torch.float32).cpu().numpy()
+                q = np.asarray(vector, dtype=np.float32)
+                if was_str and q.ndim == 2 and q.shape[0] == 1:
+                    q = q[0]
+            else:
+                q = np.asarray(vector, dtype=np.float32)
+        single = q.ndim == 1
+        if single:
+            q = q[None]
+        if q.ndim != 2:
+            raise ValueError(f"query must be [dim] or [nq, dim], got {tuple(q.shape)}")
+        if not q.flags.c_contiguous:
+            q = np.ascontiguousarray(q)
+        return q, single
+
     def _as_queries(self, vector) -> tuple[torch.Tensor, bool]:
         if isinstance(vector, str) or (isinstance(vector, (list, tuple)) and vector and isinstance(vector[0], str)):
             if self.embed_fn is None:
@@ -234,32 +291,48 @@ class RAGDatabase:
         q = q.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
         return q, single
 
+    def _where_to_group(self, w: str) -> tuple[str, int]:
+        """One `<column> != "<value>"` clause -> (column, dense group id or -1); parsed once per string."""
+        hit = self._where_cache.get(w)
+        if hit is None:
+            m = _WHERE.match(w)
+            if not m:
+                raise ValueError(f"unsupported where clause {w!r}: only `<column> != \"<value>\"` "
+                                 "(src/data/datamodule.py:235) is implemented")
+            col = m.group(1)
+            if col not in self._columns:
+                raise ValueError(f"where clause names unknown column {col!r}")
+            if len(self._where_cache) > (1 << 20):
+                self._where_cache.clear()
+            hit = self._where_cache[w] = (col, self._group_ids_lookup(col, m.group(3)))
+        return hit
+
     def _exclusion_ids(self, where, nq: int):
         """`where` is one SQL string (reference form) or one per query (batched form);
         -> int32 [nq] group ids to exclude (-1 = none) or None."""
         if where is None:
             return None
-        wheres = [where] * nq if isinstance(where, str) else list(where)
-        if len(wheres) != nq:
-            raise ValueError("need one where clause per query")
-        col, ids = None, np.full(nq, -1, dtype=np.int32)
-        for i, w in enumerate(wheres):
-            if w is None:
-                continue
-            m = _WHERE.match(w)
-            if not m:
-                raise ValueError(f"unsupported where clause {w!r}: only `<column> != \"<value>\"` "
-                                 "(src/data/datamodule.py:235) is implemented")
+        if isinstance(where, str):
+            col, gid = self._where_to_group(where)
+            ids = np.full(nq, gid, dtype=np.int32)
+        else:
+            wheres = list(where)
+            if len(wheres) != nq:
+                raise ValueError("need one where clause per query")
+            col, ids = None, np.full(nq, -1, dtype=np.int32)
+            for i, w in enumerate(wheres):
+                if w is None:
+                    continue
+                c, gid = self._where_to_group(w)
+                if col is None:
+                    col = c
+                elif col != c:
+                    raise ValueError("all where clauses of a batch must name the same column")
+                ids[i] = gid
             if col is None:
-                col = m.group(1)
-                if col not in self._columns:
-                    raise ValueError(f"where clause names unknown column {col!r}")
-            elif col != m.group(1):
-                raise ValueError("all where clauses of a batch must name the same column")
-            ids[i] = self._group_ids_lookup(col, m.group(3))
-        if col is None:
-            return None
-        self._bind_groups(col)
+                return None
+        if self._group_col != col:
+            self._bind_groups(col)
         return ids
 
     def _group_ids_lookup(self, col: str, value) -> int:
@@ -275,29 +348,45 @@ class RAGDatabase:
                     break
         return -1 if v is None else int(v)
 
+    def _column_list(self, c: str) -> list:
+        lst = self._col_lists.get(c)
+        if lst is None:
+            lst = self._col_lists[c] = self._columns[c].tolist()
+        return lst
+
     def _records(self, dist: np.ndarray, idx: np.ndarray, select: Sequence[str] | None) -> list[list[dict]]:
         names = list(select) if select is not None else list(self._columns) + list(self._vectors)
-        cols = []
         for c in names:
-            if c in self._columns:
-                cols.append((c, self._columns[c], False))
-            elif c in self._vectors:
-                cols.append((c, self._vectors[c], True))
-            else:
+            if c not in self._columns and c not in self._vectors:
                 raise ValueError(f"unknown column {c!r} in select")
+        nq, k = idx.shape
+        if nq <= 4 and not any(c in self._vectors for c in names):
+            # the reference's call pattern (one query per call): plain list indexing, no numpy round trips
+            cols = [(c, self._column_list(c)) for c in names]
+            out = []
+            for qi in range(nq):
+                recs = []
+                for i, d in zip(idx[qi].tolist(), dist[qi].tolist()):
+                    if i < 0:
+                        continue
+                    r = {c: lst[i] for c, lst in cols}
+                    r["_distance"] = d
+                    recs.append(r)
+                out.append(recs)
+            return out
         # one fancy-index + tolist() per column for the WHOLE batch, then C-speed dict(zip(...));
         # per-cell numpy scalar handling would dominate a 4096-query batch
-        nq, k = idx.shape
         valid = idx >= 0
         flat = idx[valid]
         counts = valid.sum(-1).tolist()
-        keys = [c for c, _, _ in cols] + ["_distance"]
+        keys = names + ["_distance"]
         per_col = []
-        for c, col, is_vec in cols:
-            if is_vec:
-                per_col.append([np.array(col[int(i)], dtype=np.float32) for i in flat])
+        for c in names:
+            if c in self._columns:
+                per_col.append(self._columns[c][flat].tolist())
             else:
-                per_col.append(col[flat].tolist())
+                col = self._vectors[c]
+                per_col.append([np.array(col[int(i)], dtype=np.float32) for i in flat])
         per_col.append(dist[valid].tolist())
         recs = [dict(zip(keys, vals)) for vals in zip(*per_col)]
         out, pos = [], 0
@@ -307,52 +396,57 @@ class RAGDatabase:
         return out
 
     def _search(self, vector, vector_column_name, top_k, where, refine_factor):
-        """-> (distance f32 [nq,k], index i64 [nq,k]) numpy arrays, single?"""
+        """-> (distance f32 [nq,k], index i64 [nq,k]) numpy arrays, single?
+
+        Every bf16 scan is certified: the kernels report the exactness margin of each query (mrag.h)
+        and queries that fail the test of `recheck` are re-run on the fp32 master rows — for any
+        batch size, for host and device inputs, for single-GPU and row-sharded tables."""
         column = vector_column_name or "text_embedding"
         store = self._store(column)
         refine = int(min(64, max(top_k, top_k * max(1, int(refine_factor)))))
         mode = "pre" if self.prefilter else "post"
-        on_host = isinstance(vector, np.ndarray) or (isinstance(vector, torch.Tensor) and not vector.is_cuda)
-        if on_host:
-            # the reference's call pattern (a host ndarray per annotation): one C call with host
-            # buffers, one copy each way (mrag_search_host)
-            q = np.asarray(vector.detach().float().numpy() if isinstance(vector, torch.Tensor) else vector,
-                           dtype=np.float32)
-            single = q.ndim == 1
-            q = np.ascontiguousarray(q[None] if single else q)
-            if q.ndim != 2:
-                raise ValueError(f"query must be [dim] or [nq, dim], got {tuple(q.shape)}")
-            excl = self._exclusion_ids(where, q.shape[0])
-            certify = (self.recheck == "strict" or (self.recheck == "auto" and q.shape[0] <= 4))
-            if self.path == "stream_f32" or self.prefilter or not certify:
-                dist, idx, _ = store.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
-                                                 exclude_group=excl, filter_mode=mode)
-                return dist, idx, single
-            dist, idx, _, margin = store.search_host(q, int(top_k), metric=self.metric, path=self.path,
-                                                     refine=refine, exclude_group=excl, filter_mode=mode,
-                                                     certify=True)
-            self._recheck(store, q, excl, dist, idx, margin, top_k, mode)
-            return dist, idx, single
-        q, single = self._as_queries(vector)
+        q, single = self._as_host_queries(vector)
         excl = self._exclusion_ids(where, q.shape[0])
-        excl_d = None if excl is None else torch.from_numpy(excl).to(self.device, non_blocking=True)
-        res = store.search(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
-                           exclude_group=excl_d, filter_mode=mode)
-        return res.distance.cpu().numpy(), res.index.cpu().numpy(), single
+        certify = self.recheck is not None and self.path != "stream_f32"
+        searcher = self._retriever if self._retriever is not None else store
+        res = searcher.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
+                                   exclude_group=excl, filter_mode=mode, certify=certify)
+        dist, idx = res[0], res[1]
+        if certify:
+            self._recheck(searcher, store, q, excl, dist, idx, res[3], top_k, mode)
+        return dist, idx, single
 
-    def _recheck(self, store, q, excl, dist, idx, margin, top_k, mode) -> None:
-        """Queries whose bf16-scan result is not certified exact (margin <= eps, see mrag.h) are
+    def _margin_threshold(self, store, nq: int, top_k: int) -> float:
+        from .store import PATH_NAME, margin_threshold
+        key = (id(store), nq == 1, int(top_k))
+        thr = self._thr_cache.get(key)
+        if thr is None:
+            if len(store) == 0:
+                used = "tensor_bf16"
+            else:
+                used = PATH_NAME[store.plan(nq, k=int(top_k), path=self.path).path]   # the path AUTO resolves to
+            thr = self._thr_cache[key] = margin_threshold(used, store.dim, self.recheck == "strict",
+                                                          store.info().max_norm_deviation)
+        return thr
+
+    def _recheck(self, searcher, store, q, excl, dist, idx, margin, top_k, mode) -> None:
+        """Queries whose bf16-scan result is not certified exact (margin <= threshold, see mrag.h) are
         re-run on the fp32 master rows, 4 per pass; results are patched in place."""
-        from .store import EPS, eps_typical
-        used = "stream_bf16" if (self.path == "stream_bf16" or (self.path == "auto" and q.shape[0] == 1)) else "tensor_bf16"
-        eps = EPS[used] if self.recheck == "strict" else eps_typical(used, q.shape[1])
-        doubt = np.nonzero(~(margin > eps))[0]          # NaN counts as doubt
+        thr = self._margin_threshold(store, q.shape[0], top_k)
+        if q.shape[0] == 1:
+            if margin[0] > thr:
+                return
+            doubt = np.zeros(1, dtype=np.int64)
+        else:
+            doubt = np.nonzero(~(margin > thr))[0]          # NaN counts as doubt
+            if doubt.size == 0:
+                return
         self.fp32_rechecks += int(doubt.size)
         for s in range(0, doubt.size, 4):
             rows = doubt[s:s + 4]
-            d2, i2, _ = store.search_host(q[rows], int(top_k), metric=self.metric, path="stream_f32",
-                                          exclude_group=None if excl is None else excl[rows], filter_mode=mode)
-            dist[rows], idx[rows] = d2, i2
+            r2 = searcher.search_host(q[rows], int(top_k), metric=self.metric, path="stream_f32",
+                                      exclude_group=None if excl is None else excl[rows], filter_mode=mode)
+            dist[rows], idx[rows] = r2[0], r2[1]
 
     def vector_search(self, vector, vector_column_name: str = None, top_k: int = 10, table=None,
                       where: str = None, select: list[str] = None, nprobes: int = 50, refine_factor: int = 30,
@@ -407,7 +501,9 @@ class RAGDatabase:
         against the image-embedding column in fp32 and keeps the best k1 (mrag_rescore_rows) — the
         candidate rows play the part of the reference's temporary table (src/data/rag.py:118-128)."""
         k0, k1 = int(top_k[0]), int(top_k[1])
-        q_t, _ = self._as_queries(texts)
+        if self._retriever is not None and self._retriever.world > 1:
+            raise NotImplementedError("the two-stage text -> image search runs on a single-GPU table")
+        q_t, _ = self._as_host_queries(texts)
         q_i, _ = self._as_queries(image_embeddings)
         if q_t.shape[0] != q_i.shape[0]:
             raise ValueError("need one image embedding per text query")
@@ -429,7 +525,7 @@ class RAGDatabase:
         """One scan per `batch` queries instead of one LanceDB call per annotation; returns the
         same per-query record lists the reference stores in `anno['ref_videos']`
         (src/data/datamodule.py:264-265)."""
-        q_all, _ = self._as_queries(vectors)
+        q_all, _ = self._as_host_queries(vectors)
         wheres = None if where is None else ([where] * q_all.shape[0] if isinstance(where, str) else list(where))
         out: list[list[dict]] = []
         for s in range(0, q_all.shape[0], batch):

@@ -32,9 +32,10 @@ class SearchResult:
     margin: torch.Tensor | None = None  # float32 [nq] exactness certificate (see EPS / mrag.h)
 
 
-# |bf16 scan score - true q.d| <= EPS[path] * |q| for unit rows (worst case: every element rounds the
-# same way and q is parallel to the rounding error): margin > EPS PROVES the top-k is exact
+# |bf16 scan score - true q.d| <= EPS[path] * |q| |d| (worst case: every element rounds the same way
+# and q is parallel to the rounding error): margin > EPS * max|d| PROVES the top-k is exact
 EPS = {"stream_f32": 0.0, "stream_bf16": 2.0 ** -9, "tensor_bf16": 2.0 ** -8}
+PATH_NAME = {1: "stream_f32", 2: "stream_bf16", 3: "tensor_bf16"}
 
 
 def eps_typical(path: str, dim: int, sigmas: float = 6.0) -> float:
@@ -46,6 +47,13 @@ def eps_typical(path: str, dim: int, sigmas: float = 6.0) -> float:
         return 0.0
     rounded = 2.0 if path == "tensor_bf16" else 1.0
     return sigmas * (2.0 ** -9) / (12.0 ** 0.5) / (dim ** 0.5) * (rounded ** 0.5)
+
+
+def margin_threshold(path: str, dim: int, strict: bool, max_norm_deviation: float = 0.0) -> float:
+    """What an exactness margin must exceed: the worst-case bound (strict) or 6 sigma of the rounding
+    noise, both scaled by the largest row norm the store holds."""
+    eps = EPS[path] if strict else eps_typical(path, dim)
+    return eps * (1.0 + max(0.0, float(max_norm_deviation))) ** 0.5
 
 
 class EmbeddingStore:
@@ -60,6 +68,8 @@ class EmbeddingStore:
         check(self._lib.mrag_store_create(self.dim, int(capacity_rows), self.device.index, C.byref(h)))
         self._h = h
         self._ws: dict[int, torch.Tensor] = {}   # scratch per CUDA stream: searches on different streams may overlap
+        self._need: dict[tuple, int] = {}        # workspace bytes per call shape (dropped by append / set_groups)
+        self._info: StoreInfo | None = None
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -75,9 +85,17 @@ class EmbeddingStore:
 
     # -- contents ---------------------------------------------------------------------------
     def info(self) -> StoreInfo:
-        inf = StoreInfo()
-        check(self._lib.mrag_store_get_info(self._h, C.byref(inf)))
-        return inf
+        if self._info is None:
+            inf = StoreInfo()
+            check(self._lib.mrag_store_get_info(self._h, C.byref(inf)))
+            self._info = inf
+        return self._info
+
+    def poll_error(self) -> None:
+        """Raise if a kernel of this store reported a device-side error (a peer exchange that timed
+        out) since the last poll. Call after synchronising the stream the search ran on."""
+        code = C.c_int32()
+        check(self._lib.mrag_store_poll_error(self._h, C.byref(code)))
 
     def __len__(self) -> int:
         return int(self.info().n_rows)
@@ -95,6 +113,8 @@ class EmbeddingStore:
         on_dev = rows.is_cuda
         if on_dev and rows.device != self.device:
             rows = rows.to(self.device)
+        self._need.clear()
+        self._info = None
         check(self._lib.mrag_store_append(self._h, C.c_void_p(rows.data_ptr()), rows.shape[0],
                                           1 if on_dev else 0, 1 if normalise else 0,
                                           _stream_ptr(self.device)))
@@ -107,6 +127,8 @@ class EmbeddingStore:
             groups = torch.from_numpy(np.ascontiguousarray(groups, dtype=np.int32))
         groups = groups.to(torch.int32).contiguous()
         on_dev = groups.is_cuda
+        self._need.clear()
+        self._info = None
         check(self._lib.mrag_store_set_groups(self._h, C.c_void_p(groups.data_ptr()), groups.numel(),
                                               1 if on_dev else 0, _stream_ptr(self.device)))
         if not on_dev:
@@ -192,7 +214,14 @@ class EmbeddingStore:
         elif exclude_group.device != self.device or exclude_group.dtype != torch.int32:
             raise ValueError("exclude_group must be int32 on the store's device")
         p = self._params(k, metric, path, refine, filter_mode, index_base)
-        need = int(self.plan(nq, p).workspace_bytes)
+        key = (nq, k, metric, path, refine, filter_mode, exchange is not None)
+        need = self._need.get(key)
+        if need is None:
+            if exchange is not None and len(self) == 0:
+                need = 1 << 20       # an empty shard still takes part in the exchange
+            else:
+                need = int(self.plan(nq, p).workspace_bytes)
+            self._need[key] = need
         if certify:
             out_margin = torch.empty(nq, dtype=torch.float32, device=self.device)
             p.out_margin = out_margin.data_ptr()
@@ -242,8 +271,10 @@ class EmbeddingStore:
 
     def search_host(self, queries: np.ndarray, k: int, *, metric: str = "l2", path: str = "auto",
                     refine: int = 0, exclude_group: np.ndarray | None = None,
-                    filter_mode: str = "post", index_base: int = 0, certify: bool = False):
-        """Host-buffer search through `mrag_search_host` (copies inside, synchronous).
+                    filter_mode: str = "post", index_base: int = 0, certify: bool = False, exchange=None):
+        """Host-buffer search through `mrag_search_host` (copies inside, synchronous); with
+        `exchange` (an mrag_exchange descriptor) the row-sharded variant whose last kernel merges the
+        shards over peer memory (`mrag_search_sharded_host`).
 
         Returns (distance f32 [nq,k], index i64 [nq,k], group i32 [nq,k]) numpy arrays, plus the
         float32 [nq] exactness margin when certify=True.
@@ -265,11 +296,12 @@ class EmbeddingStore:
         if certify:
             margin = np.empty(nq, dtype=np.float32)
             p.out_margin = margin.ctypes.data
-        check(self._lib.mrag_search_host(
-            self._h, q.ctypes.data_as(C.c_void_p), nq, C.byref(p),
-            ex.ctypes.data_as(C.c_void_p) if ex is not None else None,
-            dist.ctypes.data_as(C.c_void_p), idx.ctypes.data_as(C.c_void_p),
-            grp.ctypes.data_as(C.c_void_p), _stream_ptr(self.device)))
+        args = (self._h, q.ctypes.data, nq, C.byref(p), ex.ctypes.data if ex is not None else None,
+                dist.ctypes.data, idx.ctypes.data, grp.ctypes.data)
+        if exchange is None:
+            check(self._lib.mrag_search_host(*args, _stream_ptr(self.device)))
+        else:
+            check(self._lib.mrag_search_sharded_host(*args, C.byref(exchange), _stream_ptr(self.device)))
         if certify:
             return dist, idx, grp, margin
         return dist, idx, grp
@@ -332,7 +364,7 @@ class FeatureTable:
     """
 
     def __init__(self, local: torch.Tensor, rows_per_shard: int | None = None, shard_rank: int = 0,
-                 n_shards: int = 1):
+                 n_shards: int = 1, n_rows: int | None = None):
         if local.ndim != 3 or not local.is_cuda or not local.is_contiguous():
             raise ValueError("local feature block must be a contiguous CUDA tensor [rows, L, C]")
         if local.dtype not in (torch.bfloat16, torch.float32):
@@ -342,6 +374,12 @@ class FeatureTable:
         self.L, self.Cdim = int(local.shape[1]), int(local.shape[2])
         self.rows_per_shard = int(rows_per_shard if rows_per_shard is not None else local.shape[0])
         self.shard_rank, self.n_shards = int(shard_rank), int(n_shards)
+        # rows the whole table really has (the last shard may be short): the gather kernel maps any
+        # index at or beyond it to the uncond row instead of dereferencing it
+        self.n_rows = int(n_rows) if n_rows is not None else (
+            int(local.shape[0]) if self.n_shards == 1 else self.rows_per_shard * self.n_shards)
+        if self.n_rows > self.rows_per_shard * self.n_shards:
+            raise ValueError("n_rows exceeds n_shards * rows_per_shard")
         ptrs = [0] * self.n_shards
         ptrs[self.shard_rank] = local.data_ptr()
         self._peer_ptrs: list[int] = ptrs

@@ -43,11 +43,26 @@ def test_header_compiles_as_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct as gcc sees include/mrag.h == the ctypes mirror."""
     from motionrag_b200 import _cabi
-    assert C.sizeof(_cabi.SearchParams) == 40
-    assert C.sizeof(_cabi.StoreInfo) == 72
-    assert C.sizeof(_cabi.PlanInfo) == 56
+    structs = {"mrag_search_params": _cabi.SearchParams, "mrag_store_info": _cabi.StoreInfo,
+               "mrag_plan_info": _cabi.PlanInfo, "mrag_exchange": _cabi.Exchange, "mrag_cama_layer": _cabi.CamaLayer}
+    lines = []
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mrag.h"\nint main(void){\n' + "\n".join(lines) + "\nreturn 0;}\n")
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), (cname, got[cname], C.sizeof(ct))
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
 
 
 def test_library_contains_blackwell_sass(libmrag):

@@ -15,7 +15,8 @@ def _db_no_gpu(n=30, dim=8):
     db._columns = {"video": np.array([f"v{j // 3}" for j in range(n)]), "id": np.arange(n),
                    "start_sec": np.arange(n, dtype=np.float64)}
     db._vectors = {"text_embedding": rng.standard_normal((n, dim)).astype(np.float32)}
-    db._group_ids, db._group_col, db._stores = {}, None, {}
+    db._stores, db._retriever = {}, None
+    db._init_caches()
     db.recheck, db.fp32_rechecks = "auto", 0
     return db
 
@@ -47,6 +48,31 @@ def test_records_schema_and_padding_rows_are_dropped():
     assert set(full) == {"video", "id", "start_sec", "text_embedding", "_distance"}
     with pytest.raises(ValueError):
         db._records(dist, idx, ["nope"])
+    # the batched builder (more than 4 queries) produces the same records as the per-query one
+    idx8, dist8 = np.repeat(idx, 8, 0), np.repeat(dist, 8, 0)
+    assert db._records(dist8, idx8, ["video", "start_sec"]) == recs * 8
+    # columns handed over as Python lists work too
+    db2 = _db_no_gpu()
+    db2._columns = {k: rag._as_column(v.tolist()) for k, v in db2._columns.items()}
+    assert db2._records(dist8, idx8, ["video", "start_sec"]) == recs * 8
+
+
+def test_where_clauses_are_parsed_once_and_validated():
+    db = _db_no_gpu()
+    db._bind_groups = lambda col: setattr(db, "_group_col", col)      # no store in this shell
+    ids = db._exclusion_ids('video != "v3"', 2)
+    assert ids.tolist() == [db._group_ids_lookup("video", "v3")] * 2 and 'video != "v3"' in db._where_cache
+    ids = db._exclusion_ids(['video != "v1"', None, 'video != "nope"'], 3)
+    assert ids.tolist() == [db._group_ids_lookup("video", "v1"), -1, -1]
+    assert db._exclusion_ids(None, 3) is None and db._exclusion_ids([None, None], 2) is None
+    with pytest.raises(ValueError, match="unsupported where"):
+        db._exclusion_ids('start_sec > 3', 1)
+    with pytest.raises(ValueError, match="unknown column"):
+        db._exclusion_ids('nope != "x"', 1)
+    with pytest.raises(ValueError, match="same column"):
+        db._exclusion_ids(['video != "v1"', 'id != "3"'], 2)
+    with pytest.raises(ValueError, match="one where clause per query"):
+        db._exclusion_ids(['video != "v1"'], 2)
 
 
 def test_format_result_formats_and_error():

@@ -1,8 +1,12 @@
 """Worker for tests/test_gpu_multi.py: run under torch.distributed.run with >= 2 ranks (NCCL).
 
-Checks, on every rank: (1) row-sharded search over NCCL == single-table search of the same rows,
-for the streaming and tensor paths, with and without the post-filter; (2) the gather kernel
-reading a row-sharded feature table through CUDA-IPC peer pointers == the restatement.
+Checks, on every rank: (1) row-sharded search == single-table oracle search of the same rows, for the
+streaming and tensor paths, with and without the filters, over both transports (NCCL all-gather + merge
+kernel; exchange fused into the last search kernel over peer memory), incl. the exactness margin of the
+global result, batches beyond the single-phase limit, an empty shard, the host-buffer (graph) entry, the
+reference-facing RAGDatabase over a sharded table with its fp32 re-check, and a peer that never shows up
+(bounded wait -> error, then re-synchronisation); (2) the gather kernel reading a row-sharded feature
+table through CUDA-IPC peer pointers == the restatement.
 """
 import os
 import sys
@@ -22,15 +26,39 @@ from oracle import compare, flat_search as fs  # noqa: E402
 
 
 def check_retriever(retr, db, q, groups, excl, k, dev):
-    for nq, path in ((1, "stream_f32"), (4, "stream_bf16"), (300, "tensor_bf16"), (64, "auto")):
+    for nq, path in ((1, "stream_f32"), (1, "auto"), (4, "stream_bf16"), (300, "tensor_bf16"), (64, "auto")):
         for filt in (None, "post", "pre"):
             ex = None if filt is None else torch.from_numpy(excl[:nq]).to(dev)
-            r = retr.search(torch.from_numpy(q[:nq]).to(dev), k, path=path, exclude_group=ex, filter_mode=filt or "post")
+            r = retr.search(torch.from_numpy(q[:nq]).to(dev), k, path=path, exclude_group=ex, filter_mode=filt or "post",
+                            certify=True)
             rd, ri = fs.flat_search(db, q[:nq], k, "l2", groups if filt else None, excl[:nq] if filt else None,
                                     prefilter=(filt == "pre"))
-            compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[:nq])
+            rep = compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[:nq])
+            assert rep["index_mismatches"] == rep["near_tie_positions"], (nq, path, filt, rep)
             gi = r.index.cpu().numpy()
             assert np.all(r.group.cpu().numpy()[gi >= 0] == groups[gi[gi >= 0]])
+            mg = r.margin.cpu().numpy()
+            assert mg.shape == (nq,) and not np.isnan(mg).any() and (mg > -1e-6).all(), (nq, path, filt, mg[:4])
+
+
+def bf16_round(a):
+    return torch.from_numpy(a).bfloat16().float().numpy()
+
+
+def check_sharded_margin(retr, db, q, k, rps, world, dev):
+    """margin of the GLOBAL result = (exact q.d of the k-th hit - max over shards of the scan score of that
+    shard's weakest re-ranked row) / |q| — recomputed here from the definition (stream_bf16: 32 re-ranked)."""
+    nq = 3
+    r = retr.search(torch.from_numpy(q[:nq]).to(dev), k, path="stream_bf16", certify=True)
+    scan = q[:nq].astype(np.float64) @ bf16_round(db).T.astype(np.float64)
+    true = q[:nq].astype(np.float64) @ db.T.astype(np.float64)
+    idx = r.index.cpu().numpy()
+    for j in range(nq):
+        weakest = max(np.sort(scan[j, g * rps:(g + 1) * rps])[::-1][31] for g in range(world)
+                      if db[g * rps:(g + 1) * rps].shape[0] >= 32)
+        want = (true[j, idx[j, k - 1]] - weakest) / np.linalg.norm(q[j])
+        got = float(r.margin[j])
+        assert abs(got - want) < 2e-4, (j, got, want)
 
 
 def main():
@@ -49,20 +77,122 @@ def main():
     shard = m.EmbeddingStore(dim, hi - lo, dev)
     shard.append(db[lo:hi], normalise=False)
     shard.set_groups(groups[lo:hi])
-    xchg = m.PeerExchange(rank, world, dev, nq_cap=512, k_cap=32)
+    xchg = m.PeerExchange(rank, world, dev, nq_cap=4096, k_cap=32)
     for retr in (m.ShardedRetriever(shard, rank, world, rps),                    # NCCL all-gather + merge kernel
-                 m.ShardedRetriever(shard, rank, world, rps, exchange=xchg)):     # exchange fused into K3 over peer memory
+                 m.ShardedRetriever(shard, rank, world, rps, exchange=xchg)):     # exchange fused into the last kernel
         check_retriever(retr, db, q, groups, excl, k, dev)
     retr = m.ShardedRetriever(shard, rank, world, rps, exchange=xchg)
-    for rep in range(40):    # slot reuse / epoch ordering under back-to-back calls
-        r = retr.search(torch.from_numpy(q[rep:rep + 3]).to(dev), k, path="stream_f32")
-        rd, ri = fs.flat_search(db, q[rep:rep + 3], k)
-        compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[rep:rep + 3])
+    check_sharded_margin(retr, db, q, k, rps, world, dev)
+    for rep in range(40):    # slot reuse / epoch ordering under back-to-back calls (single-launch form)
+        path = ("stream_f32", "auto")[rep % 2]
+        nqr = 1 if rep % 2 else 3
+        r = retr.search(torch.from_numpy(q[rep:rep + nqr]).to(dev), k, path=path)
+        rd, ri = fs.flat_search(db, q[rep:rep + nqr], k)
+        compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[rep:rep + nqr])
     # every rank must hold the identical answer
     r = retr.search(torch.from_numpy(q[:64]).to(dev), k)
     ref = r.index.clone()
     dist.broadcast(ref, 0)
     assert torch.equal(ref, r.index)
+
+    # a batch beyond the single-phase limit: publish in K3, wait + merge in a second kernel (4096 queries, 3 epochs)
+    qbig = np.tile(q, (14, 1))[:4096] * np.linspace(0.5, 2.0, 4096, dtype=np.float32)[:, None]
+    exbig = np.tile(excl, 14)[:4096]
+    rd, ri = fs.flat_search(db, qbig[:300], k, "l2", groups, exbig[:300])
+    for rep in range(3):
+        r = retr.search(torch.from_numpy(qbig).to(dev), k, exclude_group=torch.from_numpy(exbig).to(dev), certify=True)
+        repo = compare.check_retrieval(r.distance[:300].cpu().numpy(), r.index[:300].cpu().numpy(), rd, ri, db, qbig[:300])
+        assert repo["index_mismatches"] == repo["near_tie_positions"]
+        # rows 300.. repeat rows 0..299 with another scale: same neighbours
+        assert torch.equal(r.index[300:600], r.index[:300]) and not bool(torch.isnan(r.margin).any())
+        ref = r.index.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref, r.index)
+
+    # host buffers in / out: one captured graph per rank with the exchange inside; epochs keep advancing
+    for rep in range(12):
+        nqr = (1, 1, 3, 64)[rep % 4]
+        d, i, g, mg = retr.search_host(q[rep:rep + nqr], k, exclude_group=excl[rep:rep + nqr], certify=True)
+        rd, ri = fs.flat_search(db, q[rep:rep + nqr], k, "l2", groups, excl[rep:rep + nqr])
+        repo = compare.check_retrieval(d, i, rd, ri, db, q[rep:rep + nqr])
+        assert repo["index_mismatches"] == repo["near_tie_positions"] and not np.isnan(mg).any()
+
+    # the reference-facing class over the sharded table: same records on every rank, == the oracle class
+    cols = {"video": np.array([f"video_{j // 3}" for j in range(n)]), "start_sec": np.arange(n, dtype=np.float64)}
+    rdb = m.RAGDatabase.from_store(shard, cols, retriever=retr)
+    ora = fs.OracleRAGDatabase({**cols, "text_embedding": db})
+    for j in range(6):
+        kw = dict(top_k=k, where=f'video != "{cols["video"][src[j]]}"', select=["video", "start_sec"])
+        got, want = rdb.text_search(q[j], **kw), ora.text_search(q[j], **kw)
+        assert [r["video"] for r in got] == [r["video"] for r in want], j
+        assert np.allclose([r["_distance"] for r in got], [r["_distance"] for r in want], rtol=1e-4)
+    batch = rdb.search_batch(q[:200], top_k=k, where=[f'video != "{cols["video"][s_]}"' for s_ in src[:200]], select=["video"])
+    rd, ri = fs.flat_search(db, q[:200], k, "l2", groups, excl[:200])
+    assert [[r["video"] for r in rr] for rr in batch] == [[cols["video"][i_] for i_ in row if i_ >= 0] for row in ri]
+    assert rdb.fp32_rechecks == 0
+
+    # uncertifiable queries on a sharded table are re-run on the fp32 rows of every shard
+    rng2 = np.random.default_rng(7)
+    n2 = 4000
+    base = fs.normalise_rows(rng2.standard_normal((1, dim)).astype(np.float32))[0]
+    db2 = fs.normalise_rows(rng2.standard_normal((n2, dim)).astype(np.float32))
+    twins = rng2.choice(n2, 200, replace=False)
+    db2[twins] = fs.normalise_rows(base[None] + 1e-2 / np.sqrt(dim) * rng2.standard_normal((200, dim)).astype(np.float32))
+    rps2, lo2, hi2 = m.shard_range(n2, world, rank)
+    shard2 = m.EmbeddingStore(dim, max(hi2 - lo2, 1), dev)
+    shard2.append(db2[lo2:hi2], normalise=False)
+    retr2 = m.ShardedRetriever(shard2, rank, world, rps2, exchange=xchg)
+    rdb2 = m.RAGDatabase.from_store(shard2, {"video": np.array([f"v{j}" for j in range(n2)])}, retriever=retr2)
+    q2 = np.stack([base * 9, db2[5] * 4]).astype(np.float32)
+    for qq in (q2[:1], q2):
+        res = rdb2.search_batch(qq, top_k=12, select=["video"])
+        rd, ri = fs.flat_search(db2, qq, 12)
+        got_i = np.array([[int(r["video"][1:]) for r in rr] for rr in res])
+        compare.check_retrieval(np.array([[r["_distance"] for r in rr] for rr in res]), got_i, rd, ri, db2, qq)
+        assert len(set(ri[0].tolist()) & set(got_i[0].tolist())) >= 10
+    # (with many shards a shard may hold fewer twins than it re-ranks: then everything relevant WAS re-scored
+    # in fp32 and the certificate rightly passes; the 16-candidate tensor path always has to re-run here)
+    assert rdb2.fp32_rechecks == 2 if world <= 2 else rdb2.fp32_rechecks >= 1, rdb2.fp32_rechecks
+    shard2.close()
+
+    # an EMPTY last shard still takes part in the exchange (uneven partition)
+    if world >= 2:
+        n3 = 5000
+        rps3 = -(-n3 // (world - 1))
+        lo3, hi3 = min(n3, rank * rps3), min(n3, (rank + 1) * rps3)
+        shard3 = m.EmbeddingStore(dim, max(hi3 - lo3, 1), dev)
+        if hi3 > lo3:
+            shard3.append(db[lo3:hi3], normalise=False)
+        shard3.set_groups(groups[lo3:hi3])
+        retr3 = m.ShardedRetriever(shard3, rank, world, rps3, exchange=xchg)
+        assert (len(shard3) == 0) == (rank == world - 1)
+        for nq3, path in ((1, "auto"), (3, "stream_f32"), (150, "auto")):
+            r = retr3.search(torch.from_numpy(q[:nq3]).to(dev), k, path=path, exclude_group=torch.from_numpy(excl[:nq3]).to(dev),
+                             certify=True)
+            rd, ri = fs.flat_search(db[:n3], q[:nq3], k, "l2", groups[:n3], excl[:nq3])
+            compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db[:n3], q[:nq3])
+        shard3.close()
+
+    # a peer that never publishes: the wait is bounded, the error is readable, the ranks re-synchronise
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank != 0:
+        r = shard.search(torch.from_numpy(q[:2]).to(dev), k, path="stream_f32", index_base=rank * rps,
+                         exchange=xchg.next(timeout_ms=300))
+        torch.cuda.synchronize()
+        assert bool((r.index == -1).all())
+        try:
+            shard.poll_error()
+        except m.MragError as e:
+            assert "timed out" in str(e)
+        else:
+            raise AssertionError("a missing peer must surface as an error")
+        shard.poll_error()          # cleared by the first poll
+    xchg.reset()
+    r = retr.search(torch.from_numpy(q[:5]).to(dev), k, certify=True)
+    rd, ri = fs.flat_search(db, q[:5], k)
+    compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[:5])
+    shard.poll_error()
 
     # row-sharded feature table read through peer pointers
     L, C, K = 25, 1024, 9

@@ -75,6 +75,28 @@ def test_gather_reads_row_sharded_tables_through_pointer_table(libmrag):
     assert torch.equal(x.cpu(), want)
 
 
+def test_gather_never_dereferences_rows_past_the_table(libmrag):
+    """A short last shard: indices inside its nominal range but beyond the rows the table really has (or
+    stale ones) select the uncond row; validate=True raises instead."""
+    from motionrag_b200 import FeatureTable, gather_context
+    L, C, rps = 25, 1024, 64
+    g = torch.Generator().manual_seed(4)
+    full = torch.randn(rps + 10, L, C, generator=g).to(torch.bfloat16)           # second shard holds 10 rows only
+    s0, s1 = full[:rps].contiguous().cuda(), full[rps:].contiguous().cuda()
+    ft = FeatureTable(s0, rows_per_shard=rps, shard_rank=0, n_shards=2, n_rows=rps + 10)
+    ft.set_peer_ptr(1, s1.data_ptr())
+    un = torch.randn(L, C, generator=g).to(torch.bfloat16)
+    idx = torch.tensor([[3, rps + 9, rps + 10, 127], [10_000_000, 0, -1, rps]])
+    x = gather_context(ft, idx.cuda(), full[5].cuda(), un.cuda())
+    safe = torch.where(idx >= rps + 10, torch.full_like(idx, -1), idx)
+    want = cc.context_restatement(cc.gather_restatement(full, safe, un), full[5][None], None, None)
+    assert torch.equal(x.cpu(), want)
+    with pytest.raises(IndexError):
+        gather_context(ft, idx.cuda(), full[5].cuda(), un.cuda(), validate=True)
+    with pytest.raises(ValueError):
+        FeatureTable(s0, rows_per_shard=rps, shard_rank=0, n_shards=2, n_rows=3 * rps)
+
+
 def test_gather_argument_checks(libmrag):
     from motionrag_b200 import FeatureTable, gather_context
     ft = FeatureTable(torch.zeros(4, 25, 1024, dtype=torch.bfloat16).cuda())

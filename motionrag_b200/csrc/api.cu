@@ -69,6 +69,7 @@ struct mrag_store {
   // device-side errors (a peer exchange that timed out): one word in mapped pinned host memory
   int* err_host = nullptr;
   int* err_dev = nullptr;
+  unsigned long long* stamps = nullptr;  // profiling only (MRAG_K3_STAMPS=1): 16 globaltimer stamps
   // scratch of the host-buffer entry point (mrag_search_host): grown on demand, reused
   mutable std::mutex host_mu;
   mutable char* host_dev = nullptr;
@@ -115,6 +116,7 @@ struct Knobs {
   bool k2_kc32;          // MRAG_K2_KC=32: long candidate lists in K2
   bool k1_fuse;          // MRAG_K1_FUSE=0: single-query scans launch K3 separately (A/B runs)
   long long xchg_timeout_ms;  // MRAG_XCHG_TIMEOUT_MS: bound of the peer-exchange flag wait
+  bool k3_stamps;        // MRAG_K3_STAMPS=1: mrag_search_timed prints the phase timeline of query 0
 };
 const Knobs& knobs() {
   static const Knobs k = [] {
@@ -128,6 +130,8 @@ const Knobs& knobs() {
     e = getenv("MRAG_XCHG_TIMEOUT_MS");
     v.xchg_timeout_ms = e ? atoll(e) : 10000;
     if (v.xchg_timeout_ms < 1) v.xchg_timeout_ms = 1;
+    e = getenv("MRAG_K3_STAMPS");
+    v.k3_stamps = e && e[0] == '1';
     return v;
   }();
   return k;
@@ -312,6 +316,7 @@ int mrag_store_destroy(mrag_store* s) {
   cudaFree(s->groups);
   cudaFree(s->row_bias);
   cudaFree(s->tickets);
+  cudaFree(s->stamps);
   if (s->err_host) cudaFreeHost(s->err_host);
   s->drop_host_graphs();
   if (s->host_stream) cudaStreamDestroy(s->host_stream);
@@ -487,6 +492,13 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
     kp.x.timeout_ns = static_cast<unsigned long long>(ms) * 1000000ull;
     kp.x.err_word = s->err_dev;
   }
+  if (knobs().k3_stamps && before_scan != nullptr) {  // only the timed entry point profiles
+    mrag_store* ms = const_cast<mrag_store*>(s);
+    if (!ms->stamps) CK(cudaMalloc(&ms->stamps, 16 * 8));
+    CK(cudaMemsetAsync(ms->stamps, 0, 16 * 8, st));
+    CK(cudaMemsetAsync(ms->stamps, 0xff, 8, st));  // [0] is an atomicMin target
+    kp.stamps = ms->stamps;
+  }
   if (!k3_params_ok(kp, nq)) return fail(MRAG_ERR_ARG, "unsupported K3 shape (runs %d x %d, rerank %d, k %d)",
                                          kp.n_runs, kp.run_len, kp.rerank, kp.k);
   // pre-filter: applied inside the scan (rows of the excluded group never enter a list)
@@ -585,6 +597,14 @@ int mrag_search_timed(const mrag_store* s, const float* queries_dev, int32_t nq,
     cudaEventElapsedTime(&b, e0, e3);
     if (scan_ms_out) *scan_ms_out = a;
     if (total_ms_out) *total_ms_out = b;
+    if (knobs().k3_stamps && s->stamps) {
+      unsigned long long h[16];
+      cudaMemcpy(h, s->stamps, sizeof(h), cudaMemcpyDeviceToHost);
+      auto us = [&](int i) { return h[i] ? double(h[i] - h[0]) / 1e3 : -1.0; };
+      fprintf(stderr, "[k3 stamps us from first CTA start] last CTA done streaming %.1f | tail enters %.1f | k3 start %.1f | "
+              "heads+T %.1f | compact+sort %.1f | rerank %.1f | sorted %.1f | tail done %.1f | events: scan %.1f total %.1f\n",
+              us(1), us(2), us(3), us(4), us(5), us(6), us(7), us(8), a * 1e3, b * 1e3);
+    }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

@@ -102,6 +102,71 @@ __device__ __forceinline__ void rank_sort_smem(const uint64_t* keys, uint64_t* o
   __syncthreads();
 }
 
+// ---- warp-level sorted lists of u64 keys (one key per lane, registers + shuffles only) ----------
+// ascending bitonic sort across the warp
+__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t key, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool up = (lane & k) == 0;     // this k-block sorts ascending
+      const bool lower = (lane & j) == 0;  // this lane keeps the smaller of the pair when ascending
+      const uint64_t lo = key < other ? key : other;
+      const uint64_t hi = key < other ? other : key;
+      key = (lower == up) ? lo : hi;
+    }
+  }
+  return key;
+}
+// a: sorted ascending across lanes; b_rev: lane l holds element 31-l of another ascending list.
+// min(a[l], b[31-l]) is a bitonic sequence holding the 32 smallest keys of the union; five
+// compare-exchange steps sort it: the result is the sorted list of the 32 best keys of both lists.
+__device__ __forceinline__ uint64_t warp_merge_keep32(uint64_t a, uint64_t b_rev, int lane) {
+  uint64_t c = a < b_rev ? a : b_rev;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, c, j);
+    const uint64_t lo = c < other ? c : other;
+    const uint64_t hi = c < other ? other : c;
+    c = ((lane & j) == 0) ? lo : hi;
+  }
+  return c;
+}
+// The 32 smallest of n <= 1024 keys, sorted, for a block of NT threads: every warp sorts the groups
+// of 32 keys it owns and folds them into one list, warp 0 folds the per-warp lists. `lists` is
+// shared scratch of NT keys; on return lists[0..32) holds the result (kEmptyKey-padded). Two block
+// barriers; key_at(i) is called once per key (it may load from global memory: a warp's loads are
+// all issued before its first sort).
+template <int NT, typename KeyFn>
+__device__ __forceinline__ void block_top32(KeyFn key_at, int n, uint64_t* lists) {
+  constexpr int NW = NT / 32;
+  constexpr int MAXG = (1024 / 32 + NW - 1) / NW;  // groups per warp at n = 1024
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t kk[MAXG];
+#pragma unroll
+  for (int u = 0; u < MAXG; ++u) {
+    const int i = (warp + u * NW) * 32 + lane;
+    kk[u] = (i < n) ? key_at(i) : kEmptyKey;
+  }
+  uint64_t acc = kEmptyKey;
+#pragma unroll
+  for (int u = 0; u < MAXG; ++u) {
+    if ((warp + u * NW) * 32 < n) {  // warp-uniform
+      const uint64_t sorted = warp_sort_u64(kk[u], lane);
+      acc = (u == 0) ? sorted : warp_merge_keep32(acc, __shfl_sync(0xffffffffu, sorted, 31 - lane), lane);
+    }
+  }
+  lists[threadIdx.x] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    const int used = min(NW, (n + 31) / 32);
+    for (int w = 1; w < used; ++w) acc = warp_merge_keep32(acc, lists[w * 32 + 31 - lane], lane);
+    lists[lane] = acc;
+  }
+  __syncthreads();
+}
+
 // ---- mbarrier / TMA / tcgen05 wrappers ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

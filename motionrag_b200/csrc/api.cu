@@ -162,6 +162,9 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
   if (p->metric < 0 || p->metric > 2) return fail(MRAG_ERR_ARG, "unknown metric %d", p->metric);
   if (p->filter_mode < 0 || p->filter_mode > 2)
     return fail(MRAG_ERR_ARG, "unknown filter_mode %d", p->filter_mode);
+  if (p->list_len != 0 && p->list_len != 16 && p->list_len != 32)
+    return fail(MRAG_ERR_ARG, "list_len must be 0, 16 or 32 (got %d)", p->list_len);
+  if (p->list_len == 16 && p->k > 16) return fail(MRAG_ERR_ARG, "list_len 16 cannot serve k = %d", p->k);
   // an empty shard of a row-sharded table still takes part in the exchange (it publishes nothing)
   if (s->n_rows < 1 && !sharded) return fail(MRAG_ERR_ARG, "store is empty");
   // The scan ranks by q.d. Squared L2 orders like q.d - |d|^2 / 2, so for l2 the per-row term is
@@ -195,7 +198,7 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
                   "streaming path needs dim in {256,512,768,1024} (dim=%d)", s->dim);
     const bool f32 = (path == MRAG_PATH_STREAM_F32);
     if (f32) {
-      pl.kc = (p->k <= 12) ? 16 : 32;
+      pl.kc = p->list_len ? p->list_len : ((p->k <= 12) ? 16 : 32);
       pl.rerank = pl.kc;
     } else {
       pl.kc = 32;
@@ -212,7 +215,7 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
     // per-run list length: 16 entries when k <= 12 (the reference asks for K+3 = 12), else 32.
     // The shared per-query bound guarantees the global top-KC by bf16 score, not more, so the
     // fp32 re-rank covers at most KC candidates. MRAG_K2_KC=32 forces the long list.
-    pl.kc = (p->k <= 12 && !knobs().k2_kc32) ? 16 : 32;
+    pl.kc = p->list_len ? p->list_len : ((p->k <= 12 && !knobs().k2_kc32) ? 16 : 32);
     pl.rerank = refine > pl.kc ? pl.kc : refine;
     // more than one query tile: the CTA-pair kernel (M = 256 per cluster); MRAG_K2_SINGLE=1
     // forces the single-CTA kernel for A/B measurements
@@ -686,7 +689,7 @@ static int search_host_impl(const mrag_store* s, const float* queries_host, int3
     // (the graph bakes in nk-dependent result offsets: nq and k are part of the key)
     for (auto& hg : s->host_graphs)
       if (hg.nq == nq && hg.k == p->k && hg.metric == p->metric && hg.path == p->path &&
-          hg.refine == p->refine && hg.filter_mode == p->filter_mode && hg.has_ex == has_ex &&
+          hg.refine == p->refine + 1000 * p->list_len && hg.filter_mode == p->filter_mode && hg.has_ex == has_ex &&
           hg.index_base == p->index_base && hg.n_rows == s->n_rows && hg.world == world &&
           hg.rank == rank && hg.xbufs == xbufs)
         exec = hg.exec;
@@ -717,7 +720,7 @@ static int search_host_impl(const mrag_store* s, const float* queries_host, int3
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
       if (s->host_graphs.size() >= 64) s->drop_host_graphs();
-      s->host_graphs.push_back({nq, p->k, p->metric, p->path, p->refine, p->filter_mode, has_ex, world, rank,
+      s->host_graphs.push_back({nq, p->k, p->metric, p->path, p->refine + 1000 * p->list_len, p->filter_mode, has_ex, world, rank,
                                 p->index_base, s->n_rows, xbufs, exec});
     }
     e = cudaGraphLaunch(exec, hs);

@@ -170,10 +170,10 @@ class ShardedRetriever:
 
     # default (product) implementations ------------------------------------------------------
     def _cuda_search(self, queries, k, metric, path, refine, exclude_group, filter_mode, index_base, out,
-                     certify=False):
+                     certify=False, list_len=0):
         return self.store.search(queries, k, metric=metric, path=path, refine=refine,
                                  exclude_group=exclude_group, filter_mode=filter_mode,
-                                 index_base=index_base, out=out, certify=certify)
+                                 index_base=index_base, out=out, certify=certify, list_len=list_len)
 
     @staticmethod
     def _cuda_merge(dist_v, idx_v, grp_v, k_out, exclude_group, filter_mode, stride):
@@ -191,14 +191,14 @@ class ShardedRetriever:
 
     def search(self, queries: torch.Tensor, k: int, *, metric: str = "l2", path: str = "auto",
                refine: int = 0, exclude_group: torch.Tensor | None = None,
-               filter_mode: str = "post", certify: bool = False) -> SearchResult:
+               filter_mode: str = "post", certify: bool = False, list_len: int = 0) -> SearchResult:
         """Same contract as EmbeddingStore.search, over the union of all shards. Every rank
         passes the same queries and gets the same (global-index) result; with certify the
         exactness margin of the GLOBAL result (see mrag.h) comes back in `.margin`."""
+        extra = {**({"certify": True} if certify else {}), **({"list_len": list_len} if list_len else {})}
         if self.world == 1:   # one shard: the local search already is the answer (no exchange)
             return self._local_search(queries, k, metric, path, refine, exclude_group,
-                                      filter_mode if exclude_group is not None else "none", 0, None,
-                                      **({"certify": True} if certify else {}))
+                                      filter_mode if exclude_group is not None else "none", 0, None, **extra)
         nq = queries.shape[0]
         self._validate(nq, k, path)
         if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
@@ -206,7 +206,7 @@ class ShardedRetriever:
                                      exclude_group=exclude_group,
                                      filter_mode=filter_mode if exclude_group is not None else "none",
                                      index_base=self.rank * self.rows_per_shard,
-                                     exchange=self.exchange.next(), certify=certify)
+                                     exchange=self.exchange.next(), certify=certify, list_len=list_len)
         lay = PackedLayout(nq, k)
         key = (nq, k)
         if key not in self._bufs:
@@ -219,8 +219,7 @@ class ShardedRetriever:
         local_filter = "pre" if (filter_mode == "pre" and exclude_group is not None) else "none"
         local = self._local_search(queries, k, metric, path, refine,
                                    exclude_group if local_filter == "pre" else None, local_filter,
-                                   self.rank * self.rows_per_shard, local,
-                                   **({"certify": True} if certify else {}))
+                                   self.rank * self.rows_per_shard, local, **extra)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         dv, gv, iv = lay.views(recv, self.world)
         out = self._merge(dv, iv, gv, k, exclude_group,
@@ -235,7 +234,7 @@ class ShardedRetriever:
         return out
 
     def search_host(self, queries, k: int, *, metric: str = "l2", path: str = "auto", refine: int = 0,
-                    exclude_group=None, filter_mode: str = "post", certify: bool = False):
+                    exclude_group=None, filter_mode: str = "post", certify: bool = False, list_len: int = 0):
         """Host buffers in, host buffers out (numpy), every rank with the same queries: the
         reference-facing entry of a row-sharded table. With a PeerExchange small calls replay ONE
         captured graph per rank (H2D copy, scan, fused select / exchange / merge writing straight to
@@ -244,17 +243,17 @@ class ShardedRetriever:
         q = np.ascontiguousarray(queries, dtype=np.float32)
         nq = q.shape[0]
         if self.world == 1:
-            return self.store.search_host(q, k, metric=metric, path=path, refine=refine,
-                                          exclude_group=exclude_group, filter_mode=filter_mode, certify=certify)
+            return self.store.search_host(q, k, metric=metric, path=path, refine=refine, exclude_group=exclude_group,
+                                          filter_mode=filter_mode, certify=certify, list_len=list_len)
         self._validate(nq, k, path)
         if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
             return self.store.search_host(q, k, metric=metric, path=path, refine=refine,
                                           exclude_group=exclude_group, filter_mode=filter_mode,
                                           index_base=self.rank * self.rows_per_shard, certify=certify,
-                                          exchange=self.exchange.next())
+                                          exchange=self.exchange.next(), list_len=list_len)
         ex = None if exclude_group is None else torch.from_numpy(np.ascontiguousarray(exclude_group, dtype=np.int32)).to(self.device)
         r = self.search(torch.from_numpy(q).to(self.device), k, metric=metric, path=path, refine=refine,
-                        exclude_group=ex, filter_mode=filter_mode, certify=certify)
+                        exclude_group=ex, filter_mode=filter_mode, certify=certify, list_len=list_len)
         out = (r.distance.cpu().numpy(), r.index.cpu().numpy(), r.group.cpu().numpy())
         return out + ((r.margin.cpu().numpy(),) if certify else ())
 

@@ -97,7 +97,8 @@ class RAGDatabase:
         self._ctor = dict(device=str(device), metric=metric, prefilter=prefilter, normalise=normalise,
                           path=path, recheck=recheck)
         self.recheck = recheck
-        self.fp32_rechecks = 0
+        self.fp32_rechecks = 0      # queries answered from the fp32 master rows after their margin failed
+        self.deep_rechecks = 0      # queries re-issued with 32-entry candidate lists first
         self.embed_fn = embed_fn
         self.metric, self.prefilter, self.path = metric, prefilter, path
         dev = torch.device(device) if not isinstance(device, torch.device) else device
@@ -124,7 +125,7 @@ class RAGDatabase:
     def _init_caches(self) -> None:
         self._group_col: str | None = None
         self._group_ids: dict[str, dict] = {}
-        self._thr_cache: dict[tuple, float] = {}
+        self._thr_cache: dict[tuple, tuple] = {}
         self._where_cache: dict[str, tuple[str, int]] = {}   # SQL string -> (column, group id)
         self._col_lists: dict[str, list] = {}                # scalar columns as Python lists (record building)
 
@@ -144,7 +145,7 @@ class RAGDatabase:
         self.metric, self.prefilter = kw.get("metric", "l2"), kw.get("prefilter", False)
         self.path = kw.get("path", "auto")
         self.recheck = kw.get("recheck", "auto")
-        self.fp32_rechecks = 0
+        self.fp32_rechecks = self.deep_rechecks = 0
         self.device = store.device
         self._from_memory = True
         self._columns = {k: _as_column(v) for k, v in columns.items() if k not in VECTOR_COLUMNS}
@@ -395,7 +396,7 @@ class RAGDatabase:
             pos += n
         return out
 
-    def _search(self, vector, vector_column_name, top_k, where, refine_factor):
+    def _search(self, vector, vector_column_name, top_k, where, refine_factor, exclude_group=None):
         """-> (distance f32 [nq,k], index i64 [nq,k]) numpy arrays, single?
 
         Every bf16 scan is certified: the kernels report the exactness margin of each query (mrag.h)
@@ -406,7 +407,8 @@ class RAGDatabase:
         refine = int(min(64, max(top_k, top_k * max(1, int(refine_factor)))))
         mode = "pre" if self.prefilter else "post"
         q, single = self._as_host_queries(vector)
-        excl = self._exclusion_ids(where, q.shape[0])
+        excl = self._exclusion_ids(where, q.shape[0]) if exclude_group is None else \
+            np.ascontiguousarray(exclude_group, dtype=np.int32)
         certify = self.recheck is not None and self.path != "stream_f32"
         searcher = self._retriever if self._retriever is not None else store
         res = searcher.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
@@ -416,23 +418,29 @@ class RAGDatabase:
             self._recheck(searcher, store, q, excl, dist, idx, res[3], top_k, mode)
         return dist, idx, single
 
-    def _margin_threshold(self, store, nq: int, top_k: int) -> float:
+    def _scan_profile(self, store, nq: int, top_k: int) -> tuple[str, int, float]:
+        """(scan path AUTO resolves to, length of its candidate lists, margin threshold) for this call shape."""
         from .store import PATH_NAME, margin_threshold
         key = (id(store), nq == 1, int(top_k))
-        thr = self._thr_cache.get(key)
-        if thr is None:
-            if len(store) == 0:
-                used = "tensor_bf16"
+        prof = self._thr_cache.get(key)
+        if prof is None:
+            if len(store) == 0:      # an empty shard of a sharded table: same resolution rules, nothing to plan
+                used = "stream_bf16" if (nq == 1 and self.path in ("auto", "stream_bf16")) else "tensor_bf16"
+                rerank = 32 if used == "stream_bf16" or top_k > 12 else 16
             else:
-                used = PATH_NAME[store.plan(nq, k=int(top_k), path=self.path).path]   # the path AUTO resolves to
-            thr = self._thr_cache[key] = margin_threshold(used, store.dim, self.recheck == "strict",
-                                                          store.info().max_norm_deviation)
-        return thr
+                plan = store.plan(nq, k=int(top_k), path=self.path)
+                used, rerank = PATH_NAME[plan.path], int(plan.rerank)
+            thr = margin_threshold(used, store.dim, self.recheck == "strict", store.info().max_norm_deviation)
+            prof = self._thr_cache[key] = (used, rerank, thr)
+        return prof
 
     def _recheck(self, searcher, store, q, excl, dist, idx, margin, top_k, mode) -> None:
-        """Queries whose bf16-scan result is not certified exact (margin <= threshold, see mrag.h) are
-        re-run on the fp32 master rows, 4 per pass; results are patched in place."""
-        thr = self._margin_threshold(store, q.shape[0], top_k)
+        """Queries whose bf16-scan result is not certified exact (margin <= threshold, see mrag.h) are re-run
+        and patched in place, in two stages: (1) tensor-path queries that kept 16 candidates are re-issued
+        together with 32-entry lists — the k-th result is then compared with the 32nd instead of the 16th best
+        scan score, which certifies almost all of them at a fraction of a full-batch scan; (2) what is still
+        in doubt is answered from the fp32 master rows (4 queries per pass over the table)."""
+        used, rerank, thr = self._scan_profile(store, q.shape[0], top_k)
         if q.shape[0] == 1:
             if margin[0] > thr:
                 return
@@ -441,12 +449,39 @@ class RAGDatabase:
             doubt = np.nonzero(~(margin > thr))[0]          # NaN counts as doubt
             if doubt.size == 0:
                 return
+        ex = (lambda rows: None if excl is None else excl[rows])
+        if used == "tensor_bf16" and rerank < 32 and top_k < 32:
+            self.deep_rechecks += int(doubt.size)
+            r2 = searcher.search_host(q[doubt], int(top_k), metric=self.metric, path="tensor_bf16", list_len=32,
+                                      exclude_group=ex(doubt), filter_mode=mode, certify=True)
+            dist[doubt], idx[doubt] = r2[0], r2[1]
+            from .store import margin_threshold
+            thr2 = margin_threshold("tensor_bf16", store.dim, self.recheck == "strict", store.info().max_norm_deviation)
+            doubt = doubt[~(r2[3] > thr2)]
         self.fp32_rechecks += int(doubt.size)
         for s in range(0, doubt.size, 4):
             rows = doubt[s:s + 4]
             r2 = searcher.search_host(q[rows], int(top_k), metric=self.metric, path="stream_f32",
-                                      exclude_group=None if excl is None else excl[rows], filter_mode=mode)
+                                      exclude_group=ex(rows), filter_mode=mode)
             dist[rows], idx[rows] = r2[0], r2[1]
+
+    def search_arrays(self, vectors, top_k: int = 10, where: Sequence[str | None] | str | None = None,
+                      refine_factor: int = 30, vector_column_name: str = "text_embedding", batch: int = 4096,
+                      exclude_group=None):
+        """The certified search without record building: -> (distance f32 [nq, k], index i64 [nq, k]) numpy
+        arrays (unused slots +inf / -1). Same scans, filters and re-checks as search_batch. `exclude_group`
+        (int32 [nq], -1 = none) may replace `where` when the caller already holds the group ids the store
+        was given with set_groups."""
+        q_all, _ = self._as_host_queries(vectors)
+        wheres = None if where is None else ([where] * q_all.shape[0] if isinstance(where, str) else list(where))
+        ds, is_ = [], []
+        for s in range(0, q_all.shape[0], batch):
+            w = None if wheres is None else wheres[s:s + batch]
+            d, i, _ = self._search(q_all[s:s + batch], vector_column_name, top_k, w, refine_factor,
+                                   None if exclude_group is None else exclude_group[s:s + batch])
+            ds.append(d)
+            is_.append(i)
+        return np.concatenate(ds), np.concatenate(is_)
 
     def vector_search(self, vector, vector_column_name: str = None, top_k: int = 10, table=None,
                       where: str = None, select: list[str] = None, nprobes: int = 50, refine_factor: int = 30,

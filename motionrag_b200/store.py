@@ -182,9 +182,9 @@ class EmbeddingStore:
         return _view(inf.rows_bf16_dev, (int(inf.n_rows), self.dim), torch.bfloat16, self.device, self)
 
     # -- search -----------------------------------------------------------------------------
-    def _params(self, k, metric, path, refine, filter_mode, index_base) -> SearchParams:
+    def _params(self, k, metric, path, refine, filter_mode, index_base, list_len=0) -> SearchParams:
         return SearchParams(k=int(k), metric=METRIC[metric], path=PATH[path], refine=int(refine),
-                            filter_mode=FILTER[filter_mode], reserved=0, index_base=int(index_base),
+                            filter_mode=FILTER[filter_mode], list_len=int(list_len), index_base=int(index_base),
                             out_margin=None)
 
     def plan(self, nq: int, params: SearchParams | None = None, **kw) -> PlanInfo:
@@ -192,7 +192,7 @@ class EmbeddingStore:
         if params is None:
             params = self._params(kw.get("k", 12), kw.get("metric", "l2"), kw.get("path", "auto"),
                                   kw.get("refine", 0), kw.get("filter_mode", "none"),
-                                  kw.get("index_base", 0))
+                                  kw.get("index_base", 0), kw.get("list_len", 0))
         info = PlanInfo()
         check(self._lib.mrag_search_plan(self._h, int(nq), C.byref(params), C.byref(info)))
         return info
@@ -201,7 +201,7 @@ class EmbeddingStore:
                refine: int = 0, exclude_group: torch.Tensor | None = None,
                filter_mode: str = "post", index_base: int = 0,
                out: SearchResult | None = None, timings: list | None = None,
-               exchange=None, certify: bool = False) -> SearchResult:
+               exchange=None, certify: bool = False, list_len: int = 0) -> SearchResult:
         """Device-resident search: queries [nq, dim] fp32 on this store's GPU -> SearchResult.
 
         Asynchronous on the current stream; nothing is copied to the host.
@@ -213,8 +213,8 @@ class EmbeddingStore:
             filter_mode = "none"
         elif exclude_group.device != self.device or exclude_group.dtype != torch.int32:
             raise ValueError("exclude_group must be int32 on the store's device")
-        p = self._params(k, metric, path, refine, filter_mode, index_base)
-        key = (nq, k, metric, path, refine, filter_mode, exchange is not None)
+        p = self._params(k, metric, path, refine, filter_mode, index_base, list_len)
+        key = (nq, k, metric, path, refine, filter_mode, exchange is not None, list_len)
         need = self._need.get(key)
         if need is None:
             if exchange is not None and len(self) == 0:
@@ -271,7 +271,8 @@ class EmbeddingStore:
 
     def search_host(self, queries: np.ndarray, k: int, *, metric: str = "l2", path: str = "auto",
                     refine: int = 0, exclude_group: np.ndarray | None = None,
-                    filter_mode: str = "post", index_base: int = 0, certify: bool = False, exchange=None):
+                    filter_mode: str = "post", index_base: int = 0, certify: bool = False, exchange=None,
+                    list_len: int = 0):
         """Host-buffer search through `mrag_search_host` (copies inside, synchronous); with
         `exchange` (an mrag_exchange descriptor) the row-sharded variant whose last kernel merges the
         shards over peer memory (`mrag_search_sharded_host`).
@@ -288,7 +289,7 @@ class EmbeddingStore:
             filter_mode = "none"
         else:
             ex = np.ascontiguousarray(exclude_group, dtype=np.int32)
-        p = self._params(k, metric, path, refine, filter_mode, index_base)
+        p = self._params(k, metric, path, refine, filter_mode, index_base, list_len)
         dist = np.empty((nq, k), dtype=np.float32)
         idx = np.empty((nq, k), dtype=np.int64)
         grp = np.empty((nq, k), dtype=np.int32)

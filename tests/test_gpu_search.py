@@ -233,7 +233,7 @@ def test_uncertified_queries_fall_back_to_the_fp32_scan():
     others = rng.choice(np.setdiff1d(np.arange(n), twins), 32, replace=False)
     qb = np.concatenate([np.stack([base * s for s in (3, 5, 7, 9, 11, 13, 15, 17)]), db[others] * 6]).astype(np.float32)
     res = rdb.search_batch(qb, top_k=12, select=["video"])
-    assert rdb.fp32_rechecks == 1 + 8
+    assert rdb.fp32_rechecks == 1 + 8 and rdb.deep_rechecks == 8      # deeper lists cannot separate 200 twins either
     rd, ri = fs.flat_search(db, qb, 12)
     got_i = np.array([[int(r["video"][1:]) for r in rr] for rr in res])
     got_d = np.array([[r["_distance"] for r in rr] for rr in res])
@@ -242,6 +242,37 @@ def test_uncertified_queries_fall_back_to_the_fp32_scan():
     assert [rr[0]["video"] for rr in res[8:]] == [f"v{j}" for j in others]
     for j in range(8):
         assert len(set(ri[j].tolist()) & set(got_i[j].tolist())) >= 10
+    st.close()
+
+
+def test_deeper_lists_certify_what_sixteen_candidates_cannot():
+    """20 near-duplicates around the query: with 16-entry lists the 12th and the 16th best are both twins (margin ~ 0),
+    with 32-entry lists the 32nd best is an ordinary row far away -> the re-issue with list_len = 32 certifies the
+    query and the fp32 scan is never needed; the twins themselves are resolved by the exact fp32 re-rank."""
+    from motionrag_b200 import EmbeddingStore, RAGDatabase
+    from motionrag_b200.store import eps_typical
+    rng = np.random.default_rng(5)
+    n, dim = 5000, 768
+    base = fs.normalise_rows(rng.standard_normal((1, dim)).astype(np.float32))[0]
+    db = fs.normalise_rows(rng.standard_normal((n, dim)).astype(np.float32))
+    twins = rng.choice(n, 20, replace=False)
+    db[twins] = fs.normalise_rows(base[None] + 3e-2 / np.sqrt(dim) * rng.standard_normal((20, dim)).astype(np.float32))
+    others = np.setdiff1d(np.arange(n), twins)[:7]
+    qb = np.concatenate([(base * 6)[None], db[others] * 5]).astype(np.float32)
+    st = EmbeddingStore(dim, n, 0)
+    st.append(db, normalise=False)
+    thr = eps_typical("tensor_bf16", dim)
+    m16 = st.search(torch.from_numpy(qb).cuda(), 12, certify=True).margin.cpu().numpy()
+    m32 = st.search(torch.from_numpy(qb).cuda(), 12, certify=True, list_len=32).margin.cpu().numpy()
+    assert st.plan(8, k=12).rerank == 16 and st.plan(8, k=12, list_len=32).rerank == 32
+    assert m16[0] <= thr < m32[0] and (m16[1:] > thr).all()
+    rdb = RAGDatabase(None, None, columns={"text_embedding": db, "video": np.array([f"v{j}" for j in range(n)])})
+    d, i = rdb.search_arrays(qb, top_k=12)
+    assert rdb.deep_rechecks == 1 and rdb.fp32_rechecks == 0
+    rd, ri = fs.flat_search(db, qb, 12)
+    rep = compare.check_retrieval(d, i, rd, ri, db, qb)
+    assert rep["index_mismatches"] == rep["near_tie_positions"]
+    assert set(i[0].tolist()) <= set(twins.tolist())
     st.close()
 
 

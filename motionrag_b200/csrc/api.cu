@@ -87,6 +87,8 @@ struct mrag_store {
   mutable std::vector<HostGraph> host_graphs;
   mutable cudaStream_t host_stream = nullptr;
   mutable cudaEvent_t host_event = nullptr;
+  mutable bool host_dirty = true;     // work was enqueued on a caller stream that host searches must follow
+  mutable uint32_t host_seq = 0;      // sequence number of the done-flag handshake
   void drop_host_graphs() const {
     for (auto& g : host_graphs) cudaGraphExecDestroy(g.exec);
     host_graphs.clear();
@@ -355,6 +357,7 @@ int mrag_store_append(mrag_store* s, const float* rows, int64_t n, int32_t rows_
   {
     std::lock_guard<std::mutex> lock(s->host_mu);
     s->drop_host_graphs();
+    s->host_dirty = true;
   }
   return MRAG_OK;
 }
@@ -374,6 +377,7 @@ int mrag_store_set_groups(mrag_store* s, const int32_t* groups, int64_t n, int32
   {
     std::lock_guard<std::mutex> lock(s->host_mu);
     s->drop_host_graphs();
+    s->host_dirty = true;
   }
   return MRAG_OK;
 }
@@ -440,7 +444,8 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
                        void* workspace_dev, size_t workspace_bytes, void* stream,
                        cudaEvent_t before_scan, cudaEvent_t after_scan,
                        const mrag_exchange* xchg = nullptr, const uint32_t* epoch_dev = nullptr,
-                       bool in_host_graph = false) {
+                       bool in_host_graph = false, uint32_t* done_flag = nullptr,
+                       const uint32_t* done_seq_dev = nullptr) {
   const bool sharded = xchg != nullptr && xchg->world > 1;
   Plan pl;
   int rc = make_plan(s, nq, p, &pl, sharded);
@@ -479,6 +484,10 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
   kp.out_idx = out_idx_dev;
   kp.out_group = out_group_dev;
   kp.out_margin = p->out_margin;
+  if (nq == 1) {  // one block finishes the search: it can tell the host directly
+    kp.done_flag = done_flag;
+    kp.done_seq_dev = done_seq_dev;
+  }
   if (sharded) {
     if (!xchg->bufs_dev || xchg->rank < 0 || xchg->rank >= xchg->world || xchg->world > 8 ||
         nq > xchg->nq_cap || p->k > xchg->k_cap || xchg->k_cap > 32 || (xchg->epoch == 0 && !epoch_dev))
@@ -658,12 +667,13 @@ static int search_host_impl(const mrag_store* s, const float* queries_host, int3
   void* ws = base + in_bytes + out_bytes;
   mrag_search_params pd = *p;   // device-side view of the parameters (margin pointer swapped)
   // small transfers go through pinned staging (truly asynchronous, one copy each way)
-  const bool staged = (ex_off + ex_raw) <= (256u << 10) && out_raw <= (256u << 10);
+  const bool staged = (ex_off + ex_raw) <= (256u << 10) && out_raw <= (256u << 10) - 64;
   if (staged && s->host_pin_bytes < (512u << 10)) {
     cudaFreeHost(s->host_pin);
     s->host_pin = nullptr;
     s->host_pin_bytes = 0;
     CK(cudaMallocHost(reinterpret_cast<void**>(&s->host_pin), 512u << 10));
+    memset(s->host_pin, 0, 512u << 10);   // (the done flag starts at 0; sequence numbers start at 1)
     s->host_pin_bytes = 512u << 10;
   }
   cudaError_t e;
@@ -675,12 +685,18 @@ static int search_host_impl(const mrag_store* s, const float* queries_host, int3
     memcpy(s->host_pin, queries_host, q_raw);
     // the exchange epoch changes with every call: it travels with the queries and the kernels read
     // it from device memory, so the captured graph stays valid
-    uint32_t epoch = sharded ? xchg->epoch : 0u;
-    memcpy(s->host_pin + q_raw, &epoch, 4);
+    uint32_t hdr[2] = {sharded ? xchg->epoch : 0u, ++s->host_seq};
+    if (s->host_seq == 0) hdr[1] = ++s->host_seq;   // 0 is the flag's initial value
+    memcpy(s->host_pin + q_raw, hdr, 8);
     if (exclude_group_host) memcpy(s->host_pin + ex_off, exclude_group_host, ex_raw);
     char* pin_out = s->host_pin + (256u << 10);
-    CK(cudaEventRecord(s->host_event, st));  // order after the caller's pending work (appends)
-    CK(cudaStreamWaitEvent(hs, s->host_event, 0));
+    // done flag: last 64 bytes of the staging block (results need at most 256 KB - 64: checked by `staged`)
+    volatile uint32_t* done_flag = reinterpret_cast<volatile uint32_t*>(s->host_pin + (512u << 10) - 64);
+    if (s->host_dirty) {   // order after work the caller enqueued on its stream (appends, group uploads)
+      CK(cudaEventRecord(s->host_event, st));
+      CK(cudaStreamWaitEvent(hs, s->host_event, 0));
+      s->host_dirty = false;
+    }
     const int has_ex = (exclude_group_host ? 1 : 0) | (want_margin ? 2 : 0);
     pd.out_margin = want_margin ? reinterpret_cast<float*>(pin_out + nk * 16) : nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -705,7 +721,8 @@ static int search_host_impl(const mrag_store* s, const float* queries_host, int3
                           reinterpret_cast<float*>(pin_out + nk * 8),
                           reinterpret_cast<int64_t*>(pin_out),
                           reinterpret_cast<int32_t*>(pin_out + nk * 12), ws, pl.total, hs, nullptr,
-                          nullptr, sharded ? xchg : nullptr, sharded ? epoch_d : nullptr, true);
+                          nullptr, sharded ? xchg : nullptr, sharded ? epoch_d : nullptr, true,
+                          const_cast<uint32_t*>(done_flag), epoch_d + 1);
       cudaGraph_t graph = nullptr;
       cudaError_t e2 = cudaStreamEndCapture(hs, &graph);
       if (crc != MRAG_OK) {
@@ -724,7 +741,20 @@ static int search_host_impl(const mrag_store* s, const float* queries_host, int3
                                 p->index_base, s->n_rows, xbufs, exec});
     }
     e = cudaGraphLaunch(exec, hs);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(hs);
+    if (e == cudaSuccess && nq == 1) {
+      // single query: the finishing block stores the call's sequence number to the done flag right after
+      // the results (system-scope release): return as soon as it shows up instead of waiting for the
+      // kernel to retire and the driver to notice (~5 us); stream order still protects the next call
+      const uint32_t want = hdr[1];
+      uint32_t spins = 0;
+      while (*done_flag != want) {
+        if ((++spins & 0x3ffu) == 0u && cudaStreamQuery(hs) != cudaErrorNotReady) break;  // finished or failed
+      }
+      if (*done_flag != want) e = cudaStreamSynchronize(hs);
+      else std::atomic_thread_fence(std::memory_order_acquire);
+    } else if (e == cudaSuccess) {
+      e = cudaStreamSynchronize(hs);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "graph launch of the host search");
     // kernels replayed by the graph
     note_launch(pl.path == MRAG_PATH_TENSOR_BF16 ? (sharded && nq > kK3SinglePhaseMax ? 4 : 3) : (pl.fused ? 1 : 2));

@@ -84,6 +84,10 @@ struct K3Params {
   XchgArgs x;
   // profiling only (MRAG_K3_STAMPS=1): globaltimer stamps of the phases of query 0 (see api.cu)
   unsigned long long* stamps;
+  // single-query host calls: once the results are written, the value at *done_seq_dev is stored to
+  // *done_flag (mapped pinned host memory) so the host can return without waiting for the kernel to retire
+  uint32_t* done_flag;
+  const uint32_t* done_seq_dev;
 };
 
 struct K3Smem {
@@ -163,7 +167,8 @@ template <int NT>
 __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t epoch, int q, int k,
                                                   int filter_mode, int exclude, float* out_dist,
                                                   int64_t* out_idx, int32_t* out_group,
-                                                  float* out_margin, K3Smem& sm) {
+                                                  float* out_margin, K3Smem& sm, uint32_t* done_flag = nullptr,
+                                                  const uint32_t* done_seq_dev = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = int(epoch & 1u);
   const size_t rec_bytes = xchg_rec_bytes(x.k_cap);
@@ -192,6 +197,11 @@ __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t ep
       if (out_group) out_group[j] = -1;
     }
     if (tid == 0 && out_margin != nullptr) *out_margin = __int_as_float(0x7fc00000);
+    __syncthreads();
+    if (tid == 0 && done_flag != nullptr) {
+      __threadfence_system();
+      st_release_sys(done_flag, __ldcg(done_seq_dev));
+    }
     return;
   }
   // merge world * k candidates; slot order == global row order among equal distances. Only the k
@@ -262,6 +272,11 @@ __device__ __forceinline__ void k3_exchange_merge(const XchgArgs& x, uint32_t ep
         }
         *out_margin = margin;
       }
+    }
+    if (done_flag != nullptr) {
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) st_release_sys(done_flag, __ldcg(done_seq_dev));
     }
   }
 }
@@ -465,8 +480,14 @@ __device__ __forceinline__ void k3_body(const K3Params& p, int q, K3Smem& sm) {
       }
       *out_margin = margin;
     }
-    if (warp == 0)
+    if (warp == 0) {
       emit_filtered(entry, n_rr, k, p.filter_mode, exclude, out_dist, out_idx, out_group, nullptr, lane);
+      if (p.done_flag != nullptr) {  // results (written by this warp) first, then the flag
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) st_release_sys(p.done_flag, __ldcg(p.done_seq_dev));
+      }
+    }
     return;
   }
 
@@ -499,7 +520,8 @@ __device__ __forceinline__ void k3_body(const K3Params& p, int q, K3Smem& sm) {
   if (tid < x.world)
     st_release_sys(reinterpret_cast<uint32_t*>(x.bufs[tid] + flags_off) + cell, epoch);
   if (x.phase == 1) return;  // the wait + merge runs as its own kernel (large batches)
-  k3_exchange_merge<NT>(x, epoch, q, k, p.filter_mode, exclude, out_dist, out_idx, out_group, out_margin, sm);
+  k3_exchange_merge<NT>(x, epoch, q, k, p.filter_mode, exclude, out_dist, out_idx, out_group, out_margin, sm,
+                        p.done_flag, p.done_seq_dev);
 }
 
 }  // namespace mrag

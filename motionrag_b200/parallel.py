@@ -234,23 +234,25 @@ class ShardedRetriever:
         return out
 
     def search_host(self, queries, k: int, *, metric: str = "l2", path: str = "auto", refine: int = 0,
-                    exclude_group=None, filter_mode: str = "post", certify: bool = False, list_len: int = 0):
+                    exclude_group=None, filter_mode: str = "post", certify: bool = False, list_len: int = 0,
+                    reuse: bool = False):
         """Host buffers in, host buffers out (numpy), every rank with the same queries: the
         reference-facing entry of a row-sharded table. With a PeerExchange small calls replay ONE
         captured graph per rank (H2D copy, scan, fused select / exchange / merge writing straight to
         pinned host memory); otherwise it falls back to device tensors + the NCCL transport."""
         import numpy as np
-        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = queries if (type(queries) is np.ndarray and queries.dtype == np.float32 and queries.flags.c_contiguous) \
+            else np.ascontiguousarray(queries, dtype=np.float32)
         nq = q.shape[0]
         if self.world == 1:
             return self.store.search_host(q, k, metric=metric, path=path, refine=refine, exclude_group=exclude_group,
-                                          filter_mode=filter_mode, certify=certify, list_len=list_len)
+                                          filter_mode=filter_mode, certify=certify, list_len=list_len, reuse=reuse)
         self._validate(nq, k, path)
         if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
             return self.store.search_host(q, k, metric=metric, path=path, refine=refine,
                                           exclude_group=exclude_group, filter_mode=filter_mode,
                                           index_base=self.rank * self.rows_per_shard, certify=certify,
-                                          exchange=self.exchange.next(), list_len=list_len)
+                                          exchange=self.exchange.next(), list_len=list_len, reuse=reuse)
         ex = None if exclude_group is None else torch.from_numpy(np.ascontiguousarray(exclude_group, dtype=np.int32)).to(self.device)
         r = self.search(torch.from_numpy(q).to(self.device), k, metric=metric, path=path, refine=refine,
                         exclude_group=ex, filter_mode=filter_mode, certify=certify, list_len=list_len)

@@ -396,7 +396,7 @@ class RAGDatabase:
             pos += n
         return out
 
-    def _search(self, vector, vector_column_name, top_k, where, refine_factor, exclude_group=None):
+    def _search(self, vector, vector_column_name, top_k, where, refine_factor, exclude_group=None, reuse=False):
         """-> (distance f32 [nq,k], index i64 [nq,k]) numpy arrays, single?
 
         Every bf16 scan is certified: the kernels report the exactness margin of each query (mrag.h)
@@ -411,8 +411,10 @@ class RAGDatabase:
             np.ascontiguousarray(exclude_group, dtype=np.int32)
         certify = self.recheck is not None and self.path != "stream_f32"
         searcher = self._retriever if self._retriever is not None else store
+        # reuse: result arrays are recycled between small calls (the caller builds its records right away)
         res = searcher.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
-                                   exclude_group=excl, filter_mode=mode, certify=certify)
+                                   exclude_group=excl, filter_mode=mode, certify=certify,
+                                   reuse=reuse and q.shape[0] <= 4)
         dist, idx = res[0], res[1]
         if certify:
             self._recheck(searcher, store, q, excl, dist, idx, res[3], top_k, mode)
@@ -492,7 +494,7 @@ class RAGDatabase:
         if output_format not in ("pandas", "pyarrow", "dict", "list"):
             raise ValueError(f'Invalid format: {output_format}')
         db = self if table is None else table
-        dist, idx, single = db._search(vector, vector_column_name, top_k, where, refine_factor)
+        dist, idx, single = db._search(vector, vector_column_name, top_k, where, refine_factor, reuse=True)
         recs = db._records(dist, idx, select)
         if single:
             return self.format_result(recs[0], output_format)

@@ -70,6 +70,7 @@ class EmbeddingStore:
         self._ws: dict[int, torch.Tensor] = {}   # scratch per CUDA stream: searches on different streams may overlap
         self._need: dict[tuple, int] = {}        # workspace bytes per call shape (dropped by append / set_groups)
         self._info: StoreInfo | None = None
+        self._host_calls: dict[tuple, tuple] = {}   # prebuilt parameter blocks + result arrays of small host calls
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -114,6 +115,7 @@ class EmbeddingStore:
         if on_dev and rows.device != self.device:
             rows = rows.to(self.device)
         self._need.clear()
+        self._host_calls.clear()
         self._info = None
         check(self._lib.mrag_store_append(self._h, C.c_void_p(rows.data_ptr()), rows.shape[0],
                                           1 if on_dev else 0, 1 if normalise else 0,
@@ -272,7 +274,7 @@ class EmbeddingStore:
     def search_host(self, queries: np.ndarray, k: int, *, metric: str = "l2", path: str = "auto",
                     refine: int = 0, exclude_group: np.ndarray | None = None,
                     filter_mode: str = "post", index_base: int = 0, certify: bool = False, exchange=None,
-                    list_len: int = 0):
+                    list_len: int = 0, reuse: bool = False):
         """Host-buffer search through `mrag_search_host` (copies inside, synchronous); with
         `exchange` (an mrag_exchange descriptor) the row-sharded variant whose last kernel merges the
         shards over peer memory (`mrag_search_sharded_host`).
@@ -280,7 +282,8 @@ class EmbeddingStore:
         Returns (distance f32 [nq,k], index i64 [nq,k], group i32 [nq,k]) numpy arrays, plus the
         float32 [nq] exactness margin when certify=True.
         """
-        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = queries if (type(queries) is np.ndarray and queries.dtype == np.float32 and queries.flags.c_contiguous) \
+            else np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim != 2 or q.shape[1] != self.dim:
             raise ValueError(f"queries must be [nq, {self.dim}]")
         nq = q.shape[0]
@@ -288,7 +291,34 @@ class EmbeddingStore:
         if exclude_group is None:
             filter_mode = "none"
         else:
-            ex = np.ascontiguousarray(exclude_group, dtype=np.int32)
+            ex = exclude_group if (type(exclude_group) is np.ndarray and exclude_group.dtype == np.int32
+                                   and exclude_group.flags.c_contiguous) else np.ascontiguousarray(exclude_group, dtype=np.int32)
+        if reuse:
+            # small repeated calls (the reference's one-query-per-call pattern): parameter block, result
+            # arrays and argument pointers are built once per call shape; the RETURNED ARRAYS ARE REUSED by
+            # the next call of the same shape (callers consume them immediately)
+            key = (nq, k, metric, path, refine, filter_mode, index_base, list_len, certify, exchange is None)
+            c = self._host_calls.get(key)
+            if c is None:
+                p = self._params(k, metric, path, refine, filter_mode, index_base, list_len)
+                dist = np.empty((nq, k), dtype=np.float32)
+                idx = np.empty((nq, k), dtype=np.int64)
+                grp = np.empty((nq, k), dtype=np.int32)
+                margin = np.empty(nq, dtype=np.float32) if certify else None
+                if certify:
+                    p.out_margin = margin.ctypes.data
+                c = self._host_calls[key] = (p, C.byref(p), dist, idx, grp, margin, dist.ctypes.data, idx.ctypes.data,
+                                             grp.ctypes.data, _stream_ptr(self.device))
+            p, pref, dist, idx, grp, margin, dp, ip, gp, stream = c
+            qp = q.ctypes.data
+            xp = ex.ctypes.data if ex is not None else None
+            if exchange is None:
+                rc = self._lib.mrag_search_host(self._h, qp, nq, pref, xp, dp, ip, gp, stream)
+            else:
+                rc = self._lib.mrag_search_sharded_host(self._h, qp, nq, pref, xp, dp, ip, gp, C.byref(exchange), stream)
+            if rc != 0:
+                check(rc)
+            return (dist, idx, grp, margin) if certify else (dist, idx, grp)
         p = self._params(k, metric, path, refine, filter_mode, index_base, list_len)
         dist = np.empty((nq, k), dtype=np.float32)
         idx = np.empty((nq, k), dtype=np.int64)

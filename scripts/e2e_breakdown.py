@@ -43,7 +43,22 @@ def dev_only(i):
 print("device search + sync            %.4f ms" % med(dev_only))
 print("search_host (C, graph)          %.4f ms" % med(lambda i: st.search_host(qh[i % 64:i % 64 + 1], 12, exclude_group=exh[i % 64:i % 64 + 1])))
 print("search_host certify             %.4f ms" % med(lambda i: st.search_host(qh[i % 64:i % 64 + 1], 12, exclude_group=exh[i % 64:i % 64 + 1], certify=True)))
+import ctypes as C
+from motionrag_b200 import _cabi
+lib = _cabi.load()
+p_ = st._params(12, "l2", "auto", 64, "post", 0)
+dist = np.empty((1, 12), np.float32); idx = np.empty((1, 12), np.int64); grp = np.empty((1, 12), np.int32); mg = np.empty(1, np.float32)
+p_.out_margin = mg.ctypes.data
+stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def raw(i):
+    lib.mrag_search_host(st._h, qh[i % 64:i % 64 + 1].ctypes.data, 1, C.byref(p_), exh[i % 64:i % 64 + 1].ctypes.data,
+                         dist.ctypes.data, idx.ctypes.data, grp.ctypes.data, stream)
+print("raw ctypes mrag_search_host     %.4f ms" % med(raw))
 wh = [f'video != "video_{int(exh[j]):07d}.mp4"' for j in range(64)]
+print("db._search (certified)          %.4f ms" % med(lambda i: db._search(qh[i % 64], "text_embedding", 12, wh[i % 64], 30)))
+d0, i0, _ = db._search(qh[0], "text_embedding", 12, wh[0], 30)
+print("db._records                     %.4f ms" % med(lambda i: db._records(d0, i0, ["video", "start_sec", "end_sec"])))
+print("db._exclusion_ids               %.4f ms" % med(lambda i: db._exclusion_ids(wh[i % 64], 1)))
 print("RAGDatabase.text_search         %.4f ms" % med(lambda i: db.text_search(qh[i % 64], top_k=12, where=wh[i % 64], select=["video", "start_sec", "end_sec"])))
 tm = []
 for i in range(100):

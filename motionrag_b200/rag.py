@@ -7,16 +7,17 @@ runs unchanged. What differs is what executes: the LanceDB flat scan becomes the
 kernels (K1 streaming / K2 tcgen05 scan, K3 merge + fp32 re-score + filter). There is no CPU
 path — constructing the object without a B200-class GPU raises.
 
-On-disk layout read by `RAGDatabase(db_path, table_name)` (written by `save_table`, or by
-tools/export_lancedb.py from a real LanceDB directory on a machine that has lancedb):
-    <db_path>/<table_name>/text_embedding.npy     float32 [N, dim]   (np.load mmap-able)
+On-disk forms `RAGDatabase(db_path, table_name)` opens (motionrag_b200/tables.py):
+    <db_path>/<table_name>/text_embedding.npy     float32 [N, dim]   (np.load mmap-able; `save_table`)
     <db_path>/<table_name>/image_embedding.npy    optional
     <db_path>/<table_name>/columns.parquet        every scalar column of the reference schema
                                                   (tools/build_rag_database.py:35-45)
+    <db_path>/<table_name>.parquet | <table_name>/*.parquet | <table_name>.arrow/.feather/.ipc
+                                                  an Arrow dump of the reference's table itself
+                                                  (`table.to_arrow()`; FixedSizeList<f32>[768] + scalars)
 """
 from __future__ import annotations
 
-import re
 from pathlib import Path
 from typing import Callable, Literal, Sequence
 
@@ -24,6 +25,7 @@ import numpy as np
 import torch
 
 from .store import EmbeddingStore
+from .where import parse as parse_where
 
 VECTOR_COLUMNS = ("text_embedding", "image_embedding")
 
@@ -38,8 +40,6 @@ def _as_2d(v):
     a = np.asarray(v.detach().float().cpu().numpy() if isinstance(v, torch.Tensor) else v, dtype=np.float32)
     return a[None] if a.ndim == 1 else a
 
-
-_WHERE = re.compile(r'^\s*(\w+)\s*!=\s*(["\'])((?:(?!\2).)*)\2\s*$')
 
 
 def save_table(db_path: str | Path, table_name: str, columns: dict) -> Path:
@@ -111,7 +111,7 @@ class RAGDatabase:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._from_memory = columns is not None
         if columns is None:
-            columns = self._load(Path(db_path) / table_name)
+            columns = self._load(db_path, table_name)
         self._columns = {k: _as_column(v) for k, v in columns.items() if k not in VECTOR_COLUMNS}
         self._vectors = {k: columns[k] for k in VECTOR_COLUMNS if k in columns}
         if not self._vectors:
@@ -159,16 +159,11 @@ class RAGDatabase:
 
     # -- loading ------------------------------------------------------------------------------
     @staticmethod
-    def _load(root: Path) -> dict:
-        import pandas as pd
-        if not root.is_dir():
-            raise FileNotFoundError(f"no table directory {root}")
-        cols = {c: v.to_numpy() for c, v in pd.read_parquet(root / "columns.parquet").items()}
-        for name in VECTOR_COLUMNS:
-            f = root / f"{name}.npy"
-            if f.exists():
-                cols[name] = np.load(f, mmap_mode="r")
-        return cols
+    def _load(db_path, table_name) -> dict:
+        """Own layout, a Parquet file / fragment directory or an Arrow IPC file holding the reference's
+        schema (tools/build_rag_database.py:35-45) — see motionrag_b200/tables.py."""
+        from .tables import read_table
+        return read_table(db_path, table_name)
 
     def __len__(self) -> int:
         if self._retriever is not None and self._columns:
@@ -292,49 +287,85 @@ class RAGDatabase:
         q = q.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
         return q, single
 
-    def _where_to_group(self, w: str) -> tuple[str, int]:
-        """One `<column> != "<value>"` clause -> (column, dense group id or -1); parsed once per string."""
+    def _where_to_group(self, w: str):
+        """One where clause -> (column, dense group id or -1) when it is the reference's own shape
+        `<column> != "<value>"` (src/data/datamodule.py:235; runs on the device as an excluded group id), else
+        the parsed `where.Predicate` (evaluated on the host, see motionrag_b200/where.py). Parsed once per string."""
         hit = self._where_cache.get(w)
         if hit is None:
-            m = _WHERE.match(w)
-            if not m:
-                raise ValueError(f"unsupported where clause {w!r}: only `<column> != \"<value>\"` "
-                                 "(src/data/datamodule.py:235) is implemented")
-            col = m.group(1)
-            if col not in self._columns:
-                raise ValueError(f"where clause names unknown column {col!r}")
+            pred = parse_where(w)
+            unknown = pred.columns() - set(self._columns)
+            if unknown:
+                raise ValueError(f"where clause names unknown column {sorted(unknown)[0]!r}")
             if len(self._where_cache) > (1 << 20):
                 self._where_cache.clear()
-            hit = self._where_cache[w] = (col, self._group_ids_lookup(col, m.group(3)))
+            simple = pred.simple_exclusion()
+            hit = self._where_cache[w] = pred if simple is None else (simple[0], self._group_ids_lookup(simple[0], simple[1]))
         return hit
+
+    def _bind_mask(self, pred) -> None:
+        """Pre-filter with a general predicate: rows that fail it form group 1 of a two-group labelling the scan
+        kernels skip (evaluated once over the whole table, cached while the same clause is in use)."""
+        key = ("where", pred.text)
+        if self._group_col != key:
+            ids = (~pred.evaluate(self._columns)).astype(np.int32)
+            for st in self._stores.values():
+                part = ids
+                if self._retriever is not None and self._retriever.world > 1:
+                    lo = self._retriever.rank * self._retriever.rows_per_shard
+                    part = ids[lo:lo + len(st)]
+                st.set_groups(part)
+            self._group_col = key
 
     def _exclusion_ids(self, where, nq: int):
         """`where` is one SQL string (reference form) or one per query (batched form);
-        -> int32 [nq] group ids to exclude (-1 = none) or None."""
+        -> (int32 [nq] group ids to exclude (-1 = none) or None, per-query host predicates or None)."""
         if where is None:
-            return None
-        if isinstance(where, str):
-            col, gid = self._where_to_group(where)
-            ids = np.full(nq, gid, dtype=np.int32)
-        else:
-            wheres = list(where)
-            if len(wheres) != nq:
-                raise ValueError("need one where clause per query")
-            col, ids = None, np.full(nq, -1, dtype=np.int32)
-            for i, w in enumerate(wheres):
-                if w is None:
-                    continue
-                c, gid = self._where_to_group(w)
+            return None, None
+        wheres = [where] * nq if isinstance(where, str) else list(where)
+        if len(wheres) != nq:
+            raise ValueError("need one where clause per query")
+        col, ids, preds = None, np.full(nq, -1, dtype=np.int32), None
+        for i, w in enumerate(wheres):
+            if w is None:
+                continue
+            hit = self._where_to_group(w) if i == 0 or w is not wheres[i - 1] else hit
+            if isinstance(hit, tuple):
+                c, gid = hit
                 if col is None:
                     col = c
                 elif col != c:
-                    raise ValueError("all where clauses of a batch must name the same column")
+                    raise ValueError("all `!=` where clauses of a batch must name the same column")
                 ids[i] = gid
-            if col is None:
-                return None
+            else:
+                if preds is None:
+                    preds = [None] * nq
+                preds[i] = hit
+        if preds is not None and self.prefilter:
+            first = next(p for p in preds if p is not None)
+            if col is not None or any(p is not first for p in preds):
+                raise ValueError("pre-filter mode takes ONE general where clause per batch (or `!=` clauses only)")
+            self._bind_mask(first)
+            return np.ones(nq, dtype=np.int32), None
+        if col is None:
+            return None, preds
         if self._group_col != col:
             self._bind_groups(col)
-        return ids
+        return ids, preds
+
+    def _apply_predicates(self, preds, dist: np.ndarray, idx: np.ndarray) -> None:
+        """Post-filter of general where clauses (LanceDB's `.where()` without prefilter: the k nearest rows are
+        found first, rows failing the predicate are dropped): compacts each query's result in place."""
+        for i, p in enumerate(preds):
+            if p is None:
+                continue
+            valid = idx[i] >= 0
+            rows = idx[i][valid]
+            keep = p.evaluate(self._columns, rows)
+            n = int(keep.sum())
+            d = dist[i][valid][keep]
+            idx[i, :n], idx[i, n:] = rows[keep], -1
+            dist[i, :n], dist[i, n:] = d, np.inf
 
     def _group_ids_lookup(self, col: str, value) -> int:
         g = self._groups_for(col)
@@ -407,8 +438,11 @@ class RAGDatabase:
         refine = int(min(64, max(top_k, top_k * max(1, int(refine_factor)))))
         mode = "pre" if self.prefilter else "post"
         q, single = self._as_host_queries(vector)
-        excl = self._exclusion_ids(where, q.shape[0]) if exclude_group is None else \
-            np.ascontiguousarray(exclude_group, dtype=np.int32)
+        preds = None
+        if exclude_group is None:
+            excl, preds = self._exclusion_ids(where, q.shape[0])
+        else:
+            excl = np.ascontiguousarray(exclude_group, dtype=np.int32)
         certify = self.recheck is not None and self.path != "stream_f32"
         searcher = self._retriever if self._retriever is not None else store
         # reuse: result arrays are recycled between small calls (the caller builds its records right away)
@@ -418,6 +452,8 @@ class RAGDatabase:
         dist, idx = res[0], res[1]
         if certify:
             self._recheck(searcher, store, q, excl, dist, idx, res[3], top_k, mode)
+        if preds is not None:
+            self._apply_predicates(preds, dist, idx)
         return dist, idx, single
 
     def _scan_profile(self, store, nq: int, top_k: int) -> tuple[str, int, float]:

@@ -17,7 +17,8 @@ Grammar (case-insensitive keywords):
     cmp     := = | == | != | <> | < | <= | > | >=
     operand := column | `column` | number | 'string' | "string" | TRUE | FALSE | NULL
 A double-quoted token is a string literal, as in the reference's own clause. NULL (None / NaN cells)
-makes a comparison false; IS [NOT] NULL tests it.
+follows SQL's three-valued logic: a comparison with NULL is unknown, NOT unknown stays unknown, and only
+rows whose predicate is definitely true pass; IS [NOT] NULL tests for it.
 """
 from __future__ import annotations
 
@@ -194,10 +195,13 @@ class Predicate:
 
     def __init__(self, text: str):
         self.text = text
-        p = _Parser(_tokens(text))
-        self.root = p.expr()
-        if p.peek()[0] != "end":
-            raise WhereError(f"unexpected {p.peek()[1]!r} in where clause")
+        try:
+            p = _Parser(_tokens(text))
+            self.root = p.expr()
+            if p.peek()[0] != "end":
+                raise WhereError(f"unexpected {p.peek()[1]!r}")
+        except WhereError as e:
+            raise WhereError(f"unsupported where clause {text!r}: {e}") from None
 
     def columns(self) -> set[str]:
         found: set[str] = set()
@@ -234,65 +238,78 @@ class Predicate:
             return (col if rows is None else col[rows]), None
 
         def compare(op, a, b):
+            """-> (true, false) masks; a NULL on either side leaves both unset (SQL's unknown)."""
             xa, la = value(a)
             xb, lb = value(b)
+            none = np.zeros(n, dtype=bool)
             if xa is None and xb is None:       # literal vs literal
                 if la is None or lb is None:
-                    return np.zeros(n, dtype=bool)
+                    return none, none
                 xa = np.full(n, la)
             if xa is None:                      # literal on the left: mirror
                 op = {"lt": "gt", "le": "ge", "gt": "lt", "ge": "le"}.get(op, op)
                 xa, la, xb, lb = xb, lb, None, la
             null = _is_null(xa)
             if xb is None:
+                if lb is None:
+                    return none, none
                 rhs = _coerce(lb, xa)
-                if rhs is None:
-                    return np.zeros(n, dtype=bool)
-                if isinstance(rhs, str) and xa.dtype.kind not in "OUS":
-                    return np.zeros(n, dtype=bool) if op != "ne" else ~null
+                if rhs is None or (isinstance(rhs, str) and xa.dtype.kind not in "OUS"):
+                    # a text literal that is no number never equals a numeric cell
+                    return (~null, none) if op == "ne" else (none, ~null)
             else:
                 rhs = xb
                 null = null | _is_null(xb)
             lhs = xa
-            if lhs.dtype.kind == "O":
-                safe = np.where(null, rhs if np.ndim(rhs) == 0 else "", lhs) if null.any() else lhs
-                lhs = safe
+            if lhs.dtype.kind == "O" and null.any():
+                lhs = np.where(null, rhs if np.ndim(rhs) == 0 else "", lhs)
             with np.errstate(invalid="ignore"):
                 res = {"eq": lambda: lhs == rhs, "ne": lambda: lhs != rhs, "lt": lambda: lhs < rhs,
                        "le": lambda: lhs <= rhs, "gt": lambda: lhs > rhs, "ge": lambda: lhs >= rhs}[op]()
-            return np.asarray(res, dtype=bool) & ~null
+            res = np.asarray(res, dtype=bool)
+            return res & ~null, ~res & ~null
 
-        def ev(x: Node) -> np.ndarray:
+        def ev(x: Node):
+            """Three-valued evaluation: (definitely true, definitely false); neither = unknown (NULL)."""
             if x.kind == "or":
-                return ev(x.args[0]) | ev(x.args[1])
+                (ta, fa), (tb, fb) = ev(x.args[0]), ev(x.args[1])
+                return ta | tb, fa & fb
             if x.kind == "and":
-                return ev(x.args[0]) & ev(x.args[1])
+                (ta, fa), (tb, fb) = ev(x.args[0]), ev(x.args[1])
+                return ta & tb, fa | fb
             if x.kind == "not":
-                return ~ev(x.args[0])
+                t, f = ev(x.args[0])
+                return f, t
             if x.kind == "const":
-                return np.full(n, bool(x.args[0]))
+                c = np.full(n, bool(x.args[0]))
+                return c, ~c
             if x.kind == "cmp":
                 return compare(*x.args)
             if x.kind == "in":
-                acc = np.zeros(n, dtype=bool)
+                t, f = np.zeros(n, dtype=bool), np.ones(n, dtype=bool)
                 for lit in x.args[1]:
-                    acc |= compare("eq", x.args[0], ("lit", lit))
-                return acc
+                    t1, f1 = compare("eq", x.args[0], ("lit", lit))
+                    t, f = t | t1, f & f1
+                return t, f
             if x.kind == "between":
-                return compare("ge", x.args[0], x.args[1]) & compare("le", x.args[0], x.args[2])
+                (ta, fa), (tb, fb) = compare("ge", x.args[0], x.args[1]), compare("le", x.args[0], x.args[2])
+                return ta & tb, fa | fb
             if x.kind == "isnull":
                 xa, la = value(x.args[0])
-                return np.full(n, la is None) if xa is None else _is_null(xa)
+                t = np.full(n, la is None) if xa is None else _is_null(xa)
+                return t, ~t
             if x.kind == "like":
                 xa, la = value(x.args[0])
                 if xa is None:
                     xa = np.full(n, la, dtype=object)
+                null = _is_null(xa)
                 rx = re.compile("".join(".*" if c == "%" else "." if c == "_" else re.escape(c) for c in x.args[1]) + r"\Z",
                                 re.S)
-                return np.fromiter((isinstance(s, str) and rx.match(s) is not None for s in xa.tolist()), bool, n)
+                hit = np.fromiter((isinstance(s, str) and rx.match(s) is not None for s in xa.tolist()), bool, n)
+                return hit & ~null, ~hit & ~null
             raise WhereError(f"unknown node {x.kind}")
 
-        return ev(self.root)
+        return ev(self.root)[0]
 
 
 _CACHE: dict[str, Predicate] = {}

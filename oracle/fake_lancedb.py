@@ -53,8 +53,7 @@ class FakeQuery:
         t = self.table
         row_group = exclude = None
         if self._where is not None:
-            col, val = fs.parse_where(self._where)
-            row_group = (np.asarray(t.columns[col]).astype(str) == val).astype(np.int64)
+            row_group = (~fs.where_mask(t.columns, self._where)).astype(np.int64)
             exclude = np.array([1])
         dist, idx = fs.flat_search(np.asarray(t.columns[self.column], dtype=np.float32), self.vector[None], self.k,
                                    "l2", row_group, exclude, getattr(self, "_prefilter", False))

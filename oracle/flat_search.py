@@ -137,6 +137,27 @@ def parse_where(where: str | None):
     return m.group(1), m.group(3)
 
 
+def where_mask(columns: dict, where: str) -> np.ndarray:
+    """bool [N]: rows passing an SQL predicate (src/data/rag.py:56-57 hands the string to LanceDB's
+    `.where`). Evaluated by SQLite over the scalar columns — an SQL engine independent of the product's
+    own parser (motionrag_b200/where.py). A double-quoted token that names no column is a string
+    literal there too, which is how the reference's `video != "<name>"` reads."""
+    import sqlite3
+    names = [c for c, v in columns.items() if np.asarray(v).ndim == 1]
+    n = len(np.asarray(columns[names[0]]))
+    con = sqlite3.connect(":memory:")
+    con.execute("create table t(%s)" % ", ".join(f'"{c}"' for c in names))
+    cells = [np.asarray(columns[c]).tolist() for c in names]
+    con.executemany("insert into t values(%s)" % ",".join("?" * len(names)), zip(*cells))
+    try:
+        hits = [r[0] - 1 for r in con.execute(f"select rowid from t where {where}")]
+    except sqlite3.Error as e:
+        raise ValueError(f"unsupported where clause: {where!r} ({e})") from e
+    mask = np.zeros(n, dtype=bool)
+    mask[hits] = True
+    return mask
+
+
 class OracleRAGDatabase:
     """Restatement of `RAGDatabase` (src/data/rag.py:11-80) over an in-memory table:
     `columns` is a dict of equal-length sequences that must contain the vector column."""
@@ -163,12 +184,9 @@ class OracleRAGDatabase:
 
     def vector_search(self, vector, vector_column_name=None, top_k=10, table=None, where=None,
                       select=None, nprobes=50, refine_factor=30, output_format="dict"):
-        pred = parse_where(where)
         row_group = exclude = None
-        if pred is not None:
-            col, val = pred
-            values = np.asarray(self.columns[col])
-            row_group = (values == val).astype(np.int64)  # group 1 = excluded value
+        if where is not None:
+            row_group = (~where_mask(self.columns, where)).astype(np.int64)  # group 1 = rows failing the predicate
             exclude = np.array([1])
         column = vector_column_name or self.vector_column
         mat = self.db if column == self.vector_column else np.asarray(self.columns[column], dtype=np.float32)

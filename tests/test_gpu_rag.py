@@ -53,8 +53,10 @@ def test_text_search_matches_reference_call_pattern(libmrag, table):
     assert db.image_search(table["image_embedding"][77], top_k=4)[0]["id"] == 77
     with pytest.raises(ValueError, match="Invalid format"):
         db.text_search(q, output_format="csv")
-    with pytest.raises(ValueError, match="unsupported where"):
-        db.text_search(q, where="start_sec > 1")
+    with pytest.raises(ValueError, match="where clause"):
+        db.text_search(q, where="start_sec >> 1")
+    with pytest.raises(ValueError, match="unknown column"):
+        db.text_search(q, where="nope > 1")
     with pytest.raises(NotImplementedError):
         db.text_search("a person pours water")
     db2 = RAGDatabase(None, None, columns=table, embed_fn=lambda s: table["text_embedding"][42])
@@ -161,3 +163,77 @@ def test_drop_in_class_matches_the_reference_class_recording(libmrag, golden_dir
     n = compare.replay_reference_class(lambda t: cache.setdefault(id(t), RAGDatabase(None, None, 'cuda', columns=t)),
                                        golden_dir / "rag_reference_class.json", rel=1e-3)
     assert n >= 15
+
+
+GENERAL_WHERE = ["start_sec > 1", "start_sec >= 2 AND video != 'clip_00004.mp4'", "id < 3000 or dataset = 'webvid'",
+                 "video LIKE 'clip_000%' and not (start_sec = 0)", "uid in ('u12', 'u13', 'u14', 'u4000') or id between 20 and 900",
+                 "video is not null and end_sec <= 4", "dataset != 'openvid'"]
+
+
+@pytest.mark.parametrize("prefilter", [False, True])
+def test_general_where_clauses_match_the_oracle(libmrag, table, prefilter):
+    """Any predicate of the SQL subset (src/data/rag.py:56-57 forwards the string to LanceDB): post-filter on the
+    k nearest (default) and pre-filter, against the oracle whose predicate engine is SQLite."""
+    from motionrag_b200 import RAGDatabase
+    db = RAGDatabase(None, None, 'cuda', columns=table, prefilter=prefilter)
+    ora = fs.OracleRAGDatabase(table, prefilter=prefilter)
+    rng = np.random.default_rng(11)
+    for w in GENERAL_WHERE:
+        for j in rng.integers(0, 6000, 3):
+            q = (table["text_embedding"][j] + 0.02 * rng.standard_normal(768)).astype(np.float32) * 5
+            kw = dict(text=q, top_k=12, where=w, select=['id', 'video', 'start_sec'])
+            got, want = db.text_search(**kw), ora.text_search(**kw)
+            _same(got, want)
+            if prefilter and w != "dataset != 'openvid'":
+                assert len(got) == 12
+    # a batch with one clause per query: `!=` clauses run on the device, the rest on the host, None = no filter
+    if not prefilter:
+        src = rng.integers(0, 6000, 40)
+        qs = (table["text_embedding"][src] * 4).astype(np.float32)
+        wheres = [None if i % 5 == 0 else (f'video != "{table["video"][j]}"' if i % 2 else GENERAL_WHERE[i % len(GENERAL_WHERE)])
+                  for i, j in enumerate(src)]
+        out = db.search_batch(qs, top_k=12, where=wheres, select=['id', 'video', 'start_sec'])
+        for q, w, o in zip(qs, wheres, out):
+            _same(o, ora.text_search(q, top_k=12, where=w, select=['id', 'video', 'start_sec']))
+
+
+@pytest.mark.parametrize("container", ["parquet", "arrow", "fragments"])
+def test_arrow_dump_of_the_reference_table_opens_and_matches_the_oracle(libmrag, table, tmp_path, container):
+    """A pyarrow-written table with the schema tools/build_rag_database.py:35-45 produces (FixedSizeList<f32>[768]
+    embedding + scalar columns; bf16-normalised rows like the reference's bfloat16 embedder writes) opens through
+    RAGDatabase(db_path, table_name) — no lancedb — pickles by path, and answers like the oracle on the same rows."""
+    import pickle
+
+    import pyarrow as pa
+    import pyarrow.feather as pf
+    import pyarrow.parquet as pq
+    from motionrag_b200 import RAGDatabase
+    n = 1500
+    emb = torch.from_numpy(table["text_embedding"][:n] * 1.7).bfloat16()
+    emb = (emb / emb.float().norm(dim=-1, keepdim=True).bfloat16()).float().numpy()   # unit only to bf16 precision
+    t = pa.table({"text": table["text"][:n].tolist(),
+                  "text_embedding": pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1), type=pa.float32()), 768),
+                  "id": np.arange(n), "uid": table["uid"][:n].tolist(), "dataset": table["dataset"][:n].tolist(),
+                  "video": table["video"][:n].tolist(), "start_sec": table["start_sec"][:n], "end_sec": table["end_sec"][:n]})
+    root = tmp_path / "openvid.db"
+    root.mkdir()
+    if container == "parquet":
+        pq.write_table(t, root / "motion_caption.parquet")
+    elif container == "arrow":
+        pf.write_feather(t, root / "motion_caption.arrow", compression="uncompressed")
+    else:
+        (root / "motion_caption").mkdir()
+        for i, s in enumerate(range(0, n, 400)):
+            pq.write_table(t.slice(s, 400), root / "motion_caption" / f"part-{i:03d}.parquet")
+    db = RAGDatabase(str(root), "motion_caption", 'cuda')
+    assert len(db) == n
+    cols = {name: np.asarray(t[name].to_pylist()) for name in t.column_names if name != "text_embedding"}
+    cols["text_embedding"] = emb
+    ora = fs.OracleRAGDatabase(cols)
+    rng = np.random.default_rng(21)
+    for j in rng.integers(0, n, 5):
+        q = (emb[j] + 0.02 * rng.standard_normal(768)).astype(np.float32) * 7
+        kw = dict(text=q, top_k=12, where=f'video != "{cols["video"][j]}"', select=['video', 'start_sec', 'end_sec'])
+        _same(db.text_search(**kw), ora.text_search(**kw))
+    again = pickle.loads(pickle.dumps(db.text_search)).__self__
+    _same(again.text_search(q, top_k=5, select=["id"]), ora.text_search(q, top_k=5, select=["id"]))

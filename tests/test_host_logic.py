@@ -21,11 +21,12 @@ def _db_no_gpu(n=30, dim=8):
     return db
 
 
-def test_where_regex_accepts_only_the_reference_form():
-    assert rag._WHERE.match('video != "a b/c.mp4"').group(3) == "a b/c.mp4"
-    assert rag._WHERE.match("video != 'x'").group(1) == "video"
-    for bad in ('video = "a"', 'start_sec > 3', 'video != a', 'video != "a" AND id != "3"'):
-        assert rag._WHERE.match(bad) is None
+def test_reference_where_form_is_recognised_as_a_device_exclusion():
+    from motionrag_b200.where import parse
+    assert parse('video != "a b/c.mp4"').simple_exclusion() == ("video", "a b/c.mp4")
+    assert parse("video != 'x'").simple_exclusion() == ("video", "x")
+    for general in ('video = "a"', 'start_sec > 3', 'video != "a" AND id != "3"'):
+        assert parse(general).simple_exclusion() is None
 
 
 def test_group_ids_and_lookup():
@@ -59,20 +60,37 @@ def test_records_schema_and_padding_rows_are_dropped():
 
 def test_where_clauses_are_parsed_once_and_validated():
     db = _db_no_gpu()
+    db.prefilter = False
     db._bind_groups = lambda col: setattr(db, "_group_col", col)      # no store in this shell
-    ids = db._exclusion_ids('video != "v3"', 2)
-    assert ids.tolist() == [db._group_ids_lookup("video", "v3")] * 2 and 'video != "v3"' in db._where_cache
-    ids = db._exclusion_ids(['video != "v1"', None, 'video != "nope"'], 3)
-    assert ids.tolist() == [db._group_ids_lookup("video", "v1"), -1, -1]
-    assert db._exclusion_ids(None, 3) is None and db._exclusion_ids([None, None], 2) is None
-    with pytest.raises(ValueError, match="unsupported where"):
-        db._exclusion_ids('start_sec > 3', 1)
+    ids, preds = db._exclusion_ids('video != "v3"', 2)
+    assert ids.tolist() == [db._group_ids_lookup("video", "v3")] * 2 and 'video != "v3"' in db._where_cache and preds is None
+    ids, preds = db._exclusion_ids(['video != "v1"', None, 'video != "nope"'], 3)
+    assert ids.tolist() == [db._group_ids_lookup("video", "v1"), -1, -1] and preds is None
+    assert db._exclusion_ids(None, 3) == (None, None) and db._exclusion_ids([None, None], 2) == (None, None)
+    # anything but `col != literal` is a host predicate, applied to the rows a query returned (post-filter)
+    ids, preds = db._exclusion_ids(['start_sec > 3', 'video != "v1"', None], 3)
+    assert ids.tolist() == [-1, db._group_ids_lookup("video", "v1"), -1] and preds[1] is None and preds[2] is None
+    dist = np.array([[0.1, 0.2, 0.3, np.inf], [0.1, 0.2, 0.3, 0.4], [0.5, 0.6, 0.7, 0.8]], dtype=np.float32)
+    idx = np.array([[2, 9, 4, -1], [1, 2, 3, 4], [5, 6, 7, 8]])
+    db._apply_predicates(preds, dist, idx)
+    assert idx.tolist() == [[9, 4, -1, -1], [1, 2, 3, 4], [5, 6, 7, 8]]
+    assert dist[0, :2].tolist() == pytest.approx([0.2, 0.3]) and np.isinf(dist[0, 2:]).all()
+    with pytest.raises(ValueError, match="where clause"):
+        db._exclusion_ids('start_sec >> 3', 1)
     with pytest.raises(ValueError, match="unknown column"):
         db._exclusion_ids('nope != "x"', 1)
     with pytest.raises(ValueError, match="same column"):
         db._exclusion_ids(['video != "v1"', 'id != "3"'], 2)
     with pytest.raises(ValueError, match="one where clause per query"):
         db._exclusion_ids(['video != "v1"'], 2)
+    # pre-filter: one general clause per batch becomes a two-group row mask (group 1 = rows that fail)
+    db.prefilter = True
+    bound = {}
+    db._stores = {"text_embedding": type("S", (), {"set_groups": lambda self, g: bound.update(g=g), "__len__": lambda self: 30})()}
+    ids, preds = db._exclusion_ids('start_sec > 3', 2)
+    assert ids.tolist() == [1, 1] and preds is None and bound["g"].tolist() == [1] * 4 + [0] * 26
+    with pytest.raises(ValueError, match="ONE general where"):
+        db._exclusion_ids(['start_sec > 3', 'start_sec > 4'], 2)
 
 
 def test_format_result_formats_and_error():
@@ -91,7 +109,7 @@ def test_save_table_roundtrip(tmp_path):
             "video": [f"v{j}" for j in range(n)], "start_sec": np.arange(n, dtype=np.float64),
             "end_sec": np.arange(n, dtype=np.float64) + 1, "id": np.arange(n)}
     rag.save_table(tmp_path, "motion_caption", cols)
-    back = rag.RAGDatabase._load(tmp_path / "motion_caption")
+    back = rag.RAGDatabase._load(tmp_path, "motion_caption")
     np.testing.assert_array_equal(back["text_embedding"], cols["text_embedding"])
     assert list(back["video"]) == cols["video"] and back["start_sec"].dtype == np.float64
 
@@ -182,3 +200,74 @@ def test_feature_table_builder_round_trip(tmp_path):
     with pytest.raises(IndexError):
         from motionrag_b200 import FeatureTableWriter
         FeatureTableWriter(tmp_path / "bad", 4, L, C).write([9], torch.zeros(1, L, C))
+
+
+def _reference_schema_table(n=40, dim=768, seed=3):
+    """A pyarrow table with the schema tools/build_rag_database.py:35-45 writes."""
+    import pyarrow as pa
+    rng = np.random.default_rng(seed)
+    emb = rng.standard_normal((n, dim)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=-1, keepdims=True)
+    t = pa.table({"text": [f"caption {j}" for j in range(n)],
+                  "text_embedding": pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1), type=pa.float32()), dim),
+                  "id": pa.array(np.arange(n), type=pa.int64()), "uid": [f"uid{j}" for j in range(n)],
+                  "dataset": ["openvid"] * n, "video": [f"v{j // 3}.mp4" for j in range(n)],
+                  "start_sec": np.arange(n) * 2.0, "end_sec": np.arange(n) * 2.0 + 2.0})
+    return t, emb
+
+
+def test_arrow_dumps_of_the_reference_schema_open_without_lancedb(tmp_path):
+    """Parquet file, directory of Parquet fragments, Arrow IPC file and IPC stream holding the reference's schema
+    (FixedSizeList<f32>[768] + scalar columns) all read into the same columns."""
+    import pyarrow as pa
+    import pyarrow.feather as pf
+    import pyarrow.parquet as pq
+    from motionrag_b200 import tables
+    t, emb = _reference_schema_table()
+    pq.write_table(t, tmp_path / "a.parquet")
+    pf.write_feather(t, tmp_path / "b.arrow")
+    (tmp_path / "c").mkdir()
+    pq.write_table(t.slice(0, 17), tmp_path / "c" / "part-0.parquet")
+    pq.write_table(t.slice(17), tmp_path / "c" / "part-1.parquet")
+    with pa.OSFile(str(tmp_path / "d.arrows"), "wb") as f, pa.ipc.new_stream(f, t.schema) as w:
+        w.write_table(t, max_chunksize=16)
+    for name in "abcd":
+        cols = rag.RAGDatabase._load(tmp_path, name)
+        assert cols["text_embedding"].dtype == np.float32 and np.array_equal(cols["text_embedding"], emb), name
+        assert cols["video"].tolist() == t["video"].to_pylist() and cols["start_sec"].dtype == np.float64
+        assert set(cols) == set(t.column_names)
+        facts = tables.check_table(cols)
+        assert facts["rows"] == 40 and facts["id_is_row_number"] and facts["text_embedding"]["unit_norm"]
+        tables.feature_row_alignment(cols, 40)
+    with pytest.raises(FileNotFoundError, match="no table"):
+        tables.read_table(tmp_path, "missing")
+    (tmp_path / "real.lance").mkdir()
+    with pytest.raises(FileNotFoundError, match="export_lancedb"):
+        tables.read_table(tmp_path, "real")
+
+
+def test_table_checks_flag_misaligned_ids_nulls_and_non_unit_rows():
+    import pyarrow as pa
+    from motionrag_b200 import tables
+    t, emb = _reference_schema_table(12, 16)
+    cols = tables.arrow_to_columns(t)
+    cols["id"] = cols["id"][::-1].copy()
+    assert tables.check_table(cols)["id_is_row_number"] is False
+    with pytest.raises(ValueError, match="not row-aligned"):
+        tables.feature_row_alignment(cols, 12)
+    with pytest.raises(ValueError, match="feature table has 11 rows"):
+        tables.feature_row_alignment(tables.arrow_to_columns(t), 11)
+    # NULL vectors become zero rows; a sliced array keeps its offset; List<float> columns are accepted
+    mask = np.zeros(12, dtype=bool)
+    mask[[3, 7]] = True
+    vec = pa.FixedSizeListArray.from_arrays(pa.array(emb.reshape(-1)), 16, mask=pa.array(mask))
+    want = emb.copy()
+    want[mask] = 0
+    assert np.array_equal(tables.vector_column_to_numpy(vec), want)
+    assert np.array_equal(tables.vector_column_to_numpy(vec.slice(2, 8)), want[2:10])
+    lst = pa.array([r.tolist() for r in emb], type=pa.list_(pa.float32()))
+    assert np.array_equal(tables.vector_column_to_numpy(lst), emb)
+    facts = tables.check_table({"text_embedding": want * 3})
+    assert facts["text_embedding"]["zero_rows"] == 2 and not facts["text_embedding"]["unit_norm"]
+    with pytest.raises(ValueError, match="different lengths"):
+        tables.vector_column_to_numpy(pa.array([[1.0, 2.0], [1.0]], type=pa.list_(pa.float32())))

@@ -113,7 +113,9 @@ def test_oracle_rag_database_record_schema():
     assert all(r["video"] != "v4.mp4" for r in recs)
     assert [r["_distance"] for r in recs] == sorted(r["_distance"] for r in recs)
     with pytest.raises(ValueError):
-        db.text_search(cols["text_embedding"][0], where="start_sec > 3")
+        db.text_search(cols["text_embedding"][0], where="start_sec >> ) 3")
+    later = db.text_search(cols["text_embedding"][12] * 3, top_k=12, where="start_sec > 40 AND video != 'v20.mp4'")
+    assert all(r["start_sec"] > 40 and r["video"] != "v20.mp4" for r in later)
     with pytest.raises(ValueError):
         fs.OracleRAGDatabase.format_result([], "csv")
 

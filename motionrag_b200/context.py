@@ -139,12 +139,14 @@ class MotionContext:
         return block_causal_mask(num_frames, frame_tokens, self.table.device)
 
     def build(self, ref_index: torch.Tensor, condition_emb: torch.Tensor | None = None,
-              out: torch.Tensor | None = None) -> torch.Tensor:
-        return gather_context(self.table, ref_index, self.sos, self.uncond_row, self.pos_table,
+              out: torch.Tensor | None = None, with_pe: bool = True) -> torch.Tensor:
+        """x of module.py:298-301 from row ids. with_pe=False leaves the position table out (the loss path adds
+        it, and the condition embedding, with differentiable torch ops)."""
+        return gather_context(self.table, ref_index, self.sos, self.uncond_row, self.pos_table if with_pe else None,
                               condition_emb, out)
 
     def build_from_features(self, ref_features: torch.Tensor, condition_emb: torch.Tensor | None = None,
-                            out: torch.Tensor | None = None) -> torch.Tensor:
+                            out: torch.Tensor | None = None, with_pe: bool = True) -> torch.Tensor:
         """Same `x` from already-materialised reference features (`batch['ref_features']`,
         [b, K, L, C] in similarity order, 0 = most similar) instead of table rows: the batch itself
         is the table and slot (i, k) reads row i*K + k — still one K4 launch."""
@@ -154,7 +156,8 @@ class MotionContext:
         dt, dev = self.table.local.dtype, self.table.device
         feats = ref_features.detach().to(dev, dt).reshape(b * K, self.table.L, self.table.Cdim).contiguous()
         idx = torch.arange(b * K, dtype=torch.int64, device=dev).view(b, K)
-        return gather_context(FeatureTable(feats), idx, self.sos, self.uncond_row, self.pos_table, condition_emb, out)
+        return gather_context(FeatureTable(feats), idx, self.sos, self.uncond_row, self.pos_table if with_pe else None,
+                              condition_emb, out)
 
     def uncond_action_emb(self, b: int) -> torch.Tensor:
         """predict()'s CFG branch (module.py:327-329): encode_vision(zeros)[:, 0] per sample."""
@@ -164,8 +167,8 @@ class MotionContext:
 def attach(model, ctx: MotionContext, transformer=None):
     """Teach a reference ActionTransformer to take `batch['ref_index']` ([b, K] int64 row ids
     from retrieval) or `batch['ref_features']` ([b, K, L, C] features in similarity order) instead
-    of `batch['ref_videos']` for inference (`return_loss=False`),
-    producing the same prediction tensor as module.py:292-315 with encode_vision of the K
+    of `batch['ref_videos']`, producing the same prediction tensor (`return_loss=False`) or the same
+    loss (`return_loss=True`, see loss_forward below) as module.py:292-315 with encode_vision of the K
     references replaced by the table gather. The condition embedding is still computed by the
     model's own encode_condition from `batch['ref_images']` ([b, K+1, C, H, W], refs flipped +
     target first frame, as batch_forward builds them at :321).
@@ -179,12 +182,50 @@ def attach(model, ctx: MotionContext, transformer=None):
     if transformer is not None and ctx.table.local.dtype != torch.bfloat16:
         raise ValueError("the libmrag transformer consumes a bf16 feature table")
 
+    def loss_forward(batch, ignore_ref_loss: bool):
+        """training_step / validation_step / test_step (module.py:333-351 -> forward :292-311 with
+        return_loss=True): the K reference features come from the table (K4 gather, no autograd — vision_model
+        and vision_proj are frozen in the CAMA configs), only the TARGET clip is encoded
+        (`batch['target_features']` [b, L, C] when the caller has them, else one `encode_vision` pass over
+        `batch['video']` instead of K+1). What can carry gradients stays in torch and differentiable: the SOS
+        block is the model's own `sos_token` parameter, the position table and the condition embedding are added
+        with torch ops in the reference's order (two roundings), and the model's own transformer and get_loss run."""
+        by_index = 'ref_index' in batch
+        L, C = ctx.table.L, ctx.table.Cdim
+        if by_index:
+            raw = ctx.build(batch['ref_index'], None, out=None, with_pe=False)      # [b, (K+1)L, C]: sos | refs flipped
+            b, K = batch['ref_index'].shape
+        else:
+            raw = ctx.build_from_features(batch['ref_features'], None, with_pe=False)
+            b, K = batch['ref_features'].shape[:2]
+        refs = raw[:, L:].reshape(b, K, L, C)                  # similarity rank K-1 ... 0, as batch_forward flips them
+        if 'target_features' in batch:
+            target = batch['target_features'].to(raw.device, raw.dtype)
+        else:
+            target = model.encode_vision(batch['video'][:, None])[:, 0]
+        vision_emb = torch.cat([refs, target[:, None]], dim=1)
+        cond = model.encode_condition(batch['ref_images']) if 'ref_images' in batch else batch.get('condition_emb')
+        sos = getattr(model, 'sos_token', None)
+        sos = ctx.sos[None] if sos is None else sos
+        x = torch.cat([sos.to(raw.dtype).repeat(b, 1, 1), raw[:, L:]], dim=1)
+        vision_pe = getattr(model, 'vision_pe', None)
+        if vision_pe is not None:
+            x = vision_pe(x)
+        elif ctx.pos_table is not None and not hasattr(model, 'vision_pe'):
+            x = x + ctx.pos_table[:x.size(-2)]
+        if cond is not None:
+            x = x + cond
+        pred = model.transformer(x, ctx.get_mask(K + 1, L))
+        pred = pred.reshape(b, K + 1, L, -1)
+        if ignore_ref_loss:
+            return model.get_loss(pred[:, -1:], vision_emb[:, -1:])
+        return model.get_loss(pred, vision_emb)
+
     def batch_forward(batch, return_loss: bool = True, ignore_ref_loss: bool = False):
         if 'ref_index' not in batch and 'ref_features' not in batch:
             return orig(batch, return_loss, ignore_ref_loss)
         if return_loss:
-            raise NotImplementedError("the table-backed path serves inference (predict); "
-                                      "training losses need the target clip's own features")
+            return loss_forward(batch, ignore_ref_loss)
         cond = model.encode_condition(batch['ref_images']) if 'ref_images' in batch else batch.get('condition_emb')
         by_index = 'ref_index' in batch
         b, K = (batch['ref_index'] if by_index else batch['ref_features']).shape[:2]

@@ -163,3 +163,48 @@ def reference_context(ref_feats: torch.Tensor, target_feat: torch.Tensor, cond: 
         model.batch_forward(batch, return_loss=False)
     x, mask = cap.seen
     return x, mask, model.vision_pe.pos_table
+
+
+def tiny_encoder(C: int, heads: int, ff: int, layers: int, seed: int):
+    """The CAMA transformer shape (configs/cogvideox/MotionRAG_open.yml:253-267: post-norm, GELU, batch_first) at
+    toy size, seeded."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    layer = nn.TransformerEncoderLayer(C, heads, ff, 0.0, "gelu", batch_first=True, norm_first=False)
+    return nn.TransformerEncoder(layer, layers, enable_nested_tensor=False)
+
+
+def reference_loss(ref_feats: torch.Tensor, target_feat: torch.Tensor, cond: torch.Tensor, sos: torch.Tensor,
+                   encoder, ignore_ref_loss: bool, reference_root: str = "/root/reference", max_len: int = 256):
+    """The reference's REAL ActionTransformer.batch_forward(return_loss=True) (module.py:292-311, 317-323; what
+    training_step / validation_step call) with a real transformer: returns (mse, smooth, d mse / d sos_token).
+    Features are supplied through a patched encode_vision exactly as in reference_context."""
+    import copy
+
+    import torch.nn as nn
+    _install_stubs()
+    if reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    from src.projects.condition.module import ActionTransformer
+    from src.projects.condition.position_embeddings import SinusoidPositionalEmbeddings
+    b, K, L, C = ref_feats.shape
+
+    class Ident(nn.Module):
+        num_queries, output_dim, cross_attention_dim, dim = L, C, C, C
+
+        def forward(self, x):
+            return x
+
+    model = ActionTransformer(condition_model=Ident(), condition_proj=Ident(), vision_model=Ident(),
+                              vision_proj=Ident(), transformer=copy.deepcopy(encoder), condition_pe=None,
+                              vision_pe=SinusoidPositionalEmbeddings(C, max_len))
+    with torch.no_grad():
+        model.sos_token.copy_(sos.float())
+    feats_by_slot = torch.cat([ref_feats, target_feat[:, None]], dim=1)
+    slots = torch.arange(K + 1).view(1, K + 1, 1, 1, 1, 1).expand(b, K + 1, 1, 1, 1, 1).float()
+    model.encode_vision = lambda videos: torch.stack([feats_by_slot[i, videos[i, :, 0, 0, 0, 0].long()] for i in range(b)], 0)
+    model.encode_condition = lambda images: cond
+    loss = model.batch_forward({"ref_videos": slots[:, :K], "video": slots[:, K]}, return_loss=True,
+                               ignore_ref_loss=ignore_ref_loss)
+    loss.main.backward()
+    return float(loss.mse), float(loss.smooth), model.sos_token.grad.detach().clone()

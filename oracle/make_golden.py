@@ -9,6 +9,9 @@ cama_context_{bf16,f32}.npz   inputs + the (x, mask) captured from the reference
 rag_reference_class.json      what the reference's REAL RAGDatabase class (src/data/rag.py) returns for
                               the calls prepare_annotations makes (and the other public methods), run
                               over the LanceDB stand-in oracle/fake_lancedb.py.
+cama_loss_f32.npz             mse / smooth-L1 losses and the sos_token gradient of the reference's REAL
+                              ActionTransformer.batch_forward(return_loss=True) (training_step and
+                              validation_step, module.py:305-311, 333-351) with a seeded toy transformer.
 retrieval_small.npz           seeded database / queries / group ids with the oracle's own
                               answers for l2 / cosine / dot, post- and pre-filter. LanceDB is
                               not installable here, so these pin the oracle against
@@ -44,6 +47,26 @@ def make_cama(dtype: torch.dtype, name: str, b=3, K=4, L=5, C=64, seed=11):
     np.savez_compressed(OUT / name, ref_feats=_bits(ref), target=_bits(tgt), cond=_bits(cond),
                         sos=_bits(sos), x=_bits(x), mask=mask.numpy(), pos_table=pos.numpy(),
                         dtype=str(dtype))
+
+
+def make_cama_loss(name="cama_loss_f32.npz", b=2, K=3, L=4, C=32, heads=4, ff=64, layers=2, seed=31):
+    """Loss values and the sos_token gradient of the reference's real training / validation forward
+    (module.py:305-311, 333-351) on known features and a seeded toy transformer whose weights are stored."""
+    g = torch.Generator().manual_seed(seed)
+    ref = torch.randn(b, K, L, C, generator=g)
+    tgt = torch.randn(b, L, C, generator=g)
+    cond = torch.randn(b, (K + 1) * L, C, generator=g)
+    sos = torch.randn(1, L, C, generator=g) / C ** 0.5
+    enc = cama_context.tiny_encoder(C, heads, ff, layers, seed)
+    out = {"ref_feats": ref.numpy(), "target": tgt.numpy(), "cond": cond.numpy(), "sos": sos.numpy(),
+           "shape": np.array([C, heads, ff, layers])}
+    for k, v in enc.state_dict().items():
+        out["w:" + k] = v.numpy()
+    for ignore in (False, True):
+        mse, smooth, grad = cama_context.reference_loss(ref, tgt, cond, sos, enc, ignore)
+        tag = "val" if ignore else "train"
+        out[f"{tag}_mse"], out[f"{tag}_smooth"], out[f"{tag}_sos_grad"] = np.float64(mse), np.float64(smooth), grad.numpy()
+    np.savez_compressed(OUT / name, **out)
 
 
 def make_retrieval(name="retrieval_small.npz", n=2000, dim=256, nq=16, k=12, seed=5):
@@ -168,6 +191,7 @@ def main():
     make_cama(torch.bfloat16, "cama_context_bf16.npz")
     make_cama(torch.float32, "cama_context_f32.npz")
     make_retrieval()
+    make_cama_loss()
     for f in sorted(OUT.glob("*.npz")) + sorted(OUT.glob("*.json")):
         print(f, f.stat().st_size, "bytes")
 

@@ -143,8 +143,6 @@ def test_attach_drives_a_cama_style_transformer_from_row_ids(libmrag):
         want = model.transformer(x.cuda(), cc.block_causal_mask(K + 1, L).cuda())
     assert pred.shape == (b, K + 1, L, C)
     assert torch.equal(pred.reshape(b, -1, C), want)       # same x, same mask -> same bits
-    with pytest.raises(NotImplementedError):
-        model.batch_forward({"ref_index": idx.cuda()}, return_loss=True)
     # batch['ref_features'] (SURVEY §8b face 2): the same x from materialised features
     feats = cc.gather_restatement(table, idx, un)                      # [b, K, L, C], -1 -> uncond row
     with torch.no_grad():
@@ -175,3 +173,67 @@ def test_gather_random_shapes_match_restatement(libmrag, seed):
                                   cc.sinusoid_table((K + 1) * L + 3, C) if with_pe else None,
                                   cond.clone() if with_cond else None)
     assert torch.equal(x.cpu(), want), dict(b=b, K=K, L=L, C=C, dt=dt, pe=with_pe, cond=with_cond, n=n)
+
+
+def test_loss_path_matches_the_reference_training_and_validation_forward(libmrag, golden_dir):
+    """attach().batch_forward(return_loss=True) — what training_step / validation_step / test_step call
+    (src/projects/condition/module.py:333-351) — with the K references read from the feature table and only the
+    target clip's features supplied: losses and the sos_token gradient equal the recording of the reference's REAL
+    ActionTransformer (tests/golden/cama_loss_f32.npz, oracle/make_golden.py::make_cama_loss)."""
+    import types
+
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from motionrag_b200 import FeatureTable, MotionContext, attach
+    gold = np.load(golden_dir / "cama_loss_f32.npz")
+    C, heads, ff, layers = (int(v) for v in gold["shape"])
+    ref, tgt = torch.from_numpy(gold["ref_feats"]), torch.from_numpy(gold["target"])
+    cond, sos = torch.from_numpy(gold["cond"]), torch.from_numpy(gold["sos"])
+    b, K, L, _ = ref.shape
+
+    class Cama(nn.Module):          # the members of ActionTransformer the loss path touches
+        def __init__(self):
+            super().__init__()
+            layer = nn.TransformerEncoderLayer(C, heads, ff, 0.0, "gelu", batch_first=True, norm_first=False)
+            self.transformer = nn.TransformerEncoder(layer, layers, enable_nested_tensor=False)
+            self.transformer.load_state_dict({k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w:")})
+            self.sos_token = nn.Parameter(sos.clone())
+            self.register_buffer("pos_table", cc.sinusoid_table(256, C))
+
+        def vision_pe(self, x):                      # SinusoidPositionalEmbeddings.forward (position_embeddings.py:172-174)
+            return x + self.pos_table[:, :x.size(-2)].type_as(x)
+
+        def encode_condition(self, images):
+            return images
+
+        def encode_vision(self, videos):             # must only ever see the TARGET clip: [b, 1, ...]
+            assert videos.shape[1] == 1
+            return videos[:, :, 0]
+
+        def get_loss(self, pred, emb):               # module.py:277-290
+            pred, emb = pred.flatten(0, 1), emb.flatten(0, 1)
+            mse = F.mse_loss(pred, emb)
+            return types.SimpleNamespace(main=mse, mse=mse, smooth=F.smooth_l1_loss(pred, emb))
+
+        def batch_forward(self, batch, return_loss=True, ignore_ref_loss=False):
+            raise AssertionError("the video path must not run when ref_index is given")
+
+    # the table holds the reference features at scattered rows; ref_index is in similarity order (0 = most similar)
+    rows = torch.randperm(64, generator=torch.Generator().manual_seed(1))[:b * K].view(b, K)
+    table = torch.zeros(64, L, C)
+    table[rows.flatten()] = ref.reshape(b * K, L, C)
+    un = torch.randn(L, C, generator=torch.Generator().manual_seed(2))
+    for tag, ignore in (("train", False), ("val", True)):
+        model = Cama().cuda()
+        ctx = MotionContext(FeatureTable(table.cuda()), sos, un, pe_max_length=256)
+        attach(model, ctx)
+        for batch in ({"ref_index": rows.cuda(), "ref_images": cond.cuda(), "target_features": tgt.cuda()},
+                      {"ref_index": rows.cuda(), "ref_images": cond.cuda(), "video": tgt.cuda()[:, None]},
+                      {"ref_features": ref.cuda(), "ref_images": cond.cuda(), "target_features": tgt.cuda()}):
+            model.zero_grad()
+            loss = model.batch_forward(batch, return_loss=True, ignore_ref_loss=ignore)
+            loss.main.backward()
+            assert float(loss.mse) == pytest.approx(float(gold[f"{tag}_mse"]), rel=2e-5)
+            assert float(loss.smooth) == pytest.approx(float(gold[f"{tag}_smooth"]), rel=2e-5)
+            torch.testing.assert_close(model.sos_token.grad.cpu(), torch.from_numpy(gold[f"{tag}_sos_grad"]),
+                                       rtol=1e-3, atol=1e-7)

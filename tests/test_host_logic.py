@@ -271,3 +271,74 @@ def test_table_checks_flag_misaligned_ids_nulls_and_non_unit_rows():
     assert facts["text_embedding"]["zero_rows"] == 2 and not facts["text_embedding"]["unit_norm"]
     with pytest.raises(ValueError, match="different lengths"):
         tables.vector_column_to_numpy(pa.array([[1.0, 2.0], [1.0]], type=pa.list_(pa.float32())))
+
+
+def test_loss_path_host_logic_equals_the_reference_recording(monkeypatch, golden_dir):
+    """attach().batch_forward(return_loss=True) with the K4 gather replaced by its CPU restatement: everything
+    around the kernel (target-only encoding, differentiable SOS / position / condition adds, the model's own
+    transformer and get_loss) reproduces the losses and the sos_token gradient recorded from the reference's REAL
+    ActionTransformer (tests/golden/cama_loss_f32.npz). The GPU twin runs the real kernel (tests/test_gpu_context.py)."""
+    import types
+
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from motionrag_b200 import context as ctxmod
+    gold = np.load(golden_dir / "cama_loss_f32.npz")
+    C, heads, ff, layers = (int(v) for v in gold["shape"])
+    ref, tgt = torch.from_numpy(gold["ref_feats"]), torch.from_numpy(gold["target"])
+    cond, sos = torch.from_numpy(gold["cond"]), torch.from_numpy(gold["sos"])
+    b, K, L, _ = ref.shape
+
+    class HostTable:
+        def __init__(self, t):
+            self.local, self.L, self.Cdim, self.device, self.n_rows = t, t.shape[1], t.shape[2], t.device, t.shape[0]
+
+    def host_gather(table, ref_index, sos_, un, pos, cond_, out=None, validate=False):
+        feats = cc.gather_restatement(table.local, ref_index, un)
+        return cc.context_restatement(feats, sos_.reshape(1, table.L, table.Cdim), None if pos is None else pos[None], cond_)
+    monkeypatch.setattr(ctxmod, "gather_context", host_gather)
+    monkeypatch.setattr(ctxmod, "FeatureTable", HostTable)
+
+    class Cama(nn.Module):
+        def __init__(self):
+            super().__init__()
+            layer = nn.TransformerEncoderLayer(C, heads, ff, 0.0, "gelu", batch_first=True, norm_first=False)
+            self.transformer = nn.TransformerEncoder(layer, layers, enable_nested_tensor=False)
+            self.transformer.load_state_dict({k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w:")})
+            self.sos_token = nn.Parameter(sos.clone())
+            self.register_buffer("pos_table", cc.sinusoid_table(256, C))
+
+        def vision_pe(self, x):
+            return x + self.pos_table[:, :x.size(-2)].type_as(x)
+
+        def encode_condition(self, images):
+            return images
+
+        def encode_vision(self, videos):
+            assert videos.shape[1] == 1          # only the target clip is ever encoded
+            return videos[:, :, 0]
+
+        def get_loss(self, pred, emb):
+            pred, emb = pred.flatten(0, 1), emb.flatten(0, 1)
+            mse = F.mse_loss(pred, emb)
+            return types.SimpleNamespace(main=mse, mse=mse, smooth=F.smooth_l1_loss(pred, emb))
+
+        def batch_forward(self, *a, **k):
+            raise AssertionError("the video path must not run")
+
+    rows = torch.randperm(64, generator=torch.Generator().manual_seed(1))[:b * K].view(b, K)
+    table = torch.zeros(64, L, C)
+    table[rows.flatten()] = ref.reshape(b * K, L, C)
+    un = torch.randn(L, C, generator=torch.Generator().manual_seed(2))
+    for tag, ignore in (("train", False), ("val", True)):
+        model = Cama()
+        ctxmod.attach(model, ctxmod.MotionContext(HostTable(table), sos, un, pe_max_length=256))
+        for batch in ({"ref_index": rows, "ref_images": cond, "target_features": tgt},
+                      {"ref_index": rows, "ref_images": cond, "video": tgt[:, None]},
+                      {"ref_features": ref, "ref_images": cond, "target_features": tgt}):
+            model.zero_grad()
+            loss = model.batch_forward(batch, return_loss=True, ignore_ref_loss=ignore)
+            loss.main.backward()
+            assert float(loss.mse.detach()) == pytest.approx(float(gold[f"{tag}_mse"]), rel=1e-6)
+            assert float(loss.smooth.detach()) == pytest.approx(float(gold[f"{tag}_smooth"]), rel=1e-6)
+            torch.testing.assert_close(model.sos_token.grad, torch.from_numpy(gold[f"{tag}_sos_grad"]), rtol=1e-5, atol=1e-8)

@@ -300,7 +300,7 @@ class RAGDatabase:
             if len(self._where_cache) > (1 << 20):
                 self._where_cache.clear()
             simple = pred.simple_exclusion()
-            hit = self._where_cache[w] = pred if simple is None else (simple[0], self._group_ids_lookup(simple[0], simple[1]))
+            hit = self._where_cache[w] = pred if simple is None else (simple[0], self._group_ids_lookup(simple[0], simple[1]), pred)
         return hit
 
     def _bind_mask(self, pred) -> None:
@@ -330,17 +330,16 @@ class RAGDatabase:
             if w is None:
                 continue
             hit = self._where_to_group(w) if i == 0 or w is not wheres[i - 1] else hit
-            if isinstance(hit, tuple):
-                c, gid = hit
-                if col is None:
-                    col = c
-                elif col != c:
-                    raise ValueError("all `!=` where clauses of a batch must name the same column")
-                ids[i] = gid
+            if isinstance(hit, tuple) and (col is None or col == hit[0]):
+                col, ids[i] = hit[0], hit[1]
             else:
+                # general predicates — and `!=` clauses on a second column, since the device holds one group
+                # labelling at a time — are evaluated on the host
+                if isinstance(hit, tuple) and self.prefilter:
+                    raise ValueError("all `!=` where clauses of a pre-filtered batch must name the same column")
                 if preds is None:
                     preds = [None] * nq
-                preds[i] = hit
+                preds[i] = hit[2] if isinstance(hit, tuple) else hit
         if preds is not None and self.prefilter:
             first = next(p for p in preds if p is not None)
             if col is not None or any(p is not first for p in preds):

@@ -79,8 +79,8 @@ def test_where_clauses_are_parsed_once_and_validated():
         db._exclusion_ids('start_sec >> 3', 1)
     with pytest.raises(ValueError, match="unknown column"):
         db._exclusion_ids('nope != "x"', 1)
-    with pytest.raises(ValueError, match="same column"):
-        db._exclusion_ids(['video != "v1"', 'id != "3"'], 2)
+    ids, preds = db._exclusion_ids(['video != "v1"', 'id != "3"'], 2)       # second column -> host predicate
+    assert ids.tolist() == [db._group_ids_lookup("video", "v1"), -1] and preds[0] is None and preds[1].text == 'id != "3"'
     with pytest.raises(ValueError, match="one where clause per query"):
         db._exclusion_ids(['video != "v1"'], 2)
     # pre-filter: one general clause per batch becomes a two-group row mask (group 1 = rows that fail)
@@ -91,6 +91,8 @@ def test_where_clauses_are_parsed_once_and_validated():
     assert ids.tolist() == [1, 1] and preds is None and bound["g"].tolist() == [1] * 4 + [0] * 26
     with pytest.raises(ValueError, match="ONE general where"):
         db._exclusion_ids(['start_sec > 3', 'start_sec > 4'], 2)
+    with pytest.raises(ValueError, match="same column"):
+        db._exclusion_ids(['video != "v1"', 'id != "3"'], 2)
 
 
 def test_format_result_formats_and_error():

@@ -23,7 +23,6 @@ struct mrag_cama {
   char* buf = nullptr;  // one allocation, carved below
   void *x_in = nullptr, *x_a = nullptr, *x_b = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *y_out = nullptr;
   float* partial = nullptr;
-  unsigned int* sync_counter = nullptr;  // grid barrier (+ phase time stamps) of the fused kernel
   int sm_count = 0;
   struct Graph {
     int b;
@@ -75,29 +74,7 @@ struct Guard {
   }
 };
 
-// Opt-in (MRAG_CAMA_FUSED=1): the whole forward of one or two samples as ONE cooperative kernel (K8).
-// Measured slower than the launch chain (220 vs 187 us at b = 1), so it is off by default.
-bool use_fused(const mrag_cama* c, int b) {
-  static const bool enabled = [] {
-    const char* e = getenv("MRAG_CAMA_FUSED");
-    return e && atoi(e) == 1;
-  }();
-  return enabled && k8_fused_supported(b, c->T, c->d, c->dff, c->heads, c->n_layers, c->sm_count);
-}
-
-cudaError_t run_fused(const mrag_cama* c, int b, cudaStream_t st) {
-  K8Buffers buf{c->x_in, c->x_a, c->x_b, c->att, c->y_out, c->qkv, c->h, c->partial};
-  K8LayerWeights lw[8];
-  for (int l = 0; l < c->n_layers; ++l) {
-    const mrag_cama_layer& w = c->layers[l];
-    lw[l] = K8LayerWeights{w.w_qkv, w.b_qkv, w.w_o, w.b_o, w.w_1, w.b_1, w.w_2, w.b_2, w.ln1_g, w.ln1_b, w.ln2_g, w.ln2_b};
-  }
-  return launch_k8_cama_fused(buf, lw, c->n_layers, b, c->T, c->d, c->dff, c->heads, c->groups, c->gtok, c->rows_alloc,
-                              c->sync_counter, c->sm_count, st);
-}
-
 cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
-  if (use_fused(c, b)) return run_fused(c, b, st);
   const int M = b * c->T, d = c->d, dff = c->dff;
   const void* xin = c->x_in;
   cudaError_t e = cudaSuccess;
@@ -183,7 +160,6 @@ int mrag_cama_create(int32_t n_layers, const mrag_cama_layer* layers, int32_t d_
   c->qkv = p; p += sz_qkv;
   c->h = p; p += sz_h;
   c->partial = reinterpret_cast<float*>(p); p += sz_p;
-  c->sync_counter = reinterpret_cast<unsigned int*>(p);
   *out = c;
   return MRAG_OK;
 }
@@ -239,7 +215,7 @@ int mrag_cama_forward(mrag_cama* c, int32_t b, int32_t use_graph, void* stream) 
   }
   cudaError_t e = cudaGraphLaunch(exec, st);
   if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "graph launch: %s", cudaGetErrorString(e));
-  note_launch(use_fused(c, b) ? 1 : 7 * c->n_layers);
+  note_launch(7 * c->n_layers);
   return MRAG_OK;
 }
 

@@ -296,8 +296,10 @@ template <typename T, int D, int Q>
 static cudaError_t launch_one(const void* db, int64_t n_rows, const float* queries, uint64_t* cand,
                               int kc, int grid, const K1Extra& ex, cudaStream_t st) {
   constexpr bool F = sizeof(T) == 4;
-  if constexpr (Q == 1) return launch_cfg<T, D, Q, F ? 2 : (D == 768 ? 6 : 4), 1, 512>(db, n_rows, queries, cand, kc, grid, ex, st);
-  return launch_cfg<T, D, Q, F ? 2 : 4, (F || Q >= 3 || D >= 1024) ? 2 : 3, 256>(db, n_rows, queries, cand, kc, grid, ex, st);
+  if constexpr (Q == 1)
+    return launch_cfg<T, D, Q, F ? 2 : (D == 768 ? 6 : 4), 1, 512>(db, n_rows, queries, cand, kc, grid, ex, st);
+  else  // `else` matters: without it the 256-thread form is instantiated for Q == 1 as well (8 dead kernels)
+    return launch_cfg<T, D, Q, F ? 2 : 4, (F || Q >= 3 || D >= 1024) ? 2 : 3, 256>(db, n_rows, queries, cand, kc, grid, ex, st);
 }
 
 template <typename T, int D>

@@ -891,324 +891,6 @@ __global__ void __launch_bounds__(128)
   *reinterpret_cast<uint4*>(out + size_t(row) * d + c) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-// ---- K8: the whole forward as ONE cooperative kernel (latency path for one or two samples) -----
-// With one sample every kernel of the chain lives for 4-13 us, most of it launch / drain / dependency
-// latency (28 dependent launches ~ 187 us). Here one CTA per SM stays resident for all layers and the 7
-// phases of a layer are separated by a grid-wide barrier instead of a kernel boundary. Every GEMM phase
-// has at most one tile per CTA (the host picks tile widths / K splits so), so the TMA -> tcgen05 -> TMEM
-// pipeline of K5 runs once per phase with its mbarrier parities carried in registers; attention items and
-// LayerNorm rows are dealt round-robin. Data written with ordinary stores in one phase is read by TMA in
-// the next: __threadfence + barrier on the writer side, fence.proxy.async before the first TMA load.
-constexpr int kFusedThreads = 256;
-constexpr int kFusedMaxLayers = 4;
-constexpr int kFusedStages = 6;
-constexpr uint32_t kFusedSmem = kFusedStages * (kGemmABytes + 128 * kBK * 2) + 256 + 1024;
-
-struct FusedLayer {
-  const __nv_bfloat16 *b_qkv, *b_o, *b_1, *b_2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-};
-struct FusedArgs {
-  int b, M, T, d, dff, heads, groups, gtok, n_layers;
-  int bn_qkv, bn_o, bn_1, bn_2;  // tile widths (64 or 128)
-  int so, sf;                    // K splits of out-proj / FFN2 (fp32 partial sums)
-  float scale_log2e, eps;
-  __nv_bfloat16 *x_in, *x_a, *x_b, *att, *y_out, *qkv, *h;
-  float* partial;
-  unsigned int* sync_counter;    // zeroed before every launch
-  unsigned long long* stamps;    // optional: globaltimer at every phase boundary (CTA 0), tuning aid
-  FusedLayer layers[kFusedMaxLayers];
-};
-struct FusedMaps {  // A operands (128-row boxes) and the four weight matrices of every layer
-  CUtensorMap a_xin, a_xb, a_att, a_xa, a_h;
-  CUtensorMap w[kFusedMaxLayers][4];
-};
-
-struct PipeState {  // per-thread ring position / tile parity, carried across phases
-  int stage = 0;
-  uint32_t phase = 0;
-  uint32_t tiles = 0;
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void fused_grid_sync(unsigned int* counter, unsigned int& target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    while (ld_acquire_gpu(counter) < target) {
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// one GEMM phase: CTA `blockIdx.x` owns tile (n_tile, m_tile, split) or idles
-__device__ __forceinline__ void fused_gemm(uint8_t* smem, uint64_t* bars, uint32_t tmem_base,
-                                           const CUtensorMap* tm_a, const CUtensorMap* tm_w, int M, int N, int K,
-                                           int bn, int splits, const __nv_bfloat16* bias, int gelu,
-                                           __nv_bfloat16* out, float* partial, PipeState& ps, int warp, int lane) {
-  const int tiles_n = N / bn, m_tiles = (M + kGemmBM - 1) / kGemmBM;
-  const int tile = blockIdx.x;
-  if (tile >= tiles_n * m_tiles * splits) return;
-  const int n_tile = tile % tiles_n, m_tile = (tile / tiles_n) % m_tiles, split = tile / (tiles_n * m_tiles);
-  const int kb_per = (K / kBK) / splits, kb0 = split * kb_per, kb1 = kb0 + kb_per;
-  const uint32_t stage_bytes = kGemmABytes + uint32_t(bn) * kBK * 2;
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kFusedStages;
-  uint64_t* tfull_bar = bars + 2 * kFusedStages;
-  if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("fence.proxy.async;" ::: "memory");  // earlier phases wrote A with ordinary stores
-      const uint64_t pol_a = policy_evict_last(), pol_w = policy_evict_normal();
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
-        uint8_t* sa = smem + ps.stage * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[ps.stage], stage_bytes);
-        tma_load_2d(sa, tm_a, &full_bar[ps.stage], kb * kBK, m_tile * kGemmBM, pol_a);
-        tma_load_2d(sa + kGemmABytes, tm_w, &full_bar[ps.stage], kb * kBK, n_tile * bn, pol_w);
-        if (++ps.stage == kFusedStages) {
-          ps.stage = 0;
-          ps.phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kGemmBM, bn);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[ps.stage], ps.phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + ps.stage * stage_bytes);
-        const uint64_t da = umma_desc_k_sw128(sa);
-        const uint64_t db = umma_desc_k_sw128(sa + kGemmABytes);
-#pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k)
-          umma_bf16(tmem_base, da + uint64_t(k * 2), db + uint64_t(k * 2), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[ps.stage]);
-        if (kb == kb1 - 1) umma_commit(tfull_bar);
-        if (++ps.stage == kFusedStages) {
-          ps.stage = 0;
-          ps.phase ^= 1;
-        }
-      }
-    }
-  } else if (warp < 6) {
-    const int quarter = warp & 3;
-    const int m = m_tile * kGemmBM + quarter * 32 + lane;
-    mbar_wait(tfull_bar, ps.tiles & 1u);
-    ++ps.tiles;
-    tc_fence_after();
-    const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16);
-#pragma unroll 1
-    for (int c = 0; c < bn / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_addr + c * 32, v);
-      tmem_ld_wait();
-      const int n0 = n_tile * bn + c * 32;
-      if (m < M) {
-        if (out != nullptr) {
-          uint32_t packed[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-            if (bias != nullptr) {
-              const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(bias + n0 + j);
-              a += __bfloat162float(bb.x);
-              b += __bfloat162float(bb.y);
-            }
-            if (gelu) {
-              a = gelu_erf(a);
-              b = gelu_erf(b);
-            }
-            const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
-            packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&r);
-          }
-          uint4* dst = reinterpret_cast<uint4*>(out + size_t(m) * N + n0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        } else {
-          float4* dst = reinterpret_cast<float4*>(partial + (size_t(split) * M + m) * N + n0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        }
-      }
-    }
-    tc_fence_before();
-  }
-}
-
-// residual + split-K partial sums + bias -> LayerNorm, one row per 128-thread half of the CTA (d = 1024)
-__device__ __forceinline__ void fused_layernorm(const __nv_bfloat16* __restrict__ resid, const float* __restrict__ partial,
-                                                int splits, const __nv_bfloat16* __restrict__ bias,
-                                                const __nv_bfloat16* __restrict__ gamma,
-                                                const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out,
-                                                int M, int d, float eps, float* red /* [2][4] */) {
-  const int half = threadIdx.x >> 7, t = threadIdx.x & 127, lane = t & 31, w = t >> 5;
-  const int c = t * 8;
-  float* my_red = red + half * 4;
-  auto half_sum = [&](float v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    if (lane == 0) my_red[w] = v;
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-    const float r = my_red[0] + my_red[1] + my_red[2] + my_red[3];
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-    return r;
-  };
-  for (int row = int(blockIdx.x) + int(gridDim.x) * half; row < M; row += 2 * int(gridDim.x)) {
-    const uint4 rv = *reinterpret_cast<const uint4*>(resid + size_t(row) * d + c);
-    const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + c));
-    const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c));
-    const uint4 ev = __ldg(reinterpret_cast<const uint4*>(beta + c));
-    float4 pa[kMaxSplits], pb[kMaxSplits];
-#pragma unroll
-    for (int sp = 0; sp < kMaxSplits; ++sp) {
-      if (sp < splits) {
-        const float4* pp = reinterpret_cast<const float4*>(partial + (size_t(sp) * M + row) * d + c);
-        pa[sp] = pp[0];
-        pb[sp] = pp[1];
-      }
-    }
-    const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      x[2 * j] = bf16lo_to_f32(rw[j]) + bf16lo_to_f32(bw[j]);
-      x[2 * j + 1] = bf16hi_to_f32(rw[j]) + bf16hi_to_f32(bw[j]);
-    }
-#pragma unroll
-    for (int sp = 0; sp < kMaxSplits; ++sp) {
-      if (sp < splits) {
-        x[0] += pa[sp].x; x[1] += pa[sp].y; x[2] += pa[sp].z; x[3] += pa[sp].w;
-        x[4] += pb[sp].x; x[5] += pb[sp].y; x[6] += pb[sp].z; x[7] += pb[sp].w;
-      }
-    }
-    float s1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s1 += x[j];
-    const float mean = half_sum(s1) / d;
-    float s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float tt = x[j] - mean;
-      s2 = fmaf(tt, tt, s2);
-    }
-    const float rstd = rsqrtf(half_sum(s2) / d + eps);
-    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ew[4] = {ev.x, ev.y, ev.z, ev.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float a = (x[2 * j] - mean) * rstd * bf16lo_to_f32(gw[j]) + bf16lo_to_f32(ew[j]);
-      const float b = (x[2 * j + 1] - mean) * rstd * bf16hi_to_f32(gw[j]) + bf16hi_to_f32(ew[j]);
-      const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
-      o[j] = *reinterpret_cast<const uint32_t*>(&r);
-    }
-    *reinterpret_cast<uint4*>(out + size_t(row) * d + c) = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-}
-
-__global__ void __launch_bounds__(kFusedThreads, 1)
-    k8_cama_fused_kernel(const __grid_constant__ FusedMaps maps, const __grid_constant__ FusedArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFusedSmem - 256 - 1024);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kFusedStages + 1);
-  float* red = reinterpret_cast<float*>(bars + 2 * kFusedStages + 2);  // [2][4] LayerNorm scratch
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < kFusedStages; ++s) {
-      mbar_init(&bars[s], 1);
-      mbar_init(&bars[kFusedStages + s], 1);
-    }
-    mbar_init(&bars[2 * kFusedStages], 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  PipeState ps;
-  unsigned int sync_target = 0;
-  int n_stamp = 0;
-  auto stamp = [&]() {
-    if (a.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      a.stamps[n_stamp] = t;
-    }
-    ++n_stamp;
-  };
-  stamp();
-  const int zblocks = (a.gtok + 31) / 32;
-  const int n_items = a.b * a.heads * a.groups * zblocks;
-
-  for (int l = 0; l < a.n_layers; ++l) {
-    const FusedLayer& w = a.layers[l];
-    const CUtensorMap* a_in = (l == 0) ? &maps.a_xin : &maps.a_xb;
-    const __nv_bfloat16* xin = (l == 0) ? a.x_in : a.x_b;
-    __nv_bfloat16* x2 = (l == a.n_layers - 1) ? a.y_out : a.x_b;
-    // qkv = x Wqkv^T + b
-    fused_gemm(smem, bars, tmem_base, a_in, &maps.w[l][0], a.M, 3 * a.d, a.d, a.bn_qkv, 1, w.b_qkv, 0, a.qkv, nullptr,
-               ps, warp, lane);
-    stamp();
-    fused_grid_sync(a.sync_counter, sync_target);
-    stamp();
-    // block-causal attention, longest key prefixes first
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int per_g = a.b * a.heads * zblocks;
-      const int g = a.groups - 1 - it / per_g, r = it % per_g;
-      const int bh = r / zblocks, zb = r % zblocks;
-      attention_item(smem, a.qkv, a.att, a.T, a.d, a.gtok, a.scale_log2e, bh / a.heads, bh % a.heads, g, zb,
-                     kFusedThreads);
-      __syncthreads();
-    }
-    stamp();
-    fused_grid_sync(a.sync_counter, sync_target);
-    stamp();
-    // p = att Wo^T (split K)
-    fused_gemm(smem, bars, tmem_base, &maps.a_att, &maps.w[l][1], a.M, a.d, a.d, a.bn_o, a.so, nullptr, 0, nullptr,
-               a.partial, ps, warp, lane);
-    stamp();
-    fused_grid_sync(a.sync_counter, sync_target);
-    stamp();
-    fused_layernorm(xin, a.partial, a.so, w.b_o, w.ln1_g, w.ln1_b, a.x_a, a.M, a.d, a.eps, red);
-    stamp();
-    fused_grid_sync(a.sync_counter, sync_target);
-    stamp();
-    // h = gelu(x1 W1^T + b1)
-    fused_gemm(smem, bars, tmem_base, &maps.a_xa, &maps.w[l][2], a.M, a.dff, a.d, a.bn_1, 1, w.b_1, 1, a.h, nullptr, ps,
-               warp, lane);
-    stamp();
-    fused_grid_sync(a.sync_counter, sync_target);
-    stamp();
-    // p = h W2^T (split K)
-    fused_gemm(smem, bars, tmem_base, &maps.a_h, &maps.w[l][3], a.M, a.d, a.dff, a.bn_2, a.sf, nullptr, 0, nullptr,
-               a.partial, ps, warp, lane);
-    stamp();
-    fused_grid_sync(a.sync_counter, sync_target);
-    stamp();
-    fused_layernorm(a.x_a, a.partial, a.sf, w.b_2, w.ln2_g, w.ln2_b, x2, a.M, a.d, a.eps, red);
-    stamp();
-    if (l + 1 < a.n_layers) fused_grid_sync(a.sync_counter, sync_target);
-    stamp();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
-  }
-}
-
 // ---- host side ---------------------------------------------------------------------------------
 static cudaError_t launch_pdl(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args,
                               unsigned cluster_z = 1) {
@@ -1352,95 +1034,6 @@ cudaError_t launch_k7_add_layernorm(const void* resid, const float* partial, int
   cudaError_t e = launch_pdl(reinterpret_cast<const void*>(k7_add_layernorm_kernel), dim3(unsigned(M)),
                              dim3(unsigned(d / 8)), 0, st, args);
   note_launch();
-  return e != cudaSuccess ? e : cudaGetLastError();
-}
-
-// ---- fused forward: host side --------------------------------------------------------------------
-// tile width / K splits of one GEMM phase so that it has at most `ctas` tiles; false if impossible
-static bool fused_pick(int M, int N, int K, int max_splits, int ctas, int* bn, int* splits) {
-  const int tiles128 = ((M + kGemmBM - 1) / kGemmBM) * (N / 128);
-  if (tiles128 > ctas) return false;
-  int sp = 1;
-  while (sp * 2 <= max_splits && tiles128 * sp * 2 <= ctas && (K / kBK) % (sp * 2) == 0) sp *= 2;
-  *splits = sp;
-  *bn = (tiles128 * sp * 2 <= ctas) ? 64 : 128;
-  return true;
-}
-
-bool k8_fused_supported(int b, int T, int d, int dff, int heads, int n_layers, int sm_count) {
-  const int M = b * T;
-  int bn, sp;
-  return d == 1024 && heads * kHeadDim == d && n_layers >= 1 && n_layers <= kFusedMaxLayers && T <= 256 &&
-         fused_pick(M, 3 * d, d, 1, sm_count, &bn, &sp) && fused_pick(M, d, d, 4, sm_count, &bn, &sp) &&
-         fused_pick(M, dff, d, 1, sm_count, &bn, &sp) && fused_pick(M, d, dff, kMaxSplits, sm_count, &bn, &sp);
-}
-
-cudaError_t launch_k8_cama_fused(const K8Buffers& buf, const K8LayerWeights* layers, int n_layers, int b, int T, int d,
-                                 int dff, int heads, int groups, int gtok, int rows_alloc, unsigned int* sync_counter,
-                                 int sm_count, cudaStream_t st) {
-  if (!k8_fused_supported(b, T, d, dff, heads, n_layers, sm_count)) return cudaErrorInvalidValue;
-  FusedArgs a{};
-  FusedMaps maps{};
-  a.b = b;
-  a.M = b * T;
-  a.T = T;
-  a.d = d;
-  a.dff = dff;
-  a.heads = heads;
-  a.groups = groups;
-  a.gtok = gtok;
-  a.n_layers = n_layers;
-  int one;
-  fused_pick(a.M, 3 * d, d, 1, sm_count, &a.bn_qkv, &one);
-  fused_pick(a.M, d, d, 4, sm_count, &a.bn_o, &a.so);
-  fused_pick(a.M, dff, d, 1, sm_count, &a.bn_1, &one);
-  fused_pick(a.M, d, dff, kMaxSplits, sm_count, &a.bn_2, &a.sf);
-  a.scale_log2e = 1.4426950408889634f / sqrtf(float(kHeadDim));
-  a.eps = 1e-5f;
-  a.x_in = static_cast<__nv_bfloat16*>(buf.x_in);
-  a.x_a = static_cast<__nv_bfloat16*>(buf.x_a);
-  a.x_b = static_cast<__nv_bfloat16*>(buf.x_b);
-  a.att = static_cast<__nv_bfloat16*>(buf.att);
-  a.y_out = static_cast<__nv_bfloat16*>(buf.y_out);
-  a.qkv = static_cast<__nv_bfloat16*>(buf.qkv);
-  a.h = static_cast<__nv_bfloat16*>(buf.h);
-  a.partial = buf.partial;
-  a.sync_counter = sync_counter;
-  a.stamps = getenv("MRAG_CAMA_FUSED_STAMPS") ? reinterpret_cast<unsigned long long*>(sync_counter + 16) : nullptr;
-  bool ok = make_tmap(&maps.a_xin, buf.x_in, rows_alloc, d, kGemmBM) && make_tmap(&maps.a_xb, buf.x_b, rows_alloc, d, kGemmBM) &&
-            make_tmap(&maps.a_att, buf.att, rows_alloc, d, kGemmBM) && make_tmap(&maps.a_xa, buf.x_a, rows_alloc, d, kGemmBM) &&
-            make_tmap(&maps.a_h, buf.h, rows_alloc, dff, kGemmBM);
-  for (int l = 0; l < n_layers && ok; ++l) {
-    const K8LayerWeights& w = layers[l];
-    a.layers[l] = FusedLayer{static_cast<const __nv_bfloat16*>(w.b_qkv), static_cast<const __nv_bfloat16*>(w.b_o),
-                             static_cast<const __nv_bfloat16*>(w.b_1),   static_cast<const __nv_bfloat16*>(w.b_2),
-                             static_cast<const __nv_bfloat16*>(w.ln1_g), static_cast<const __nv_bfloat16*>(w.ln1_b),
-                             static_cast<const __nv_bfloat16*>(w.ln2_g), static_cast<const __nv_bfloat16*>(w.ln2_b)};
-    ok = make_tmap(&maps.w[l][0], w.w_qkv, 3 * d, d, a.bn_qkv) && make_tmap(&maps.w[l][1], w.w_o, d, d, a.bn_o) &&
-         make_tmap(&maps.w[l][2], w.w_1, dff, d, a.bn_1) && make_tmap(&maps.w[l][3], w.w_2, d, dff, a.bn_2);
-  }
-  if (!ok) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(k8_cama_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmem));
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(sync_counter, 0, sizeof(unsigned int), st);
-  if (e != cudaSuccess) return e;
-  void* args[] = {&maps, &a};
-  // cooperative launch: the grid barrier needs every CTA resident (one per SM)
-  e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k8_cama_fused_kernel), dim3(unsigned(sm_count)),
-                                  dim3(kFusedThreads), args, kFusedSmem, st);
-  note_launch();
-  if (e == cudaSuccess && a.stamps != nullptr) {  // tuning aid: print the phase timeline of CTA 0
-    unsigned long long h[14 * kFusedMaxLayers + 1];
-    cudaStreamSynchronize(st);
-    cudaMemcpy(h, a.stamps, sizeof(h), cudaMemcpyDeviceToHost);
-    static const char* names[14] = {"qkv", "sync", "attn", "sync", "out", "sync", "ln1", "sync",
-                                    "ffn1", "sync", "ffn2", "sync", "ln2", "sync"};
-    for (int l = 0; l < n_layers; ++l) {
-      fprintf(stderr, "fused layer %d:", l);
-      for (int i = 0; i < 14; ++i) fprintf(stderr, " %s %.1f", names[i], double(h[14 * l + i + 1] - h[14 * l + i]) / 1e3);
-      fprintf(stderr, " us\n");
-    }
-  }
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -115,17 +115,4 @@ cudaError_t launch_k7_add_layernorm(const void* resid, const float* partial, int
                                     const void* gamma, const void* beta, void* out, int M, int d, float eps,
                                     cudaStream_t st);
 
-// K8: the whole transformer forward as one cooperative kernel (one or two samples; opt-in)
-struct K8Buffers {
-  void *x_in, *x_a, *x_b, *att, *y_out, *qkv, *h;
-  float* partial;
-};
-struct K8LayerWeights {
-  const void *w_qkv, *b_qkv, *w_o, *b_o, *w_1, *b_1, *w_2, *b_2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-};
-bool k8_fused_supported(int b, int T, int d, int dff, int heads, int n_layers, int sm_count);
-cudaError_t launch_k8_cama_fused(const K8Buffers& buf, const K8LayerWeights* layers, int n_layers, int b, int T, int d,
-                                 int dff, int heads, int groups, int gtok, int rows_alloc, unsigned int* sync_counter,
-                                 int sm_count, cudaStream_t st);
-
 }  // namespace mrag

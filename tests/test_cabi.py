@@ -72,13 +72,13 @@ def test_library_contains_blackwell_sass(libmrag):
     assert "UTCHMMA" in sass and "LDTM" in sass and "UTMALDG" in sass
     assert "HGMMA" not in sass
     # warp-level mma.sync is allowed in one place only: the 25-row block-causal attention tiles of K6
-    # (far below a tcgen05 tile) — also inlined into the fused forward K8; the scan and every GEMM must be on tcgen05
+    # (far below a tcgen05 tile); the scan and every GEMM must be on tcgen05
     fn = None
     for line in sass.splitlines():
         if "Function :" in line:
             fn = line.split("Function :")[1].strip()
         elif "HMMA.16816" in line:
-            assert fn is not None and ("k6_attention" in fn or "k8_cama_fused" in fn), fn
+            assert fn is not None and "k6_attention" in fn, fn
     elf = subprocess.run(["cuobjdump", "-lelf", str(_cabi.LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in elf
 

@@ -507,6 +507,33 @@ def run_ours(args):
                             "roofline": {"bound": "hbm" if b >= 256 else "latency (one short wave: %d CTAs)" % (b * 10 * 4),
                                          "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                                          "bytes_per_launch": nbytes}}
+            # the kernel without the host: 16 launches (16 different index sets) captured once, replayed as a graph.
+            # At b = 1 / 16 the eager figure above is the Python + launch cost of one call, not the kernel.
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    ctx.build(idx[0], cond, out)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for i in range(16):
+                        ctx.build(idx[i], cond, out)
+                reps = 3 if b == 4096 else 50
+                for _ in range(2):
+                    graph.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ms_k = e0.elapsed_time(e1) / (reps * 16)
+                res[f"b{b}"]["kernel_ms_graph_replay"] = ms_k
+                res[f"b{b}"]["roofline"]["frac_graph_replay"] = nbytes / (ms_k / 1e3) / 1e9 / pk["hbm_gbs"]
+                del graph
+            except Exception as e:   # noqa: BLE001
+                res[f"b{b}"]["graph_replay_error"] = f"{type(e).__name__}: {e}"[:200]
         feats.clear()
         torch.cuda.empty_cache()
         return res
@@ -552,23 +579,70 @@ def run_ours(args):
         res = {"workload": "CAMA forward: 4 layers, d_model 1024, 16 heads, d_ff 4096, 250 tokens, bf16, CUDA-graph replay",
                "kernels": "k5_linear_kernel / k5_linear_pair_kernel (tcgen05), k6_attention_kernel, k7_add_layernorm_kernel; 28 launches/forward"}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for b in (1, 16):
-            cama.input_view(b).normal_()
+
+        def timed(fn, n):
             for _ in range(warmup):
-                cama.forward(b=b)
+                fn()
             torch.cuda.synchronize()
             e0.record()
-            for _ in range(steps):
-                cama.forward(b=b)
+            for _ in range(n):
+                fn()
             e1.record()
             torch.cuda.synchronize()
-            us = e0.elapsed_time(e1) / steps * 1e3
+            return e0.elapsed_time(e1) / n * 1e3
+
+        def gemm_flop(rows):      # the four GEMMs of one layer over `rows` token rows
+            return 2.0 * rows * C_FEAT * (3 * C_FEAT + C_FEAT + 2 * 4096)
+
+        def attn_flop(b, groups):  # block-causal attention: group gi sees (gi+1)*L keys; QK^T and PV
+            return sum(b * 16 * 2 * (2.0 * L_TOK * (gi + 1) * L_TOK * 64) for gi in groups)
+
+        enc_bf16 = None
+        xs_all = {b: torch.randn(b, T, C_FEAT, device=dev).bfloat16() for b in (1, 16)}   # before any graph capture
+        for b in (1, 16):
+            cama.input_view(b).copy_(xs_all[b])
+            us = timed(lambda: cama.forward(b=b), steps)
             M = b * T
-            flop = 4 * (2.0 * M * C_FEAT * (3 * C_FEAT + C_FEAT + 2 * 4096))
-            for gi in range(K_REF + 1):     # block-causal attention: group gi sees (gi+1)*L keys
-                flop += 4 * b * 16 * 2 * (2.0 * L_TOK * (gi + 1) * L_TOK * 64)
-            res[f"b{b}"] = {"us_per_forward": us, "samples_per_s": b / (us * 1e-6), "tflops": flop / (us * 1e-6) / 1e12,
-                            "frac_of_tensor_peak": flop / (us * 1e-6) / 1e12 / pk["bf16_tflops"]}
+            flop = 4 * (gemm_flop(M) + attn_flop(b, range(K_REF + 1)))
+            tf = flop / (us * 1e-6) / 1e12
+            res[f"b{b}"] = {"us_per_forward": us, "samples_per_s": b / (us * 1e-6), "tflops": tf,
+                            "frac_of_tensor_peak": tf / pk["bf16_tflops"],
+                            "roofline": {"bound": "tensor" if b >= 16 else "latency (28 dependent launches of < 1 wave each)",
+                                         "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
+                                         "flop_per_forward": flop, "peak_source": pk["source"]}}
+            # predict(): what ActionTransformer.predict needs (module.py:326 keeps the last group only) — the last
+            # layer runs attention / out-proj / FFN / LayerNorms on that group's 25 rows per sample; executed flops
+            us_p = timed(lambda: cama.predict(b=b), steps)
+            flop_p = (3 * (gemm_flop(M) + attn_flop(b, range(K_REF + 1))) + 2.0 * M * C_FEAT * 3 * C_FEAT
+                      + attn_flop(b, [K_REF]) + 2.0 * b * L_TOK * C_FEAT * (C_FEAT + 2 * 4096))
+            res[f"b{b}"]["predict"] = {"us": us_p, "samples_per_s": b / (us_p * 1e-6), "executed_tflops": flop_p / (us_p * 1e-6) / 1e12,
+                                       "frac_of_tensor_peak": flop_p / (us_p * 1e-6) / 1e12 / pk["bf16_tflops"]}
+            # torch baseline: the reference's own module (torch.nn.TransformerEncoder, bf16) under the same mask,
+            # eager and replayed as ONE CUDA graph (so launch overhead is taken out of the comparison)
+            try:
+                import copy
+                if enc_bf16 is None:
+                    enc_bf16 = copy.deepcopy(enc).to(dev).bfloat16().eval()
+                mask = m.context.block_causal_mask(K_REF + 1, L_TOK, dev)
+                xs = xs_all[b]
+                with torch.no_grad():
+                    # is_causal=False: without it the module compares the mask with a triangular one on every call
+                    # (a device->host sync, illegal inside a capture); the mask itself is still applied
+                    res[f"b{b}"]["torch_bf16_eager_us"] = timed(lambda: enc_bf16(xs, mask, is_causal=False), max(10, steps // 2))
+                    side = torch.cuda.Stream(device=dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        for _ in range(3):
+                            enc_bf16(xs, mask, is_causal=False)
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        ys = enc_bf16(xs, mask, is_causal=False)
+                    res[f"b{b}"]["torch_bf16_cuda_graph_us"] = timed(graph.replay, steps)
+                    del graph, ys
+            except Exception as e:   # noqa: BLE001
+                res[f"b{b}"]["torch_baseline_error"] = f"{type(e).__name__}: {e}"[:200]
+        del enc_bf16
         # one query end to end on the device: scan + select + gather into the transformer's input + forward
         st, retr, rps, lo, hi = get_store(1_000_000, "clustered")
         q, ex = make_queries(st, 1, 21)                   # [POOL, 1, DIM], own-group ids [POOL, 1]
@@ -600,8 +674,11 @@ def run_ours(args):
     main = measure(args.workload, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
     extra = {}
     if not args.no_extras:
+        only = set(filter(None, args.extras.split(",")))
         todo = [w for w in ("c0", "c0loop", "c1", "c1q4", "c1f", "c2", "c4", "c3q1", "c3q4096") if w != args.workload]
         for w in todo:
+            if only and w not in only:
+                continue
             try:
                 steps = 200 if WORKLOADS[w][1] == 1 else (30 if WORKLOADS[w][1] <= 64 else 8)
                 extra[w] = measure(w, steps, 3, with_e2e=(w in ("c0", "c0loop", "c2", "c4")))
@@ -610,6 +687,8 @@ def run_ours(args):
         if world == 1:
             for key, fn in (("bulk_annotations", measure_bulk), ("k4_gather", measure_gather),
                             ("cama_forward", measure_cama)):
+                if only and key not in only:
+                    continue
                 try:
                     extra[key] = fn()
                 except Exception as e:
@@ -733,6 +812,7 @@ def main():
     ap.add_argument("--workload", default="c1", choices=list(WORKLOADS))
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras", default="", help="comma-separated subset of the extra measurements (default: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MRAG_ABI_VERSION 3
+#define MRAG_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MRAG_API __attribute__((visibility("default")))
@@ -277,6 +277,13 @@ MRAG_API int mrag_cama_io(const mrag_cama* c, void** x_in_dev, void** y_out_dev)
 /* runs the n_layers forward for the first b samples of the input buffer on `stream`; with use_graph
  * the 7*n_layers launch chain is captured once per b and replayed as one CUDA graph */
 MRAG_API int mrag_cama_forward(mrag_cama* c, int32_t b, int32_t use_graph, void* stream);
+/* ActionTransformer.predict (src/projects/condition/module.py:325-326 keeps `[:, -1]`, the last group of the
+ * output): the same forward, but the last layer computes attention, out-projection, FFN and LayerNorms for the
+ * last group's rows only. *y_last_dev (optional) receives the device pointer of the result
+ * [b, group_tokens, d_model] bf16, owned by the handle and valid until the next call. Rows equal those of
+ * mrag_cama_forward's output up to the fp32 summation order of the split-K GEMMs (the K split is chosen per
+ * row count). */
+MRAG_API int mrag_cama_predict(mrag_cama* c, int32_t b, int32_t use_graph, void* stream, void** y_last_dev);
 /* the GEMM building block on its own (tests / profiling): C[M,N] = A[M,K] W[N,K]^T (+bias)(gelu) to
  * bf16 (splits > 1: split-K summed inside a thread-block cluster, splits a power of two <= 8), or fp32
  * partial sums [splits][M,N] when out_bf16_dev is NULL; N %% 128 == 0, K %% 64 == 0, splits | K/64 */

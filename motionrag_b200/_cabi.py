@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "libmrag.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums of include/mrag.h
 METRIC = {"l2": 0, "cosine": 1, "dot": 2}
@@ -98,6 +98,7 @@ SIGNATURES = {
     "mrag_cama_destroy": (C.c_int, [C.c_void_p]),
     "mrag_cama_io": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "mrag_cama_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "mrag_cama_predict": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "mrag_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                               C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "mrag_device_alloc": (C.c_int, [C.c_int32, C.c_size_t, C.POINTER(C.c_void_p)]),

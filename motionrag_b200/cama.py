@@ -64,6 +64,7 @@ class CamaTransformer:
         shape = (self.max_batch, self.tokens, self.d_model)
         self.x_in = _view(xin.value, shape, torch.bfloat16, self.device, self)
         self.y_out = _view(yout.value, shape, torch.bfloat16, self.device, self)
+        self._y_last = None
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -93,9 +94,22 @@ class CamaTransformer:
         check(self._lib.mrag_cama_forward(self._h, int(b), 1 if use_graph else 0, _stream_ptr(self.device)))
         return self.y_out[:b]
 
-    def predict(self, x: torch.Tensor | None = None, b: int | None = None) -> torch.Tensor:
-        """ActionTransformer.predict's slice (module.py:326): the last group's tokens [b, L, d]."""
-        return self.forward(x, b)[:, -self.group_tokens:]
+    def predict(self, x: torch.Tensor | None = None, b: int | None = None, use_graph: bool = True) -> torch.Tensor:
+        """ActionTransformer.predict's slice (module.py:326): the last group's tokens [b, L, d] — a view of the
+        handle's prediction buffer, valid until the next call. The last layer only computes that group's rows
+        (mrag_cama_predict); the values equal forward(...)[:, -L:] up to the fp32 summation order of the split-K GEMMs."""
+        if x is not None:
+            b = x.shape[0]
+            if tuple(x.shape[1:]) != (self.tokens, self.d_model):
+                raise ValueError(f"x must be [b, {self.tokens}, {self.d_model}]")
+            self.x_in[:b].copy_(x)
+        if b is None:
+            raise ValueError("pass x or b")
+        ptr = C.c_void_p()
+        check(self._lib.mrag_cama_predict(self._h, int(b), 1 if use_graph else 0, _stream_ptr(self.device), C.byref(ptr)))
+        if self._y_last is None or self._y_last.data_ptr() != ptr.value:
+            self._y_last = _view(ptr.value, (self.max_batch, self.group_tokens, self.d_model), torch.bfloat16, self.device, self)
+        return self._y_last[:b]
 
 
 def linear(a: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, gelu: bool = False,

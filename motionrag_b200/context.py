@@ -221,11 +221,8 @@ def attach(model, ctx: MotionContext, transformer=None):
             return model.get_loss(pred[:, -1:], vision_emb[:, -1:])
         return model.get_loss(pred, vision_emb)
 
-    def batch_forward(batch, return_loss: bool = True, ignore_ref_loss: bool = False):
-        if 'ref_index' not in batch and 'ref_features' not in batch:
-            return orig(batch, return_loss, ignore_ref_loss)
-        if return_loss:
-            return loss_forward(batch, ignore_ref_loss)
+    def run(batch, last_only: bool):
+        """Gather the context and run the transformer; last_only -> [b, L, C] (the slice predict keeps)."""
         cond = model.encode_condition(batch['ref_images']) if 'ref_images' in batch else batch.get('condition_emb')
         by_index = 'ref_index' in batch
         b, K = (batch['ref_index'] if by_index else batch['ref_features']).shape[:2]
@@ -238,20 +235,30 @@ def attach(model, ctx: MotionContext, transformer=None):
         if transformer is None:
             x = build()
             pred = model.transformer(x, ctx.get_mask(K + 1, ctx.table.L))
-        else:
-            if (K + 1, ctx.table.L) != (transformer.groups, transformer.group_tokens):
-                raise ValueError(f"transformer was built for {transformer.groups} groups of "
-                                 f"{transformer.group_tokens} tokens, got {K + 1} x {ctx.table.L}")
-            build(out=transformer.input_view(b))
-            pred = transformer.forward(b=b)
+            pred = pred.reshape(pred.shape[0], K + 1, ctx.table.L, -1)
+            return pred[:, -1] if last_only else pred
+        if (K + 1, ctx.table.L) != (transformer.groups, transformer.group_tokens):
+            raise ValueError(f"transformer was built for {transformer.groups} groups of "
+                             f"{transformer.group_tokens} tokens, got {K + 1} x {ctx.table.L}")
+        build(out=transformer.input_view(b))
+        if last_only:      # the last layer then only computes the last group's rows (mrag_cama_predict)
+            return transformer.predict(b=b)
+        pred = transformer.forward(b=b)
         return pred.reshape(pred.shape[0], K + 1, ctx.table.L, -1)
+
+    def batch_forward(batch, return_loss: bool = True, ignore_ref_loss: bool = False):
+        if 'ref_index' not in batch and 'ref_features' not in batch:
+            return orig(batch, return_loss, ignore_ref_loss)
+        if return_loss:
+            return loss_forward(batch, ignore_ref_loss)
+        return run(batch, last_only=False)
 
     def predict(batch, do_classifier_free_guidance: bool = False):
         if 'ref_index' not in batch and 'ref_features' not in batch:
             if orig_predict is None:
                 raise AttributeError("the wrapped model has no predict() for the video path")
             return orig_predict(batch, do_classifier_free_guidance)
-        action_emb = batch_forward(batch, return_loss=False)[:, -1]
+        action_emb = run(batch, last_only=True)
         if do_classifier_free_guidance:
             action_emb = torch.cat([ctx.uncond_action_emb(action_emb.shape[0]).to(action_emb.dtype), action_emb], dim=0)
         return action_emb

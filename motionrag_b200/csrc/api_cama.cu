@@ -22,10 +22,12 @@ struct mrag_cama {
   std::vector<mrag_cama_layer> layers;
   char* buf = nullptr;  // one allocation, carved below
   void *x_in = nullptr, *x_a = nullptr, *x_b = nullptr, *qkv = nullptr, *att = nullptr, *h = nullptr, *y_out = nullptr;
+  void* y_last = nullptr;  // [max_b, group_tokens, d] bf16: the last group's rows of the prediction (mrag_cama_predict)
   float* partial = nullptr;
   int sm_count = 0;
   struct Graph {
     int b;
+    bool last_only;
     cudaGraphExec_t exec;
   };
   std::vector<Graph> graphs;
@@ -74,7 +76,11 @@ struct Guard {
   }
 };
 
-cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
+// last_only: ActionTransformer.predict keeps only the last group of the output (module.py:326), so the
+// LAST layer runs its attention, out-projection, FFN and both LayerNorms for that group's rows alone
+// (b * group_tokens compact rows instead of b * T); K and V are still needed for every row, so its QKV
+// GEMM stays whole. The result lands in y_last [b, group_tokens, d].
+cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st, bool last_only) {
   const int M = b * c->T, d = c->d, dff = c->dff;
   const void* xin = c->x_in;
   cudaError_t e = cudaSuccess;
@@ -83,8 +89,27 @@ cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
   for (int l = 0; l < c->n_layers && e == cudaSuccess; ++l) {
     const mrag_cama_layer& w = c->layers[l];
     void* x1 = c->x_a;
-    void* x2 = (l == c->n_layers - 1) ? c->y_out : c->x_b;
+    const bool tail = last_only && l == c->n_layers - 1;
     e = launch_k5_linear(xin, c->rows_alloc, w.w_qkv, M, 3 * d, d, w.b_qkv, false, c->qkv, nullptr, sq, st);
+    if (tail) {
+      const int Ml = b * c->gtok;
+      const int sol = pick_splits(Ml, d, kSplitsO), sfl = pick_splits(Ml, d, kSplitsF);
+      const int s1l = pick_cluster_splits(Ml, dff, d);
+      if (e == cudaSuccess)
+        e = launch_k6_attention(c->qkv, c->att, b, c->T, d, c->heads, c->groups, c->gtok, st, c->groups - 1);
+      if (e == cudaSuccess)
+        e = launch_k5_linear(c->att, c->rows_alloc, w.w_o, Ml, d, d, nullptr, false, nullptr, c->partial, sol, st);
+      if (e == cudaSuccess)
+        e = launch_k7_add_layernorm(xin, c->partial, sol, w.b_o, w.ln1_g, w.ln1_b, x1, Ml, d, 1e-5f, st, c->T, c->gtok);
+      if (e == cudaSuccess)
+        e = launch_k5_linear(x1, c->rows_alloc, w.w_1, Ml, dff, d, w.b_1, true, c->h, nullptr, s1l, st);
+      if (e == cudaSuccess)
+        e = launch_k5_linear(c->h, c->rows_alloc, w.w_2, Ml, d, dff, nullptr, false, nullptr, c->partial, sfl, st);
+      if (e == cudaSuccess)
+        e = launch_k7_add_layernorm(x1, c->partial, sfl, w.b_2, w.ln2_g, w.ln2_b, c->y_last, Ml, d, 1e-5f, st);
+      break;
+    }
+    void* x2 = (l == c->n_layers - 1) ? c->y_out : c->x_b;
     if (e == cudaSuccess) e = launch_k6_attention(c->qkv, c->att, b, c->T, d, c->heads, c->groups, c->gtok, st);
     if (e == cudaSuccess)
       e = launch_k5_linear(c->att, c->rows_alloc, w.w_o, M, d, d, nullptr, false, nullptr, c->partial, so, st);
@@ -98,6 +123,44 @@ cudaError_t run_chain(const mrag_cama* c, int b, cudaStream_t st) {
     xin = x2;
   }
   return e;
+}
+
+int run_forward(mrag_cama* c, int32_t b, int32_t use_graph, void* stream, bool last_only) {
+  if (!c) return api_fail(MRAG_ERR_ARG, "null handle");
+  if (b < 1 || b > c->max_b) return api_fail(MRAG_ERR_ARG, "batch %d outside 1..%d", b, c->max_b);
+  Guard g(c->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!use_graph) {
+    cudaError_t e = run_chain(c, b, st, last_only);
+    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "transformer launch chain: %s", cudaGetErrorString(e));
+    return MRAG_OK;
+  }
+  cudaGraphExec_t exec = nullptr;
+  for (auto& gr : c->graphs)
+    if (gr.b == b && gr.last_only == last_only) exec = gr.exec;
+  if (!exec) {
+    if (!c->capture_stream &&
+        cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
+      return api_fail(MRAG_ERR_CUDA, "cannot create the capture stream");
+    cudaError_t e = cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e));
+    cudaError_t ce = run_chain(c, b, c->capture_stream, last_only);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(c->capture_stream, &graph);
+    if (ce != cudaSuccess || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      return api_fail(MRAG_ERR_CUDA, "capture of the transformer chain: %s",
+                      cudaGetErrorString(ce != cudaSuccess ? ce : e));
+    }
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+    c->graphs.push_back({b, last_only, exec});
+  }
+  cudaError_t e = cudaGraphLaunch(exec, st);
+  if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "graph launch: %s", cudaGetErrorString(e));
+  note_launch(7 * c->n_layers);
+  return MRAG_OK;
 }
 }  // namespace
 
@@ -143,7 +206,7 @@ int mrag_cama_create(int32_t n_layers, const mrag_cama_layer* layers, int32_t d_
   const size_t R = size_t(c->rows_alloc);
   const size_t sz_x = R * d_model * 2, sz_qkv = R * 3 * d_model * 2, sz_h = R * d_ff * 2;
   const size_t sz_p = size_t(kSplitsF) * R * d_model * 4;
-  const size_t total = 5 * sz_x + sz_qkv + sz_h + sz_p + 1024;
+  const size_t total = 6 * sz_x + sz_qkv + sz_h + sz_p + 1024;
   c->sm_count = prop.multiProcessorCount;
   if (cudaMalloc(reinterpret_cast<void**>(&c->buf), total) != cudaSuccess) {
     cudaGetLastError();
@@ -157,6 +220,7 @@ int mrag_cama_create(int32_t n_layers, const mrag_cama_layer* layers, int32_t d_
   c->x_b = p; p += sz_x;
   c->att = p; p += sz_x;
   c->y_out = p; p += sz_x;
+  c->y_last = p; p += sz_x;
   c->qkv = p; p += sz_qkv;
   c->h = p; p += sz_h;
   c->partial = reinterpret_cast<float*>(p); p += sz_p;
@@ -182,41 +246,13 @@ int mrag_cama_io(const mrag_cama* c, void** x_in_dev, void** y_out_dev) {
 }
 
 int mrag_cama_forward(mrag_cama* c, int32_t b, int32_t use_graph, void* stream) {
-  if (!c) return api_fail(MRAG_ERR_ARG, "null handle");
-  if (b < 1 || b > c->max_b) return api_fail(MRAG_ERR_ARG, "batch %d outside 1..%d", b, c->max_b);
-  Guard g(c->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!use_graph) {
-    cudaError_t e = run_chain(c, b, st);
-    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "transformer launch chain: %s", cudaGetErrorString(e));
-    return MRAG_OK;
-  }
-  cudaGraphExec_t exec = nullptr;
-  for (auto& gr : c->graphs)
-    if (gr.b == b) exec = gr.exec;
-  if (!exec) {
-    if (!c->capture_stream &&
-        cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking) != cudaSuccess)
-      return api_fail(MRAG_ERR_CUDA, "cannot create the capture stream");
-    cudaError_t e = cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "begin capture: %s", cudaGetErrorString(e));
-    cudaError_t ce = run_chain(c, b, c->capture_stream);
-    cudaGraph_t graph = nullptr;
-    e = cudaStreamEndCapture(c->capture_stream, &graph);
-    if (ce != cudaSuccess || e != cudaSuccess) {
-      if (graph) cudaGraphDestroy(graph);
-      return api_fail(MRAG_ERR_CUDA, "capture of the transformer chain: %s",
-                      cudaGetErrorString(ce != cudaSuccess ? ce : e));
-    }
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
-    c->graphs.push_back({b, exec});
-  }
-  cudaError_t e = cudaGraphLaunch(exec, st);
-  if (e != cudaSuccess) return api_fail(MRAG_ERR_CUDA, "graph launch: %s", cudaGetErrorString(e));
-  note_launch(7 * c->n_layers);
-  return MRAG_OK;
+  return run_forward(c, b, use_graph, stream, false);
+}
+
+int mrag_cama_predict(mrag_cama* c, int32_t b, int32_t use_graph, void* stream, void** y_last_dev) {
+  const int rc = run_forward(c, b, use_graph, stream, true);
+  if (rc == MRAG_OK && y_last_dev) *y_last_dev = c->y_last;
+  return rc;
 }
 
 int mrag_linear(const void* a_dev, int32_t a_rows_alloc, const void* w_dev, int32_t M, int32_t N, int32_t K,

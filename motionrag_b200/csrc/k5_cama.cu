@@ -637,7 +637,8 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
 // thread of the CTA (it contains CTA barriers); the first four warps compute, all threads help staging.
 __device__ __forceinline__ void attention_item(uint8_t* smem_attn, const __nv_bfloat16* __restrict__ qkv,
                                                __nv_bfloat16* __restrict__ out, int T, int d_model, int group_tokens,
-                                               float scale_log2e, int b, int h, int g, int zblk, int n_threads) {
+                                               float scale_log2e, int b, int h, int g, int zblk, int n_threads,
+                                               bool compact_out = false) {
   const int nk = (g + 1) * group_tokens;               // visible keys
   const int n_chunks = (nk + kKeyChunk - 1) / kKeyChunk;
   const int rows_pad = n_chunks * kKeyChunk;
@@ -788,8 +789,10 @@ __device__ __forceinline__ void attention_item(uint8_t* smem_attn, const __nv_bf
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.f / l0, i1 = 1.f / l1;
-    __nv_bfloat16* o0 = out + (size_t(b) * T + g * group_tokens + r0) * d_model + h * kHeadDim + 2 * qlane;
-    __nv_bfloat16* o1 = out + (size_t(b) * T + g * group_tokens + r1) * d_model + h * kHeadDim + 2 * qlane;
+    // compact_out: only one group is computed and its rows are written densely as [b][group_tokens]
+    const size_t orow = compact_out ? size_t(b) * group_tokens : size_t(b) * T + g * group_tokens;
+    __nv_bfloat16* o0 = out + (orow + r0) * d_model + h * kHeadDim + 2 * qlane;
+    __nv_bfloat16* o1 = out + (orow + r1) * d_model + h * kHeadDim + 2 * qlane;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float x0 = (o[j][0] * f0 + xch[(4 * j + 0) * 32 + lane] * g0) * i0;
@@ -804,13 +807,15 @@ __device__ __forceinline__ void attention_item(uint8_t* smem_attn, const __nv_bf
 
 __global__ void __launch_bounds__(kAttnThreads, 3)
     k6_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T,
-                        int d_model, int heads, int group_tokens, float scale_log2e) {
+                        int d_model, int heads, int group_tokens, float scale_log2e, int only_group) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int bh = blockIdx.x;
-  attention_item(smem_attn, qkv, out, T, d_model, group_tokens, scale_log2e, bh / heads, bh % heads,
-                 int(gridDim.y) - 1 - int(blockIdx.y) /* longest key prefixes first */, int(blockIdx.z), kAttnThreads);
+  // only_group >= 0 (grid.y == 1): just that group's query rows, written compactly (last layer of predict)
+  const int g = only_group >= 0 ? only_group : int(gridDim.y) - 1 - int(blockIdx.y) /* longest key prefixes first */;
+  attention_item(smem_attn, qkv, out, T, d_model, group_tokens, scale_log2e, bh / heads, bh % heads, g,
+                 int(blockIdx.z), kAttnThreads, only_group >= 0);
 }
 
 // ---- K7: y = LayerNorm(resid + sum_s partial[s] + bias) * gamma + beta ---------------------------
@@ -834,14 +839,17 @@ __global__ void __launch_bounds__(128)
     k7_add_layernorm_kernel(const __nv_bfloat16* __restrict__ resid, const float* __restrict__ partial,
                             int splits, const __nv_bfloat16* __restrict__ bias,
                             const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
-                            __nv_bfloat16* __restrict__ out, int M, int d, float eps) {
+                            __nv_bfloat16* __restrict__ out, int M, int d, float eps, int resid_T, int resid_L) {
   __shared__ float red[4];
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int row = blockIdx.x;
   const int c = tid * 8;
-  const uint4 rv = *reinterpret_cast<const uint4*>(resid + size_t(row) * d + c);
+  // resid_T > 0: the rows of this launch are the LAST resid_L tokens of each resid_T-token sample, stored
+  // compactly, while the residual stream still has all tokens (last layer of predict)
+  const size_t rrow = resid_T > 0 ? size_t(row / resid_L) * resid_T + (resid_T - resid_L) + row % resid_L : size_t(row);
+  const uint4 rv = *reinterpret_cast<const uint4*>(resid + rrow * d + c);
   const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + c));
   const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c));
   const uint4 ev = __ldg(reinterpret_cast<const uint4*>(beta + c));
@@ -1004,7 +1012,8 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
 }
 
 cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_model, int heads,
-                                int groups, int group_tokens, cudaStream_t st) {
+                                int groups, int group_tokens, cudaStream_t st, int only_group) {
+  if (only_group >= groups) return cudaErrorInvalidValue;
   if (d_model != heads * kHeadDim || groups * group_tokens != T || T > kAttnMaxT) return cudaErrorInvalidValue;
   const int rows_pad = (T + kKeyChunk - 1) / kKeyChunk * kKeyChunk;
   const size_t smem = size_t(rows_pad) * kKVStride * 2 * 2;
@@ -1013,9 +1022,9 @@ cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   float scale_log2e = 1.4426950408889634f / sqrtf(float(kHeadDim));
-  void* args[] = {&q, &o, &T, &d_model, &heads, &group_tokens, &scale_log2e};
+  void* args[] = {&q, &o, &T, &d_model, &heads, &group_tokens, &scale_log2e, &only_group};
   e = launch_pdl(reinterpret_cast<const void*>(k6_attention_kernel),
-                 dim3(unsigned(b * heads), unsigned(groups), unsigned((group_tokens + 31) / 32)),
+                 dim3(unsigned(b * heads), unsigned(only_group >= 0 ? 1 : groups), unsigned((group_tokens + 31) / 32)),
                  dim3(kAttnThreads), smem, st, args);
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
@@ -1023,14 +1032,14 @@ cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_
 
 cudaError_t launch_k7_add_layernorm(const void* resid, const float* partial, int splits, const void* bias,
                                     const void* gamma, const void* beta, void* out, int M, int d, float eps,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, int resid_T, int resid_L) {
   if (d % 256 != 0 || d > 1024 || splits > kMaxSplits) return cudaErrorInvalidValue;
   const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(resid);
   const __nv_bfloat16* bi = static_cast<const __nv_bfloat16*>(bias);
   const __nv_bfloat16* ga = static_cast<const __nv_bfloat16*>(gamma);
   const __nv_bfloat16* be = static_cast<const __nv_bfloat16*>(beta);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-  void* args[] = {&r, &partial, &splits, &bi, &ga, &be, &o, &M, &d, &eps};
+  void* args[] = {&r, &partial, &splits, &bi, &ga, &be, &o, &M, &d, &eps, &resid_T, &resid_L};
   cudaError_t e = launch_pdl(reinterpret_cast<const void*>(k7_add_layernorm_kernel), dim3(unsigned(M)),
                              dim3(unsigned(d / 8)), 0, st, args);
   note_launch();

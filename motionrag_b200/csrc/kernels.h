@@ -109,10 +109,13 @@ cudaError_t launch_k3_rescore_rows(const float* db_f32, int64_t n_rows, int dim,
 cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w_bf16, int M, int N, int K,
                              const void* bias, bool gelu, void* out_bf16, float* partial, int splits,
                              cudaStream_t st);
+// only_group >= 0: just that group's query rows, output rows written compactly as [b][group_tokens]
 cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_model, int heads,
-                                int groups, int group_tokens, cudaStream_t st);
+                                int groups, int group_tokens, cudaStream_t st, int only_group = -1);
+// resid_T > 0: the M rows are the last resid_L tokens of every resid_T-token sample (compact), the
+// residual is read from the full-length stream
 cudaError_t launch_k7_add_layernorm(const void* resid, const float* partial, int splits, const void* bias,
                                     const void* gamma, const void* beta, void* out, int M, int d, float eps,
-                                    cudaStream_t st);
+                                    cudaStream_t st, int resid_T = 0, int resid_L = 0);
 
 }  // namespace mrag

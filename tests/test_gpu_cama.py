@@ -115,7 +115,14 @@ def test_forward_matches_reference_encoder(libmrag, b, G, L, d, heads, dff, laye
     # outputs are LayerNorm-ed (unit scale): bf16 carries ~3 significant digits
     assert float(err.max()) < 6e-2 and float(err.mean()) < 6e-3, (float(err.max()), float(err.mean()))
     assert float(err.mean()) <= 1.25 * float(err_torch.mean()) + 1e-4, (float(err.mean()), float(err_torch.mean()))
-    assert torch.equal(cama.predict(b=b).float().cpu(), got[:, -L:])
+    # predict(): the last layer computes the last group's rows only; same values up to the fp32 summation order
+    # of the split-K GEMMs (the K split depends on the row count), same parity bar against the fp32 oracle
+    pred = cama.predict(b=b).float().cpu()
+    assert pred.shape == (b, L, d)
+    assert float((pred - got[:, -L:]).abs().max()) < 4e-2
+    perr = (pred - want[:, -L:]).abs()
+    assert float(perr.max()) < 6e-2 and float(perr.mean()) < 6e-3, (float(perr.max()), float(perr.mean()))
+    assert torch.equal(pred, cama.predict(x.cuda(), use_graph=False).float().cpu())
     # in-place input: the gather can write straight into the handle's buffer
     cama.input_view(b).copy_(x.cuda())
     assert torch.equal(cama.forward(b=b).float().cpu(), got)

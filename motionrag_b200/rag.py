@@ -127,7 +127,9 @@ class RAGDatabase:
         self._group_ids: dict[str, dict] = {}
         self._thr_cache: dict[tuple, tuple] = {}
         self._where_cache: dict[str, tuple[str, int]] = {}   # SQL string -> (column, group id)
+        self._excl_one: dict[str, tuple[str, np.ndarray]] = {}   # SQL string -> (column, int32[1] group id)
         self._col_lists: dict[str, list] = {}                # scalar columns as Python lists (record building)
+        self._rec_plans: dict[tuple, tuple] = {}             # select tuple -> (names..., column lists...)
 
     @classmethod
     def from_store(cls, store: EmbeddingStore, columns: dict, vector_column: str = "text_embedding",
@@ -322,6 +324,19 @@ class RAGDatabase:
         -> (int32 [nq] group ids to exclude (-1 = none) or None, per-query host predicates or None)."""
         if where is None:
             return None, None
+        if nq == 1 and type(where) is str:
+            # the reference's call pattern (one query, one `video != "<own>"` clause): one dict lookup
+            one = self._excl_one.get(where)
+            if one is None:
+                hit = self._where_to_group(where)
+                if isinstance(hit, tuple):
+                    if len(self._excl_one) > (1 << 20):
+                        self._excl_one.clear()
+                    one = self._excl_one[where] = (hit[0], np.array([hit[1]], dtype=np.int32))
+            if one is not None:
+                if self._group_col != one[0]:
+                    self._bind_groups(one[0])
+                return one[1], None
         wheres = [where] * nq if isinstance(where, str) else list(where)
         if len(wheres) != nq:
             raise ValueError("need one where clause per query")
@@ -386,15 +401,25 @@ class RAGDatabase:
         return lst
 
     def _records(self, dist: np.ndarray, idx: np.ndarray, select: Sequence[str] | None) -> list[list[dict]]:
+        nq, k = idx.shape
+        if nq == 1 and select is not None and len(select) == 3:
+            # the call prepare_annotations makes (select=['video', 'start_sec', 'end_sec'], one query,
+            # src/data/datamodule.py:233-236): validated once per select list, then one dict display per row
+            plan = self._rec_plans.get(tuple(select))
+            if plan is None and all(c in self._columns for c in select):
+                plan = self._rec_plans[tuple(select)] = (*select, *(self._column_list(c) for c in select))
+            if plan is not None:
+                k0, k1, k2, l0, l1, l2 = plan
+                return [[{k0: l0[i], k1: l1[i], k2: l2[i], "_distance": d}
+                         for i, d in zip(idx[0].tolist(), dist[0].tolist()) if i >= 0]]
         names = list(select) if select is not None else list(self._columns) + list(self._vectors)
         for c in names:
             if c not in self._columns and c not in self._vectors:
                 raise ValueError(f"unknown column {c!r} in select")
-        nq, k = idx.shape
         if nq <= 4 and not any(c in self._vectors for c in names):
             # the reference's call pattern (one query per call): plain list indexing, no numpy round trips
-            cols = [(c, self._column_list(c)) for c in names]
             out = []
+            cols = [(c, self._column_list(c)) for c in names]
             for qi in range(nq):
                 recs = []
                 for i, d in zip(idx[qi].tolist(), dist[qi].tolist()):

@@ -85,7 +85,8 @@ class RAGDatabase:
         Keyword-only extensions: `columns` (in-memory table instead of a path), `embed_fn`
         (text -> vector, for str queries; the reference delegates that to LanceDB's registered
         gte-base-en-v1.5 function), `metric` / `prefilter` (LanceDB 0.14 defaults: "l2", post-
-        filter), `normalise` (L2-normalise rows on upload; the reference's tables already are),
+        filter; metric="reference" picks "dot" for tables of more than 1 M rows, which the reference indexes
+        with that metric), `normalise` (L2-normalise rows on upload; the reference's tables already are),
         `path` (force a scan kernel: auto | stream_f32 | stream_bf16 | tensor_bf16), `recheck`
         (what to do with the exactness margin every bf16 scan reports per query, see mrag.h: "auto"
         re-runs a query on the fp32 master rows when its margin is below 6 sigma of the bf16
@@ -121,6 +122,17 @@ class RAGDatabase:
         self._retriever = None
         self._init_caches()
         self.table = self  # reference attribute name (rag.py:14); `table=` arguments accept it
+        self._resolve_metric()
+
+    INDEXED_ABOVE = 1_000_000   # tools/build_rag_database.py:51-52: create_index(metric='dot') iff len(table) > 1 M
+
+    def _resolve_metric(self) -> None:
+        """metric="reference": the metric the reference's own table would answer with — squared L2 (LanceDB's
+        default, src/data/rag.py:54 sets none) up to 1 M rows, `dot` above, where build_rag_database.py adds an
+        IVF-PQ `dot` index. The reference is approximate in that regime (nprobes=50, refine_factor=30); this
+        search stays exact, see tests/test_ivf_pq.py for the comparison that is defined there."""
+        if self.metric == "reference":
+            self.metric = "dot" if len(self) > self.INDEXED_ABOVE else "l2"
 
     def _init_caches(self) -> None:
         self._group_col: str | None = None
@@ -157,6 +169,7 @@ class RAGDatabase:
         self._retriever = retriever
         self._init_caches()
         self.table = self
+        self._resolve_metric()
         return self
 
     # -- loading ------------------------------------------------------------------------------

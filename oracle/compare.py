@@ -104,3 +104,36 @@ def replay_reference_class(factory, golden_json, rel: float = 1e-5) -> int:
                 else:
                     assert g[key] == val, (call, key, g[key], val)
     return len(gold["calls"])
+
+
+def check_recall(exact_dist: np.ndarray, exact_idx: np.ndarray, approx_dist: np.ndarray, approx_idx: np.ndarray,
+                 rtol: float = 1e-3, atol: float = 1e-6) -> dict:
+    """Parity rule for the regime where the REFERENCE is approximate (tables > 1 M rows carry an IVF-PQ index,
+    tools/build_rag_database.py:51-52; see oracle/ivf_pq.py): index-identical answers are not defined there, so an
+    exact search is held to what must be true of it against ANY approximate answer over the same rows:
+      1. domination: rank by rank the exact `_distance` is <= the approximate one (within rtol);
+      2. agreement: a row both return carries the same `_distance` (the reference re-scores its candidates exactly,
+         refine_factor=30, so distances of shared rows are comparable);
+      3. nothing better was missed: a row only the approximate answer returns is no nearer than the exact answer's
+         last row (within rtol).
+    Inputs are one query's or a batch's (distance, index) lists, unused slots (inf / -1). Returns recall@k of the
+    approximate answer against the exact one (reported, not asserted: it measures the reference, not the product)."""
+    exact_dist, approx_dist = np.atleast_2d(np.asarray(exact_dist, np.float64)), np.atleast_2d(np.asarray(approx_dist, np.float64))
+    exact_idx, approx_idx = np.atleast_2d(np.asarray(exact_idx, np.int64)), np.atleast_2d(np.asarray(approx_idx, np.int64))
+    hits = total = 0
+    for q in range(exact_idx.shape[0]):
+        ei, ai = exact_idx[q][exact_idx[q] >= 0], approx_idx[q][approx_idx[q] >= 0]
+        ed, ad = exact_dist[q][:len(ei)], approx_dist[q][:len(ai)]
+        assert len(ei) >= len(ai), f"query {q}: exact search returned {len(ei)} rows, approximate {len(ai)}"
+        tol = lambda v: rtol * max(abs(v), atol / rtol)
+        for j in range(len(ai)):
+            assert ed[j] <= ad[j] + tol(ad[j]), f"query {q} rank {j}: exact {ed[j]:.9g} > approximate {ad[j]:.9g}"
+        where = {int(r): j for j, r in enumerate(ei)}
+        for j, r in enumerate(ai):
+            if int(r) in where:
+                assert abs(ed[where[int(r)]] - ad[j]) <= tol(ad[j]), f"query {q}: row {r} scored {ed[where[int(r)]]} vs {ad[j]}"
+                hits += 1
+            elif len(ei):
+                assert ad[j] >= ed[-1] - tol(ed[-1]), f"query {q}: row {r} (d={ad[j]:.9g}) beats the exact answer's last row"
+        total += len(ei)
+    return {"queries": int(exact_idx.shape[0]), "recall_at_k": hits / max(total, 1), "positions": int(total)}

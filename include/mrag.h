@@ -152,7 +152,15 @@ MRAG_API int mrag_search_plan(const mrag_store* s, int32_t nq, const mrag_search
                               mrag_plan_info* out);
 /* queries_dev [nq, dim] fp32 (not normalised, as in src/data/datamodule.py:300-302);
  * exclude_group_dev [nq] int32 or NULL; outputs [nq, k]: ascending distance, ties by lowest
- * row index, unused slots = (+inf, -1, -1). out_group_dev may be NULL. */
+ * row index, unused slots = (+inf, -1, -1). out_group_dev may be NULL.
+ * Stream semantics: the call is ordered on `stream` like any kernel launch, with one refinement for
+ * single-query searches (one launch: scan + select/re-rank tail in its last CTA). That kernel is launched
+ * with programmatic stream serialization, so its READ-ONLY scan phase may start while the previous kernel
+ * in the stream is still running — in practice the previous search's single-CTA tail, because only
+ * libmrag's own kernels release their dependents early; it waits for that kernel to complete before it
+ * writes anything (candidates, results, exchange records). Back-to-back searches therefore pipeline
+ * (scan of query i+1 under the tail of query i) while every result is still produced in stream order.
+ * MRAG_K1_OVERLAP=0 turns this off. */
 MRAG_API int mrag_search(const mrag_store* s, const float* queries_dev, int32_t nq,
                 const mrag_search_params* p, const int32_t* exclude_group_dev,
                 float* out_dist_dev, int64_t* out_idx_dev, int32_t* out_group_dev,

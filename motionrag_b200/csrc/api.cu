@@ -119,6 +119,7 @@ struct Knobs {
   bool k1_fuse;          // MRAG_K1_FUSE=0: single-query scans launch K3 separately (A/B runs)
   long long xchg_timeout_ms;  // MRAG_XCHG_TIMEOUT_MS: bound of the peer-exchange flag wait
   bool k3_stamps;        // MRAG_K3_STAMPS=1: mrag_search_timed prints the phase timeline of query 0
+  bool k1_overlap;       // MRAG_K1_OVERLAP=0: fused single-query scans are launched fully stream-ordered (A/B runs)
 };
 const Knobs& knobs() {
   static const Knobs k = [] {
@@ -134,6 +135,8 @@ const Knobs& knobs() {
     if (v.xchg_timeout_ms < 1) v.xchg_timeout_ms = 1;
     e = getenv("MRAG_K3_STAMPS");
     v.k3_stamps = e && e[0] == '1';
+    e = getenv("MRAG_K1_OVERLAP");
+    v.k1_overlap = !(e && e[0] == '0');
     return v;
   }();
   return k;
@@ -208,9 +211,9 @@ int make_plan(const mrag_store* s, int32_t nq, const mrag_search_params* p, Plan
       // top-`rerank` by scan score, which the exactness certificate (out_margin) relies on
       pl.rerank = refine > 32 ? 32 : refine;
     }
-    pl.k1_grid = k1_grid(s->n_rows, f32 ? 4 : 2, s->dim, nq < 4 ? nq : 4, s->sm_count);
-    pl.cands_per_query = pl.k1_grid * pl.kc;
     pl.fused = nq == 1 && knobs().k1_fuse;
+    pl.k1_grid = k1_grid(s->n_rows, f32 ? 4 : 2, s->dim, nq < 4 ? nq : 4, s->sm_count, pl.fused && knobs().k1_overlap);
+    pl.cands_per_query = pl.k1_grid * pl.kc;
   } else if (path == MRAG_PATH_TENSOR_BF16) {
     if (!k2_supported(s->dim))
       return fail(MRAG_ERR_UNSUPPORTED, "tensor path needs dim %% 64 == 0 (dim=%d)", s->dim);
@@ -532,6 +535,7 @@ static int search_impl(const mrag_store* s, const float* queries_dev, int32_t nq
         ex.ticket = s->tickets + (in_host_graph ? kTickets - 1
                                                 : s->next_ticket.fetch_add(1, std::memory_order_relaxed) % (kTickets - 1));
         ex.k3 = kp;
+        ex.overlap = knobs().k1_overlap ? 1 : 0;
       }
       // a 1..3-query tail uses the kernel instantiated for that count but is launched with the
       // plan's grid, so every query shares one candidate layout ([nq][grid][kc])

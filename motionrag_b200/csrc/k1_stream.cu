@@ -223,6 +223,12 @@ __global__ void __launch_bounds__(NT, MINB)
   if constexpr (Q == 1) {
     if (ex.k3.stamps != nullptr && tid == 0) atomicMax(ex.k3.stamps + 1, global_timer_ns());
   }
+  // Everything above only READ global memory (rows, bias, groups, the query: inputs that were complete before
+  // this kernel was enqueued). When the single-query form is launched with the programmatic-stream-serialization
+  // attribute this grid may have started while its predecessor in the stream — normally the previous search,
+  // whose last CTA is still selecting / re-ranking / exchanging — was running: wait for it to complete (and
+  // its writes to be visible) before the first global write. A no-op for ordinary launches.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // CTA merge: every warp sorts its 32 slots with shuffles; the sorted lists are folded four at a time
   // (bitonic "keep the 32 smallest" merges), then warp 0 folds the partial results into the best kc —
   // three barriers per query, no sorting network in shared memory
@@ -286,8 +292,24 @@ static cudaError_t launch_cfg(const void* db, int64_t n_rows, const float* queri
   rows_per_cta = (rows_per_cta + quantum - 1) / quantum * quantum;
   K1Extra e = ex;
   if (Q != 1) e.ticket = nullptr;
-  k1_stream_kernel<T, D, Q, R, MINB, NT><<<grid, NT, 0, st>>>(
-      static_cast<const T*>(db), n_rows, queries, cand, kc, rows_per_cta, e);
+  const T* dbt = static_cast<const T*>(db);
+  if (Q == 1 && e.ticket != nullptr && e.overlap) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, k1_stream_kernel<T, D, Q, R, MINB, NT>, dbt, n_rows, queries, cand, kc,
+                                        rows_per_cta, e);
+    note_launch();
+    return le != cudaSuccess ? le : cudaGetLastError();
+  }
+  k1_stream_kernel<T, D, Q, R, MINB, NT><<<grid, NT, 0, st>>>(dbt, n_rows, queries, cand, kc, rows_per_cta, e);
   note_launch();
   return cudaGetLastError();
 }
@@ -330,13 +352,14 @@ bool k1_supported(int dim, int nq) {
   return (dim == 256 || dim == 512 || dim == 768 || dim == 1024) && nq >= 1 && nq <= 4;
 }
 
-int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count) {
+int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count, bool spare_sm) {
   const int r = elt_bytes == 4 ? 2 : ((dim == 768 && nq == 1) ? 6 : 4);
   const int minb = nq == 1 ? 1 : ((elt_bytes == 4 || nq >= 3 || dim >= 1024) ? 2 : 3);
   const int64_t quantum = int64_t(nq == 1 ? 16 : 8) * r;
   // one resident wave; small tables get fewer CTAs
   int64_t want = (n_rows + quantum - 1) / quantum;
   int64_t cap = int64_t(sm_count) * minb;
+  if (spare_sm && nq == 1 && cap > 1) cap -= 1;
   return int(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 

@@ -26,14 +26,21 @@ cudaError_t launch_cast_queries_bf16(const float* q, void* q_bf16, int nq, int d
 // (both non-null) drop the rows of each query's excluded group before selection (pre-filter);
 // ticket (single query only, null = off) points at a zero-initialised counter and makes the last
 // CTA to finish run the K3 body `k3` itself (fused tail: the search is one launch).
+// overlap (host-side flag, fused single-query form only): launch with the programmatic-stream-serialization
+// attribute, so that the READ-ONLY scan phase of this search may run while the previous kernel in the stream
+// (typically the previous search's single-CTA tail) is still finishing; the kernel waits for its predecessor
+// (griddepcontrol.wait) before its first global write.
 struct K1Extra {
   const float* row_bias;
   const int32_t* row_group;
   const int32_t* exclude_group;
   int* ticket;
   K3Params k3;
+  int overlap;
 };
-int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count);
+// spare_sm: leave one SM free (grid <= sm_count - 1 in the one-CTA-per-SM single-query form) — the SM on
+// which the previous search's tail CTA may still be running when this grid starts
+int k1_grid(int64_t n_rows, int elt_bytes, int dim, int nq, int sm_count, bool spare_sm = false);
 bool k1_supported(int dim, int nq);
 cudaError_t launch_k1_stream(const void* db, int elt_bytes, int64_t n_rows, int dim,
                              const float* queries, int nq, uint64_t* cand, int kc, int grid,

@@ -140,8 +140,7 @@ class RAGDatabase:
         self._thr_cache: dict[tuple, tuple] = {}
         self._where_cache: dict[str, tuple[str, int]] = {}   # SQL string -> (column, group id)
         self._excl_one: dict[str, tuple[str, np.ndarray]] = {}   # SQL string -> (column, int32[1] group id)
-        self._col_lists: dict[str, list] = {}                # scalar columns as Python lists (record building)
-        self._rec_plans: dict[tuple, tuple] = {}             # select tuple -> (names..., column lists...)
+        self._rec_plans: dict[tuple, list] = {}              # select tuple -> validated column names
 
     @classmethod
     def from_store(cls, store: EmbeddingStore, columns: dict, vector_column: str = "text_embedding",
@@ -407,41 +406,34 @@ class RAGDatabase:
                     break
         return -1 if v is None else int(v)
 
-    def _column_list(self, c: str) -> list:
-        lst = self._col_lists.get(c)
-        if lst is None:
-            lst = self._col_lists[c] = self._columns[c].tolist()
-        return lst
-
     def _records(self, dist: np.ndarray, idx: np.ndarray, select: Sequence[str] | None) -> list[list[dict]]:
         nq, k = idx.shape
-        if nq == 1 and select is not None and len(select) == 3:
-            # the call prepare_annotations makes (select=['video', 'start_sec', 'end_sec'], one query,
-            # src/data/datamodule.py:233-236): validated once per select list, then one dict display per row
-            plan = self._rec_plans.get(tuple(select))
-            if plan is None and all(c in self._columns for c in select):
-                plan = self._rec_plans[tuple(select)] = (*select, *(self._column_list(c) for c in select))
-            if plan is not None:
-                k0, k1, k2, l0, l1, l2 = plan
-                return [[{k0: l0[i], k1: l1[i], k2: l2[i], "_distance": d}
-                         for i, d in zip(idx[0].tolist(), dist[0].tolist()) if i >= 0]]
-        names = list(select) if select is not None else list(self._columns) + list(self._vectors)
-        for c in names:
-            if c not in self._columns and c not in self._vectors:
-                raise ValueError(f"unknown column {c!r} in select")
+        names = self._rec_plans.get(tuple(select)) if select is not None else None
+        if names is None:
+            names = list(select) if select is not None else list(self._columns) + list(self._vectors)
+            for c in names:
+                if c not in self._columns and c not in self._vectors:
+                    raise ValueError(f"unknown column {c!r} in select")
+            if select is not None:
+                self._rec_plans[tuple(select)] = names
         if nq <= 4 and not any(c in self._vectors for c in names):
-            # the reference's call pattern (one query per call): plain list indexing, no numpy round trips
+            # the reference's call pattern (one query per call): one 12-row fancy index + tolist() per column.
+            # Columns stay numpy arrays — Python lists of a million cells would be re-traversed by every full
+            # garbage collection (tens of ms per stall, measured) and cost the same per lookup at that size.
             out = []
-            cols = [(c, self._column_list(c)) for c in names]
             for qi in range(nq):
-                recs = []
-                for i, d in zip(idx[qi].tolist(), dist[qi].tolist()):
-                    if i < 0:
-                        continue
-                    r = {c: lst[i] for c, lst in cols}
-                    r["_distance"] = d
-                    recs.append(r)
-                out.append(recs)
+                rows = idx[qi]
+                if rows[k - 1] < 0:                      # valid entries come first (the kernels compact them)
+                    rows = rows[:int((rows >= 0).sum())]
+                d = dist[qi, :rows.shape[0]].tolist()
+                if len(names) == 3:      # select=['video', 'start_sec', 'end_sec'] (src/data/datamodule.py:236)
+                    k0, k1, k2 = names
+                    out.append([{k0: a, k1: b, k2: c, "_distance": e}
+                                for a, b, c, e in zip(self._columns[k0][rows].tolist(), self._columns[k1][rows].tolist(),
+                                                      self._columns[k2][rows].tolist(), d)])
+                else:
+                    keys = (*names, "_distance")
+                    out.append([dict(zip(keys, vals)) for vals in zip(*(self._columns[c][rows].tolist() for c in names), d)])
             return out
         # one fancy-index + tolist() per column for the WHOLE batch, then C-speed dict(zip(...));
         # per-cell numpy scalar handling would dominate a 4096-query batch

@@ -89,6 +89,19 @@ def main():
         r = retr.search(torch.from_numpy(q[rep:rep + nqr]).to(dev), k, path=path)
         rd, ri = fs.flat_search(db, q[rep:rep + nqr], k)
         compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, db, q[rep:rep + nqr])
+    # pipelined single-query searches: 300 launches enqueued without a host sync in between, so the scan of call
+    # i+1 runs under the tail (select, re-rank, peer exchange) of call i on every rank; all results checked after
+    qd = torch.from_numpy(q).to(dev)
+    exd = torch.from_numpy(excl).to(dev)
+    pending = [retr.search(qd[j:j + 1], k, exclude_group=exd[j:j + 1], certify=True) for j in range(300)]
+    torch.cuda.synchronize()
+    rd, ri = fs.flat_search(db, q[:300], k, "l2", groups, excl[:300])
+    got_d = torch.cat([r.distance for r in pending]).cpu().numpy()
+    got_i = torch.cat([r.index for r in pending]).cpu().numpy()
+    repo = compare.check_retrieval(got_d, got_i, rd, ri, db, q[:300])
+    assert repo["index_mismatches"] == repo["near_tie_positions"], repo
+    assert not bool(torch.isnan(torch.cat([r.margin for r in pending])).any())
+    del pending
     # every rank must hold the identical answer
     r = retr.search(torch.from_numpy(q[:64]).to(dev), k)
     ref = r.index.clone()
@@ -108,6 +121,14 @@ def main():
         ref = r.index.clone()
         dist.broadcast(ref, 0)
         assert torch.equal(ref, r.index)
+    # soak: 100 more epochs of the two-phase exchange back to back (slot reuse, flags, epochs); the answer of every
+    # epoch must be the first one's, bit for bit
+    first_i, first_d = r.index.clone(), r.distance.clone()
+    qbig_d, exbig_d = torch.from_numpy(qbig).to(dev), torch.from_numpy(exbig).to(dev)
+    for rep in range(100):
+        r = retr.search(qbig_d, k, exclude_group=exbig_d)
+        assert torch.equal(r.index, first_i) and torch.equal(r.distance, first_d), rep
+    shard.poll_error()
 
     # host buffers in / out: one captured graph per rank with the exchange inside; epochs keep advancing
     for rep in range(12):

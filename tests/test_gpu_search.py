@@ -122,6 +122,46 @@ def test_single_query_scan_with_a_separate_k3_launch(libmrag):
     assert "PLAN 1" in out and out.strip().splitlines()[0].endswith(" 0")
 
 
+def test_single_query_scan_without_the_pipelined_launch(libmrag):
+    """MRAG_K1_OVERLAP=0: fully stream-ordered launches on all 148 SMs (the A/B form of the default, which leaves
+    one SM to the previous search's tail and starts its scan under it)."""
+    out = _run_with_env({"MRAG_K1_OVERLAP": "0"}, [(1, 12, "stream_bf16"), (1, 32, "stream_f32")])
+    assert "PLAN 1 148 1" in out
+    assert "PLAN 1 147 1" in _run_with_env({}, [(1, 12, "auto")])
+
+
+@pytest.mark.parametrize("path", ["auto", "stream_f32"])
+def test_back_to_back_single_query_searches_pipeline_correctly(case, path):
+    """Single-query searches are one launch each, started with programmatic stream serialization: the read-only
+    scan of call i+1 runs under the select / re-rank tail of call i. 200 calls enqueued without any host sync in
+    between (alternating filters, shared workspace and rotating tickets), every result checked afterwards, and
+    the same sequence with a dependent torch op squeezed between the calls (which must see finished results)."""
+    store, q, excl = case["store"], case["q"], case["excl"]
+    qd, exd = torch.from_numpy(q).cuda(), torch.from_numpy(excl).cuda()
+    pending = []
+    for j in range(200):
+        if j % 3 == 0:
+            pending.append(store.search(qd[j:j + 1], 12, path=path, certify=(path == "auto")))
+        else:
+            pending.append(store.search(qd[j:j + 1], 12, path=path, exclude_group=exd[j:j + 1],
+                                        filter_mode=("post", "pre")[j % 2], certify=(path == "auto")))
+    torch.cuda.synchronize()
+    for j, r in enumerate(pending):
+        filt = None if j % 3 == 0 else ("post", "pre")[j % 2]
+        rd, ri = fs.flat_search(case["db"], q[j:j + 1], 12, "l2", case["groups"] if filt else None,
+                                excl[j:j + 1] if filt else None, prefilter=(filt == "pre"))
+        rep = compare.check_retrieval(r.distance.cpu().numpy(), r.index.cpu().numpy(), rd, ri, case["db"], q[j:j + 1])
+        assert rep["index_mismatches"] == rep["near_tie_positions"], (j, rep)
+    # a consumer kernel right behind each search reads complete results (ordinary stream order)
+    sums = []
+    for j in range(50):
+        r = store.search(qd[j:j + 1], 12, path=path)
+        sums.append(r.index.sum() + 0)                 # torch kernel enqueued directly after the search
+    torch.cuda.synchronize()
+    for j, t in enumerate(sums):
+        assert int(t) == int(fs.flat_search(case["db"], q[j:j + 1], 12)[1].sum()), j
+
+
 @pytest.mark.parametrize("path,nq", [("stream_f32", 4), ("stream_bf16", 3), ("tensor_bf16", 64)])
 @pytest.mark.parametrize("metric", ["cosine", "dot"])
 def test_metrics(case, path, nq, metric):

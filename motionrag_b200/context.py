@@ -104,7 +104,11 @@ def select_refs(index: torch.Tensor, distance: torch.Tensor, ref_video_num: int,
     becomes index -1 (the all-zero clip -> uncond row) with `_distance` 1.0 (:305-310).
 
     index / distance: [b, k>=K] from a search (unused slots -1 / inf). Returns
-    (ref_index int64 [b, K], ref_distance float32 [b, K])."""
+    (ref_index int64 [b, K], ref_distance float32 [b, K]). One deliberate difference: when a search returned
+    fewer than K rows the reference's distance LIST is simply shorter (:296 iterates over what exists) while its
+    clip tensor still has K slots (zeros); the consumer of the distances, `condition_fusion(..., 'weight')`
+    (src/projects/condition/utils.py:25-28: w ~ 1 - distance), needs one value per slot, so the tensor form
+    here fills the missing slots with 1.0 — weight 0, exactly what a dropped clip gets."""
     K = int(ref_video_num)
     idx = index[:, :K].clone()
     dist = distance[:, :K].clone().to(torch.float32)

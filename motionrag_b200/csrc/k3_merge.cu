@@ -103,13 +103,20 @@ cudaError_t launch_cast_queries_bf16(const float* q, void* q_bf16, int nq, int d
 }
 
 // ---- K3 kernels (body in k3_body.cuh) ----------------------------------------------------------
-constexpr int kK3Threads = 1024;  // 32 warps: one re-rank candidate / one qualifying run per warp
+// Block size by the number of candidate runs: 1 024 threads (32 warps: one re-rank candidate / one qualifying
+// run per warp) when a query has hundreds of runs (K1 with 2-4 queries: one run per CTA), 256 threads for the
+// tensor path's few dozen runs when the batch is several waves of blocks — it then keeps 8 blocks per SM in
+// flight instead of 2, which is what the latency chain of a block (heads -> keys -> 16-32 master rows -> sort)
+// needs to be hidden (4096 queries: p50 of the whole step 4.54 -> 4.44 ms). A batch that fits one wave keeps
+// the wide blocks: more warps per query = shorter chain (64 queries: 70 vs 73 us per step).
+constexpr int kK3Threads = 1024, kK3ThreadsSmall = 256, kK3SmallMaxRuns = 256, kK3SmallMinQueries = 600;
 
-__global__ void __launch_bounds__(kK3Threads) k3_merge_rerank_kernel(const K3Params p) {
+template <int NT>
+__global__ void __launch_bounds__(NT) k3_merge_rerank_kernel(const K3Params p) {
   __shared__ K3Smem sm;
   // launched with programmatic stream serialization: wait here for the scan kernel's results
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  k3_body<kK3Threads>(p, blockIdx.x, sm);
+  k3_body<NT>(p, blockIdx.x, sm);
 }
 
 // second phase of the exchange for batches that cannot all be resident at once: every block of the
@@ -144,7 +151,8 @@ cudaError_t launch_k3_merge_rerank(const K3Params& p_in, int nq, cudaStream_t st
   p.x.phase = two_phase ? 1 : 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(nq));
-  cfg.blockDim = dim3(kK3Threads);
+  const bool small = p.n_runs <= kK3SmallMaxRuns && nq >= kK3SmallMinQueries;
+  cfg.blockDim = dim3(small ? kK3ThreadsSmall : kK3Threads);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -152,7 +160,8 @@ cudaError_t launch_k3_merge_rerank(const K3Params& p_in, int nq, cudaStream_t st
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, k3_merge_rerank_kernel, p);
+  cudaError_t le = small ? cudaLaunchKernelEx(&cfg, k3_merge_rerank_kernel<kK3ThreadsSmall>, p)
+                         : cudaLaunchKernelEx(&cfg, k3_merge_rerank_kernel<kK3Threads>, p);
   note_launch();
   if (le != cudaSuccess) return le;
   if (two_phase) {

@@ -819,11 +819,96 @@ __global__ void __launch_bounds__(kAttnThreads, 3)
 }
 
 // ---- K7: y = LayerNorm(resid + sum_s partial[s] + bias) * gamma + beta ---------------------------
-// one CTA of d/8 threads per row, 8 elements per thread; every load of a thread (residual, bias,
-// `splits` partial sums, gamma, beta) is independent and issued up front, the two reductions go
-// through warp shuffles + one shared-memory hop.
+// One WARP per row, 8 rows per CTA: lane l owns the 8-element chunks l, l+32, ... of the row (16-byte bf16 /
+// 32-byte fp32 pieces, coalesced across the warp), mean and variance are two xor-shuffle reductions — no shared
+// memory, no CTA barrier (the first version ran one 128-thread CTA per row with two barrier-separated block
+// reductions: 13 us for 4 000 rows, most of it CTA launch and barrier latency).
 constexpr int kMaxSplits = 8;
+constexpr int kLnRowsPerCta = 8;
+constexpr int kLnWarpRowsMin = 2000;  // rows from which the warp-per-row form is used (see the CTA-per-row form below)
 
+__global__ void __launch_bounds__(32 * kLnRowsPerCta)
+    k7_add_layernorm_kernel(const __nv_bfloat16* __restrict__ resid, const float* __restrict__ partial,
+                            int splits, const __nv_bfloat16* __restrict__ bias,
+                            const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                            __nv_bfloat16* __restrict__ out, int M, int d, float eps, int resid_T, int resid_L) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * kLnRowsPerCta + warp;
+  if (row >= M) return;  // warp-uniform
+  // resid_T > 0: the rows of this launch are the LAST resid_L tokens of each resid_T-token sample, stored
+  // compactly, while the residual stream still has all tokens (last layer of predict)
+  const size_t rrow = resid_T > 0 ? size_t(row / resid_L) * resid_T + (resid_T - resid_L) + row % resid_L : size_t(row);
+  const int chunks = d >> 8;  // 8-element chunks per lane: d / (32 * 8), 1..4
+  float x[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < chunks) {
+      const int c = (j * 32 + lane) * 8;
+      const uint4 rv = *reinterpret_cast<const uint4*>(resid + rrow * d + c);
+      const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + c));
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        x[j][2 * e] = bf16lo_to_f32(rw[e]) + bf16lo_to_f32(bw[e]);
+        x[j][2 * e + 1] = bf16hi_to_f32(rw[e]) + bf16hi_to_f32(bw[e]);
+      }
+#pragma unroll
+      for (int sp = 0; sp < kMaxSplits; ++sp) {
+        if (sp < splits) {
+          const float4* pp = reinterpret_cast<const float4*>(partial + (size_t(sp) * M + row) * d + c);
+          const float4 a = pp[0], b = pp[1];
+          x[j][0] += a.x; x[j][1] += a.y; x[j][2] += a.z; x[j][3] += a.w;
+          x[j][4] += b.x; x[j][5] += b.y; x[j][6] += b.z; x[j][7] += b.w;
+        }
+      }
+    }
+  }
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < chunks)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s1 += x[j][e];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+  const float mean = s1 / d;
+  float s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < chunks)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float t = x[j][e] - mean;
+        s2 = fmaf(t, t, s2);
+      }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+  const float rstd = rsqrtf(s2 / d + eps);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j < chunks) {
+      const int c = (j * 32 + lane) * 8;
+      const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gamma + c));
+      const uint4 ev = __ldg(reinterpret_cast<const uint4*>(beta + c));
+      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ew[4] = {ev.x, ev.y, ev.z, ev.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = (x[j][2 * e] - mean) * rstd * bf16lo_to_f32(gw[e]) + bf16lo_to_f32(ew[e]);
+        const float b = (x[j][2 * e + 1] - mean) * rstd * bf16hi_to_f32(gw[e]) + bf16hi_to_f32(ew[e]);
+        const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
+        o[e] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+      *reinterpret_cast<uint4*>(out + size_t(row) * d + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// CTA-per-row form (d/8 threads, 8 elements each, two barrier-separated block reductions): four times the
+// parallelism inside a row and one CTA per row — the shorter latency chain when there are only a few hundred
+// rows (one sample: 250 rows; 4.4 us against 9 us for the warp-per-row form, which wins from ~2 000 rows on).
 __device__ __forceinline__ float block_sum(float v, float* red, int warp, int lane, int nwarps) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -836,7 +921,7 @@ __device__ __forceinline__ float block_sum(float v, float* red, int warp, int la
 }
 
 __global__ void __launch_bounds__(128)
-    k7_add_layernorm_kernel(const __nv_bfloat16* __restrict__ resid, const float* __restrict__ partial,
+    k7_add_layernorm_cta_kernel(const __nv_bfloat16* __restrict__ resid, const float* __restrict__ partial,
                             int splits, const __nv_bfloat16* __restrict__ bias,
                             const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                             __nv_bfloat16* __restrict__ out, int M, int d, float eps, int resid_T, int resid_L) {
@@ -1040,8 +1125,11 @@ cudaError_t launch_k7_add_layernorm(const void* resid, const float* partial, int
   const __nv_bfloat16* be = static_cast<const __nv_bfloat16*>(beta);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   void* args[] = {&r, &partial, &splits, &bi, &ga, &be, &o, &M, &d, &eps, &resid_T, &resid_L};
-  cudaError_t e = launch_pdl(reinterpret_cast<const void*>(k7_add_layernorm_kernel), dim3(unsigned(M)),
-                             dim3(unsigned(d / 8)), 0, st, args);
+  cudaError_t e = M >= kLnWarpRowsMin
+                      ? launch_pdl(reinterpret_cast<const void*>(k7_add_layernorm_kernel),
+                                   dim3(unsigned((M + kLnRowsPerCta - 1) / kLnRowsPerCta)), dim3(32 * kLnRowsPerCta), 0, st, args)
+                      : launch_pdl(reinterpret_cast<const void*>(k7_add_layernorm_cta_kernel), dim3(unsigned(M)),
+                                   dim3(unsigned(d / 8)), 0, st, args);
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }

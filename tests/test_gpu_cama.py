@@ -95,7 +95,9 @@ def _encoder(d, heads, dff, layers, seed):
 
 
 @pytest.mark.parametrize("b,G,L,d,heads,dff,layers", [(1, 10, 25, 1024, 16, 4096, 4), (3, 10, 25, 1024, 16, 4096, 4),
-                                                      (2, 4, 5, 256, 4, 512, 2), (2, 3, 40, 512, 8, 1024, 2)])
+                                                      (2, 4, 5, 256, 4, 512, 2), (2, 3, 40, 512, 8, 1024, 2),
+                                                      (10, 10, 25, 1024, 16, 4096, 2),   # 2 500 rows: persistent GEMMs, warp-per-row LayerNorm
+                                                      (9, 10, 25, 768, 12, 1536, 2)])
 def test_forward_matches_reference_encoder(libmrag, b, G, L, d, heads, dff, layers):
     """Reference configuration (configs/cogvideox/MotionRAG_open.yml:253-267) and a small one."""
     from motionrag_b200 import CamaTransformer
@@ -106,7 +108,7 @@ def test_forward_matches_reference_encoder(libmrag, b, G, L, d, heads, dff, laye
     with torch.no_grad():
         want = enc(x.float(), mask)                                   # fp32 evaluation = the oracle
         torch_bf16 = enc.cuda().bfloat16()(x.cuda(), mask.cuda()).float().cpu()
-    cama = CamaTransformer(enc, groups=G, group_tokens=L, max_batch=4, device=0)
+    cama = CamaTransformer(enc, groups=G, group_tokens=L, max_batch=max(4, b), device=0)
     got = cama.forward(x.cuda()).float().cpu()
     got_nograph = cama.forward(x.cuda(), use_graph=False).float().cpu()
     assert torch.equal(got, got_nograph)                               # graph replay == direct launches

@@ -100,11 +100,12 @@ def lancedb_search_factory(tmpdir: str):
     import lancedb
     import pyarrow as pa
     db = lancedb.connect(tmpdir)
-    made = {}
+    made, keep = {}, []
 
     def search_one(table, q, k, where, select, nprobes, refine_factor):
         key = id(table)
         if key not in made:
+            keep.append(table)                 # keeps id(table) unique for the life of this factory
             cols = {c: (pa.FixedSizeListArray.from_arrays(pa.array(v.reshape(-1), type=pa.float32()), v.shape[1])
                         if c == "text_embedding" else pa.array(v.tolist())) for c, v in table.items()}
             made[key] = db.create_table(f"t{len(made)}", data=pa.table(cols))
@@ -120,11 +121,9 @@ def lancedb_search_factory(tmpdir: str):
 def oracle_search_one(table, q, k, where, select, nprobes, refine_factor):
     from . import flat_search as fs
     cache = oracle_search_one.__dict__.setdefault("dbs", {})
-    db = cache.get(id(table))
-    if db is None:
-        cache.clear()
-        db = cache[id(table)] = fs.OracleRAGDatabase(table)
-    return db.text_search(q, top_k=k, where=where, select=select, nprobes=nprobes, refine_factor=refine_factor)
+    if cache.get("table") is not table:        # keyed by identity with the table kept alive (an id() can be reused)
+        cache["table"], cache["db"] = table, fs.OracleRAGDatabase(table)
+    return cache["db"].text_search(q, top_k=k, where=where, select=select, nprobes=nprobes, refine_factor=refine_factor)
 
 
 def compare_runs(got: dict, gold: dict, rel: float = 1e-3) -> dict:

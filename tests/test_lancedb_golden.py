@@ -59,11 +59,9 @@ def test_cuda_drop_in_matches_lancedb_golden_or_the_oracle(libmrag):
     dbs = {}
 
     def cuda_search_one(table, q, k, where, select, nprobes, refine_factor):
-        db = dbs.get(id(table))
-        if db is None:
-            dbs.clear()
-            db = dbs[id(table)] = RAGDatabase(None, None, 'cuda', columns=table)
-        return db.text_search(q, top_k=k, where=where, select=select, nprobes=nprobes, refine_factor=refine_factor)
+        if dbs.get("table") is not table:      # keyed by identity with the table kept alive (an id() can be reused)
+            dbs["table"], dbs["db"] = table, RAGDatabase(None, None, 'cuda', columns=table)
+        return dbs["db"].text_search(q, top_k=k, where=where, select=select, nprobes=nprobes, refine_factor=refine_factor)
     runs = gold["runs"] if gold is not None else [lg.run_engine(lg.oracle_search_one, c) for c in lg.CASES]
     for run in runs:
         rep = lg.compare_runs(lg.run_engine(cuda_search_one, run["case"]), run)

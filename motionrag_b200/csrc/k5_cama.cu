@@ -49,7 +49,75 @@ struct GemmArgs {
   float* partial;       // split mode: [splits][M,N] fp32 (out == null)
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf GELU, 0.5 x (1 + erf(x / sqrt 2)), evaluated through erfc(z) = (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z),
+// z = |x| / sqrt 2 (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7 on erf): at most 3.4e-7 absolute off the float64
+// GELU over [-8, 8] (tests/test_host_logic.py restates it), three orders below the bf16 rounding of the output.
+// 14 instructions, two of them MUFU, against ~30 for erff(): the FFN1 epilogue of the multi-tile kernels was
+// issue-bound on it (profiles/r2_k5_pair_ffn1_b16.txt). The negative side is h * erfc(z) directly, no cancellation.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = fabsf(0.5f * x) * (p * t * e);  // |x| / 2 * erfc(z)
+  return x > 0.f ? x - r : -r;
+}
+
+// ---- epilogue pieces shared by the multi-tile kernels (thread = output row, warp = 32 rows x CW columns) ----------
+// The bias slice of the warp's columns is parked in a warp-private strip of shared memory before the accumulator is
+// waited for (one coalesced load instead of 16 scalar loads per 32 columns on the critical path; broadcast LDS.128).
+template <int CW>
+__device__ __forceinline__ void k5_stage_bias(const GemmArgs& g, int n0, float* bias_s, int lane) {
+  __syncwarp();  // the previous tile's reads of the strip are done
+  if constexpr (CW == 64) {
+    float2 b = make_float2(0.f, 0.f);
+    if (g.bias != nullptr) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(g.bias + n0 + 2 * lane);
+      b = make_float2(bf16lo_to_f32(w), bf16hi_to_f32(w));
+    }
+    *reinterpret_cast<float2*>(bias_s + 2 * lane) = b;
+  } else {
+    static_assert(CW == 32, "32 or 64 columns per epilogue warp");
+    bias_s[lane] = g.bias != nullptr ? __bfloat162float(g.bias[n0 + lane]) : 0.f;
+  }
+  __syncwarp();
+}
+
+// 32 accumulator columns of one row: + bias (+ GELU) -> bf16, or the raw fp32 partial sums
+__device__ __forceinline__ void k5_write_cols32(const GemmArgs& g, const uint32_t (&v)[32], const float* bias_s, int m,
+                                                int n0) {
+  if (g.out != nullptr) {
+    uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(m) * g.N + n0);
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c), b1 = *reinterpret_cast<const float4*>(bias_s + c + 4);
+      float x[8] = {__uint_as_float(v[c]) + b0.x,     __uint_as_float(v[c + 1]) + b0.y, __uint_as_float(v[c + 2]) + b0.z,
+                    __uint_as_float(v[c + 3]) + b0.w, __uint_as_float(v[c + 4]) + b1.x, __uint_as_float(v[c + 5]) + b1.y,
+                    __uint_as_float(v[c + 6]) + b1.z, __uint_as_float(v[c + 7]) + b1.w};
+      if (g.gelu) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = gelu_erf(x[e]);
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 r = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+        w[e] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+      dst[c >> 3] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>(g.partial + size_t(m) * g.N + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                           __uint_as_float(v[4 * j + 3]));
+  }
+}
 
 // REDUCE: the grid.z K splits of a tile form one thread-block cluster and their fp32 partial tiles are
 // summed on chip: every CTA parks its TMEM accumulator in its own shared memory, then CTA r of the
@@ -258,18 +326,20 @@ __global__ void __launch_bounds__(kGemmThreads, STAGES <= 3 ? 2 : 1)
 // ---- K5p: persistent form of K5 for GEMMs of several waves of tiles -----------------------------
 // One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so the CTAs of one
 // round share A tiles in L2). Two 128-column TMEM accumulators: the MMA thread starts the k-loop of
-// tile i+1 while the eight epilogue warps (two per TMEM lane quarter, 64 columns each) drain tile i —
-// bias / erf-GELU / bf16 packing no longer sits on the tensor pipe's critical path. The TMA producer
-// runs ahead across tile boundaries through the same 6-stage ring. bf16 output or one fp32 partial.
-constexpr int kPersEpiWarps = 8;
+// tile i+1 while the sixteen epilogue warps (four per TMEM lane quarter, a quarter of the columns each) drain
+// tile i — bias / erf-GELU / bf16 packing no longer sits on the tensor pipe's critical path. (Eight warps, two
+// per scheduler, could not hide their own latencies: issue slots 36 % busy while a GELU tile took 2.8x its MMA
+// time.) The TMA producer runs ahead across tile boundaries through the same ring. bf16 output or one fp32 partial.
+constexpr int kPersEpiWarps = 16;
 constexpr int kPersThreads = 64 + 32 * kPersEpiWarps;
+constexpr uint32_t kPersBiasBytes = kPersEpiWarps * 64 * 4;  // warp-private bias strips
 // BN = 256 halves the L2 -> shared-memory bytes per flop (the bound of 128 x 128 tiles at ~0.65 PF/s):
 // 48 KB per k-block for a 128 x 256 x 64 MMA block, 4 stages, both accumulators fill the 512 TMEM columns
 template <int BN>
 struct PersCfg {
   static constexpr int kStages = BN == 256 ? 4 : 6;
   static constexpr uint32_t kStageBytes = kGemmABytes + BN * kBK * 2;
-  static constexpr uint32_t kSmem = kStages * kStageBytes + 256 + 1024;
+  static constexpr uint32_t kSmem = kStages * kStageBytes + 256 + kPersBiasBytes + 1024;
 };
 
 template <int BN>
@@ -360,62 +430,29 @@ __global__ void __launch_bounds__(kPersThreads, 1)
       }
     }
   } else {
-    // epilogue warp: TMEM lane quarter = warp % 4 (hardware rule), column half by warp group
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    // epilogue warp: TMEM lane quarter = warp % 4 (hardware rule), column quarter by warp group
+    constexpr int kCW = kPersBN / 4;
+    const int quarter = warp & 3, part = (warp - 2) >> 2;
+    float* bias_s = reinterpret_cast<float*>(smem + kPersStages * kPersStageBytes + 256) + (warp - 2) * 64;
     int i = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++i) {
       const int m_tile = t / n_tiles, n_tile = t % n_tiles, buf = i & 1;
+      const int n0 = n_tile * kPersBN + part * kCW;
+      if (g.out != nullptr) k5_stage_bias<kCW>(g, n0, bias_s, lane);
       mbar_wait(&tfull_bar[buf], (i >> 1) & 1);
       tc_fence_after();
-      constexpr int kColsPerWarp = kPersBN / 2, kBatches = kColsPerWarp / 64;
-      const uint32_t t_addr =
-          tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kPersBN + half * kColsPerWarp);
+      const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kPersBN + part * kCW);
       const int m = m_tile * kGemmBM + quarter * 32 + lane;
-#pragma unroll 1
-      for (int bt = 0; bt < kBatches; ++bt) {
-        uint32_t v[2][32];
-        tmem_ld_32x32(t_addr + bt * 64, v[0]);
-        tmem_ld_32x32(t_addr + bt * 64 + 32, v[1]);
-        tmem_ld_wait();
-        if (bt == kBatches - 1) {  // everything of this accumulator is in registers: release it now
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
-        }
-        if (m < g.M) {
+      uint32_t v[kCW / 32][32];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int n0 = n_tile * kPersBN + half * kColsPerWarp + bt * 64 + c * 32;
-            if (g.out != nullptr) {
-              uint32_t packed[16];
+      for (int c = 0; c < kCW / 32; ++c) tmem_ld_32x32(t_addr + c * 32, v[c]);
+      tmem_ld_wait();
+      tc_fence_before();  // this warp's share of the accumulator is in registers: release it now
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (m < g.M) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float a = __uint_as_float(v[c][j]), b = __uint_as_float(v[c][j + 1]);
-                if (g.bias != nullptr) {
-                  const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(g.bias + n0 + j);
-                  a += __bfloat162float(bb.x);
-                  b += __bfloat162float(bb.y);
-                }
-                if (g.gelu) {
-                  a = gelu_erf(a);
-                  b = gelu_erf(b);
-                }
-                const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
-                packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&r);
-              }
-              uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(m) * g.N + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            } else {
-              float4* dst = reinterpret_cast<float4*>(g.partial + size_t(m) * g.N + n0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                dst[j] = make_float4(__uint_as_float(v[c][4 * j]), __uint_as_float(v[c][4 * j + 1]),
-                                     __uint_as_float(v[c][4 * j + 2]), __uint_as_float(v[c][4 * j + 3]));
-            }
-          }
-        }
+        for (int c = 0; c < kCW / 32; ++c) k5_write_cols32(g, v[c], bias_s + c * 32, m, n0 + c * 32);
       }
     }
   }
@@ -432,12 +469,12 @@ __global__ void __launch_bounds__(kPersThreads, 1)
 // 128 x 256 x 64 MMA block). Two CTAs of a cluster share one M = 256 x N = 256 MMA stream instead: each
 // stages its own 128 rows of A and 128 of the 256 rows of the W tile (32 KB per k-block and SM for the
 // same flops, 6 stages), the leader's single thread issues tcgen05.mma.cta_group::2, commits are
-// multicast to both CTAs, and each CTA drains the 128 x 256 accumulator of its own rows with eight
+// multicast to both CTAs, and each CTA drains the 128 x 256 accumulator of its own rows with sixteen
 // epilogue warps while the next tile accumulates in the other half of TMEM. Same structure as the
 // CTA-pair scan kernel (k2_batch2.cu). Tiles: (256-row pair, 256-column block), n fastest.
 constexpr int kPairBN = 256, kPairStages = 6;
 constexpr uint32_t kPairStageBytes = kGemmABytes + (kPairBN / 2) * kBK * 2;  // 16 KB A + 16 KB half of W
-constexpr uint32_t kPairSmem = kPairStages * kPairStageBytes + 256 + 1024;
+constexpr uint32_t kPairSmem = kPairStages * kPairStageBytes + 256 + kPersBiasBytes + 1024;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersThreads, 1)
     k5_linear_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
@@ -529,61 +566,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersThreads, 1)
       }
     }
   } else {
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    constexpr int kCW = kPairBN / 4;  // 64 columns per epilogue warp
+    const int quarter = warp & 3, part = (warp - 2) >> 2;
+    float* bias_s = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes + 256) + (warp - 2) * 64;
     int i = 0;
     for (int t = pair_id; t < total; t += n_pairs, ++i) {
       const int m_pair = t / n_tiles, n_tile = t % n_tiles, buf = i & 1;
+      const int n0 = n_tile * kPairBN + part * kCW;
+      if (g.out != nullptr) k5_stage_bias<kCW>(g, n0, bias_s, lane);
       mbar_wait(&tfull_bar[buf], (i >> 1) & 1);
       tc_fence_after();
-      constexpr int kColsPerWarp = kPairBN / 2;
-      const uint32_t t_addr =
-          tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kPairBN + half * kColsPerWarp);
+      const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(buf * kPairBN + part * kCW);
       const int m = (m_pair * 2 + int(cta_rank)) * kGemmBM + quarter * 32 + lane;
-#pragma unroll 1
-      for (int bt = 0; bt < kColsPerWarp / 64; ++bt) {
-        uint32_t v[2][32];
-        tmem_ld_32x32(t_addr + bt * 64, v[0]);
-        tmem_ld_32x32(t_addr + bt * 64 + 32, v[1]);
-        tmem_ld_wait();
-        if (bt == kColsPerWarp / 64 - 1) {  // accumulator fully in registers: hand it back to the leader's MMA thread
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&tempty_bar[buf], 0);
-        }
-        if (m < g.M) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int n0 = n_tile * kPairBN + half * kColsPerWarp + bt * 64 + c * 32;
-            if (g.out != nullptr) {
-              uint32_t packed[16];
-#pragma unroll
-              for (int j = 0; j < 32; j += 2) {
-                float a = __uint_as_float(v[c][j]), b = __uint_as_float(v[c][j + 1]);
-                if (g.bias != nullptr) {
-                  const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(g.bias + n0 + j);
-                  a += __bfloat162float(bb.x);
-                  b += __bfloat162float(bb.y);
-                }
-                if (g.gelu) {
-                  a = gelu_erf(a);
-                  b = gelu_erf(b);
-                }
-                const __nv_bfloat162 r = __floats2bfloat162_rn(a, b);
-                packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&r);
-              }
-              uint4* dst = reinterpret_cast<uint4*>(g.out + size_t(m) * g.N + n0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            } else {
-              float4* dst = reinterpret_cast<float4*>(g.partial + size_t(m) * g.N + n0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                dst[j] = make_float4(__uint_as_float(v[c][4 * j]), __uint_as_float(v[c][4 * j + 1]),
-                                     __uint_as_float(v[c][4 * j + 2]), __uint_as_float(v[c][4 * j + 3]));
-            }
-          }
-        }
+      uint32_t v[2][32];
+      tmem_ld_32x32(t_addr, v[0]);
+      tmem_ld_32x32(t_addr + 32, v[1]);
+      tmem_ld_wait();
+      tc_fence_before();  // accumulator share in registers: hand it back to the leader's MMA thread
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[buf], 0);
+      if (m < g.M) {
+        k5_write_cols32(g, v[0], bias_s, m, n0);
+        k5_write_cols32(g, v[1], bias_s + 32, m, n0 + 32);
       }
     }
   }
@@ -818,6 +822,168 @@ __global__ void __launch_bounds__(kAttnThreads, 3)
                  int(blockIdx.z), kAttnThreads, only_group >= 0);
 }
 
+// ---- K6w: the same attention for batches that fill the GPU with one CTA per (sample, head) ------------
+// k6_attention_kernel re-stages the visible K / V prefix in every (sample, head, group) CTA: 5.5x the bytes of
+// one head per (sample, head) and a stage -> wait -> compute -> merge sequence per 25 query rows with three small
+// CTAs per SM to hide it (b = 16: 2 560 CTAs, 32 us per layer, tensor pipe 21 % active, issue slots 42 % busy,
+// profiles/r2_k6_attention_b16.txt). Here a 256-thread CTA owns ALL T query rows of one (sample, head): K and V are
+// staged once, the T rows are cut into 16-row MMA tiles that ignore group borders, and warp w takes tiles
+// w, 15 - w, 16 + w, ... (short and long key prefixes paired, 5 or 6 key chunks per warp at T = 250). A tile walks
+// the 64-key chunks its LAST row may see; rows of the earlier group inside a tile are masked per element in the
+// chunks beyond their own prefix (every row sees chunk 0, so the running maximum is finite from the first chunk
+// on). No parity split, no merge through shared memory, one barrier per CTA.
+constexpr int kAttnWideThreads = 256;
+
+__global__ void __launch_bounds__(kAttnWideThreads, 2)
+    k6_attention_wide_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int d_model,
+                             int heads, int group_tokens, float scale_log2e) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int rows_pad = (T + kKeyChunk - 1) / kKeyChunk * kKeyChunk;
+  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem_attn);  // [rows_pad][72]
+  __nv_bfloat16* vs = ks + size_t(rows_pad) * kKVStride;            // [rows_pad][72]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int quad = lane >> 2, qlane = lane & 3;
+  const size_t row_stride = size_t(3) * d_model;
+  const __nv_bfloat16* base = qkv + size_t(b) * T * row_stride + h * kHeadDim;
+
+  for (int i = tid; i < rows_pad * 8; i += kAttnWideThreads) {
+    const int r = i >> 3, c = i & 7;
+    __nv_bfloat16* dk = ks + size_t(r) * kKVStride + 8 * c;
+    __nv_bfloat16* dv = vs + size_t(r) * kKVStride + 8 * c;
+    if (r < T) {
+      const __nv_bfloat16* src = base + size_t(r) * row_stride + 8 * c;
+      cp_async_16(dk, src + d_model);
+      cp_async_16(dv, src + 2 * d_model);
+    } else {  // padding rows of the last chunk: masked scores, but 0 * garbage must not produce NaN in P V
+      *reinterpret_cast<uint4*>(dk) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dv) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int n_tiles = (T + 15) / 16;
+  const uint32_t vs_u32 = smem_u32(vs);
+  constexpr int kWarps = kAttnWideThreads / 32;
+  for (int k = 0;; ++k) {
+    const int t = (k & 1) ? kWarps * (k + 1) - 1 - warp : kWarps * k + warp;
+    if (kWarps * (k & ~1) >= n_tiles) break;   // both tiles of this pair of rounds are past the end for every warp
+    if (t >= n_tiles) continue;
+    const int r0 = 16 * t + quad, r1 = r0 + 8;
+    const bool valid0 = r0 < T, valid1 = r1 < T;
+    const int last_row = min(16 * t + 15, T - 1);
+    const int vis_min = (16 * t / group_tokens + 1) * group_tokens;     // keys the tile's first row sees
+    const int vis_max = (last_row / group_tokens + 1) * group_tokens;   // keys its last row sees
+    const int vis0 = ((valid0 ? r0 : last_row) / group_tokens + 1) * group_tokens;
+    const int vis1 = ((valid1 ? r1 : last_row) / group_tokens + 1) * group_tokens;
+    const int n_chunks = (vis_max + kKeyChunk - 1) / kKeyChunk;
+    const __nv_bfloat16* q0 = base + size_t(valid0 ? r0 : 0) * row_stride;
+    const __nv_bfloat16* q1 = base + size_t(valid1 ? r1 : 0) * row_stride;
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const int col = 16 * kt + 2 * qlane;
+      qa[kt][0] = valid0 ? *reinterpret_cast<const uint32_t*>(q0 + col) : 0u;
+      qa[kt][1] = valid1 ? *reinterpret_cast<const uint32_t*>(q1 + col) : 0u;
+      qa[kt][2] = valid0 ? *reinterpret_cast<const uint32_t*>(q0 + col + 8) : 0u;
+      qa[kt][3] = valid1 ? *reinterpret_cast<const uint32_t*>(q1 + col + 8) : 0u;
+    }
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int key0 = ch * kKeyChunk;
+      float sc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+        const __nv_bfloat16* kp = ks + size_t(key0 + 8 * j + quad) * kKVStride + 2 * qlane;
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt)
+          mma_bf16_16816(sc[j], qa[kt], *reinterpret_cast<const uint32_t*>(kp + 16 * kt),
+                         *reinterpret_cast<const uint32_t*>(kp + 16 * kt + 8));
+      }
+      if (key0 + kKeyChunk > vis_min) {  // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int key = key0 + 8 * j + 2 * qlane;
+          if (key >= vis0) sc[j][0] = -INFINITY;
+          if (key + 1 >= vis0) sc[j][1] = -INFINITY;
+          if (key >= vis1) sc[j][2] = -INFINITY;
+          if (key + 1 >= vis1) sc[j][3] = -INFINITY;
+        }
+      }
+      float c0 = -INFINITY, c1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c0 = fmaxf(c0, fmaxf(sc[j][0], sc[j][1]));
+        c1 = fmaxf(c1, fmaxf(sc[j][2], sc[j][3]));
+      }
+      c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 1));
+      c0 = fmaxf(c0, __shfl_xor_sync(0xffffffffu, c0, 2));
+      c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 1));
+      c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, 2));
+      const float n0 = fmaxf(m0, c0), n1 = fmaxf(m1, c1);  // finite: chunk 0 holds a visible key for every row
+      const float a0 = exp2f((m0 - n0) * scale_log2e), a1 = exp2f((m1 - n1) * scale_log2e);
+      m0 = n0;
+      m1 = n1;
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j][0] = exp2f((sc[j][0] - m0) * scale_log2e);
+        sc[j][1] = exp2f((sc[j][1] - m0) * scale_log2e);
+        sc[j][2] = exp2f((sc[j][2] - m1) * scale_log2e);
+        sc[j][3] = exp2f((sc[j][3] - m1) * scale_log2e);
+        rs0 += sc[j][0] + sc[j][1];
+        rs1 += sc[j][2] + sc[j][3];
+      }
+      l0 = l0 * a0 + rs0;
+      l1 = l1 * a1 + rs1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j][0] *= a0;
+        o[j][1] *= a0;
+        o[j][2] *= a1;
+        o[j][3] *= a1;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(sc[2 * kk][0], sc[2 * kk][1]);
+        pa[1] = pack_bf16x2(sc[2 * kk][2], sc[2 * kk][3]);
+        pa[2] = pack_bf16x2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+        const uint32_t vrow = vs_u32 + uint32_t((key0 + 16 * kk + (lane & 7) + 8 * ((lane >> 3) & 1)) * kKVStride +
+                                                8 * (lane >> 4)) * 2u;
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {  // 16 output dims per step
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, vrow + uint32_t(16 * jp) * 2u);
+          mma_bf16_16816(o[2 * jp], pa, vb[0], vb[1]);
+          mma_bf16_16816(o[2 * jp + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    __nv_bfloat16* o0 = out + (size_t(b) * T + r0) * d_model + h * kHeadDim + 2 * qlane;
+    __nv_bfloat16* o1 = out + (size_t(b) * T + r1) * d_model + h * kHeadDim + 2 * qlane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (valid0) *reinterpret_cast<uint32_t*>(o0 + 8 * j) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+      if (valid1) *reinterpret_cast<uint32_t*>(o1 + 8 * j) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+    }
+  }
+}
+
 // ---- K7: y = LayerNorm(resid + sum_s partial[s] + bias) * gamma + beta ---------------------------
 // One WARP per row, 8 rows per CTA: lane l owns the 8-element chunks l, l+32, ... of the row (16-byte bf16 /
 // 32-byte fp32 pieces, coalesced across the warp), mean and variance are two xor-shuffle reductions — no shared
@@ -1027,10 +1193,11 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   const int ctas128 = (N / 128) * m_tiles * splits;
   const bool reduce = out_bf16 != nullptr && splits > 1;
   int bn = (ctas128 < 120 && !reduce) ? 64 : 128;  // fill the 148 SMs when tiles are few
-  if (const char* v = getenv("MRAG_K5_BN")) {  // tuning knob (scripts/cama_gemm_bench.py)
-    const int o = atoi(v);
-    if ((o == 64 || o == 128) && !reduce) bn = o;
-  }
+  static const int bn_knob = [] {  // MRAG_K5_BN: tuning knob (scripts/cama_gemm_bench.py), read once
+    const char* v = getenv("MRAG_K5_BN");
+    return v ? atoi(v) : 0;
+  }();
+  if ((bn_knob == 64 || bn_knob == 128) && !reduce) bn = bn_knob;
   CUtensorMap tm_a, tm_w;
   if (!make_tmap(&tm_a, a_bf16, a_rows_alloc, K, kGemmBM) || !make_tmap(&tm_w, w_bf16, N, K, bn))
     return cudaErrorInvalidValue;
@@ -1061,7 +1228,15 @@ cudaError_t launch_k5_linear(const void* a_bf16, int a_rows_alloc, const void* w
   }();
   const int m_pairs = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
   const int pair_tiles = (N % kPairBN == 0) ? (N / kPairBN) * m_pairs : 0;
-  if (!reduce && splits == 1 && persistent_ok && pair_ok && pair_tiles >= 2 * (sms / 2)) {
+  // The pair kernel also takes GEMMs of ONE round of 256 x 256 tiles when they occupy half of the pairs (N = 1024
+  // from b = 10 on: out-proj, FFN2; b = 16: 616 -> 590 us per forward): 128 x 128 tiles move twice the bytes per flop from L2 into shared memory, and that
+  // path, not the tensor pipe, bounds them (FFN2 at b = 16: 537 MB through it in 37 us).
+  static const int pair_min = [] {  // MRAG_K5_PAIR_MIN: smallest tile count for the pair kernel (A/B runs)
+    const char* v = getenv("MRAG_K5_PAIR_MIN");
+    return v ? atoi(v) : 0;
+  }();
+  const int pair_floor = pair_min > 0 ? pair_min : sms / 4;  // half of the pairs busy (b = 10: 520 -> 503 us per forward)
+  if (!reduce && splits == 1 && persistent_ok && pair_ok && pair_tiles >= pair_floor) {
     if (!make_tmap(&tm_w, w_bf16, N, K, kPairBN / 2)) return cudaErrorInvalidValue;
     e = cudaFuncSetAttribute(k5_linear_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kPairSmem));
     if (e != cudaSuccess) return e;
@@ -1102,15 +1277,30 @@ cudaError_t launch_k6_attention(const void* qkv, void* out, int b, int T, int d_
   if (d_model != heads * kHeadDim || groups * group_tokens != T || T > kAttnMaxT) return cudaErrorInvalidValue;
   const int rows_pad = (T + kKeyChunk - 1) / kKeyChunk * kKeyChunk;
   const size_t smem = size_t(rows_pad) * kKVStride * 2 * 2;
-  cudaError_t e = cudaFuncSetAttribute(k6_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  if (e != cudaSuccess) return e;
   const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   float scale_log2e = 1.4426950408889634f / sqrtf(float(kHeadDim));
-  void* args[] = {&q, &o, &T, &d_model, &heads, &group_tokens, &scale_log2e, &only_group};
-  e = launch_pdl(reinterpret_cast<const void*>(k6_attention_kernel),
-                 dim3(unsigned(b * heads), unsigned(only_group >= 0 ? 1 : groups), unsigned((group_tokens + 31) / 32)),
-                 dim3(kAttnThreads), smem, st, args);
+  // one CTA per (sample, head) once those alone load every SM; the (sample, head, group) grid below that. Measured
+  // per forward with the threshold moved: 128 pairs 422 vs 415 us, 160 pairs 520 vs 524 us, 256 pairs 590 vs 619 us.
+  static const int wide_min = [] {  // MRAG_K6_WIDE_MIN: (sample, head) count from which K6w runs; 0 = never (A/B runs)
+    const char* v = getenv("MRAG_K6_WIDE_MIN");
+    return v ? atoi(v) : 176;
+  }();
+  cudaError_t e;
+  if (only_group < 0 && wide_min > 0 && b * heads >= wide_min) {
+    e = cudaFuncSetAttribute(k6_attention_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    void* args[] = {&q, &o, &T, &d_model, &heads, &group_tokens, &scale_log2e};
+    e = launch_pdl(reinterpret_cast<const void*>(k6_attention_wide_kernel), dim3(unsigned(b * heads)),
+                   dim3(kAttnWideThreads), smem, st, args);
+  } else {
+    e = cudaFuncSetAttribute(k6_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    void* args[] = {&q, &o, &T, &d_model, &heads, &group_tokens, &scale_log2e, &only_group};
+    e = launch_pdl(reinterpret_cast<const void*>(k6_attention_kernel),
+                   dim3(unsigned(b * heads), unsigned(only_group >= 0 ? 1 : groups), unsigned((group_tokens + 31) / 32)),
+                   dim3(kAttnThreads), smem, st, args);
+  }
   note_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }

@@ -32,11 +32,15 @@ def timed(fn, reps=200):
     return statistics.median(ts)
 
 
-for b in (1, 2, 16):
+BATCHES = (1, 2, 16)
+for a in sys.argv[1:]:
+    if a.startswith("--b="):
+        BATCHES = tuple(int(v) for v in a[4:].split(","))
+for b in BATCHES:
     x = torch.randn(b, 250, 1024, device="cuda").bfloat16()
     cama.input_view(b).copy_(x)
     with torch.no_grad():
-        t_eager = timed(lambda: enc(x, mask))
+        t_eager = float("nan") if "--no-torch" in sys.argv else timed(lambda: enc(x, mask))
         t_graph = float("nan")
         if "--torch-graph" in sys.argv:   # torch's MHA fast path is not always capturable
             try:

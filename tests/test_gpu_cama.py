@@ -61,7 +61,10 @@ def test_linear_with_cluster_reduced_split_k(libmrag, M, N, K, bias, gelu, split
                                                      (6000, 2048, 256, False, False, True),
                                                      (12803, 384, 128, True, False, False),       # 128 x 128 tiles
                                                      (12803, 384, 192, False, False, True),
-                                                     (2500, 1024, 4096, False, False, True)])      # one tile per CTA
+                                                     (2500, 1024, 4096, False, False, True),       # one tile per CTA
+                                                     (4000, 1024, 4096, False, False, True),       # one round of 256 x 256 pair tiles
+                                                     (3900, 1024, 512, True, True, False),         # same, last pair half empty
+                                                     (3700, 1024, 1024, False, False, True)])
 def test_persistent_linear_for_many_tiles(libmrag, M, N, K, bias, gelu, partial):
     """More than one wave of 128 x 128 tiles runs the persistent kernel (double-buffered TMEM accumulators)."""
     from motionrag_b200.cama import linear
@@ -97,7 +100,12 @@ def _encoder(d, heads, dff, layers, seed):
 @pytest.mark.parametrize("b,G,L,d,heads,dff,layers", [(1, 10, 25, 1024, 16, 4096, 4), (3, 10, 25, 1024, 16, 4096, 4),
                                                       (2, 4, 5, 256, 4, 512, 2), (2, 3, 40, 512, 8, 1024, 2),
                                                       (10, 10, 25, 1024, 16, 4096, 2),   # 2 500 rows: persistent GEMMs, warp-per-row LayerNorm
-                                                      (9, 10, 25, 768, 12, 1536, 2)])
+                                                      (9, 10, 25, 768, 12, 1536, 2),
+                                                      # >= 176 (sample, head) pairs: one attention CTA per pair (K6w)
+                                                      (16, 10, 25, 1024, 16, 4096, 1),   # 4 000 rows: pair GEMMs for N = 1024 too
+                                                      (44, 3, 7, 256, 4, 512, 1),        # 21 tokens: second MMA tile mostly padding
+                                                      (22, 7, 13, 512, 8, 512, 2),       # 91 tokens, groups cut MMA tiles anywhere
+                                                      (22, 11, 64, 512, 8, 512, 1)])     # 704 tokens, the longest supported
 def test_forward_matches_reference_encoder(libmrag, b, G, L, d, heads, dff, layers):
     """Reference configuration (configs/cogvideox/MotionRAG_open.yml:253-267) and a small one."""
     from motionrag_b200 import CamaTransformer

@@ -344,3 +344,23 @@ def test_loss_path_host_logic_equals_the_reference_recording(monkeypatch, golden
             assert float(loss.mse.detach()) == pytest.approx(float(gold[f"{tag}_mse"]), rel=1e-6)
             assert float(loss.smooth.detach()) == pytest.approx(float(gold[f"{tag}_smooth"]), rel=1e-6)
             torch.testing.assert_close(model.sos_token.grad, torch.from_numpy(gold[f"{tag}_sos_grad"]), rtol=1e-5, atol=1e-8)
+
+
+def test_erfc_polynomial_gelu_of_the_gemm_epilogue_is_within_4e7_of_the_exact_gelu():
+    """k5_cama.cu::gelu_erf evaluates the reference's exact (erf) GELU (nn.TransformerEncoderLayer(activation='gelu'),
+    configs/cogvideox/MotionRAG_open.yml:253-267) through Abramowitz & Stegun 7.1.26; restated here in float32 step by
+    step and held to the float64 GELU: the bound the kernel comment quotes."""
+    from scipy.special import erf
+    f = np.float32
+    x = np.linspace(-8, 8, 400001).astype(f)
+    z = np.abs(x) * f(0.70710678118654752)
+    t = (f(1) / (f(0.3275911) * z + f(1))).astype(f)
+    p = f(1.061405429) * t + f(-1.453152027)
+    for c in (1.421413741, -0.284496736, 0.254829592):
+        p = (p * t + f(c)).astype(f)
+    e = np.exp2((z * z * f(-1.4426950408889634)).astype(f)).astype(f)
+    r = (np.abs(f(0.5) * x) * (p * t * e).astype(f)).astype(f)
+    got = np.where(x > 0, x - r, -r).astype(f)
+    want = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
+    assert np.abs(got - want).max() < 4e-7
+    assert np.abs(got - want).max() < 2.0 ** -9 * 1e-3      # three orders below a bf16 half-ulp at unit scale

@@ -30,6 +30,8 @@ from .where import parse as parse_where
 VECTOR_COLUMNS = ("text_embedding", "image_embedding")
 
 
+MAX_K = 32       # results per scan the kernels produce (mrag.h); larger top_k runs in passes, RAGDatabase._search_deep
+
 def _as_column(v):
     """Scalar columns are indexed with integer arrays: lists / tuples become numpy arrays."""
     return v if isinstance(v, np.ndarray) else np.asarray(v)
@@ -464,26 +466,84 @@ class RAGDatabase:
         batch size, for host and device inputs, for single-GPU and row-sharded tables."""
         column = vector_column_name or "text_embedding"
         store = self._store(column)
-        refine = int(min(64, max(top_k, top_k * max(1, int(refine_factor)))))
-        mode = "pre" if self.prefilter else "post"
         q, single = self._as_host_queries(vector)
+        if int(top_k) > MAX_K:
+            dist, idx = self._search_deep(store, q, int(top_k), where, refine_factor, exclude_group)
+            return dist, idx, single
+        mode = "pre" if self.prefilter else "post"
         preds = None
         if exclude_group is None:
             excl, preds = self._exclusion_ids(where, q.shape[0])
         else:
             excl = np.ascontiguousarray(exclude_group, dtype=np.int32)
+        dist, idx = self._scan(store, q, int(top_k), excl, mode, refine_factor, reuse)
+        if preds is not None:
+            self._apply_predicates(preds, dist, idx)
+        return dist, idx, single
+
+    def _scan(self, store, q, top_k: int, excl, mode: str, refine_factor, reuse: bool = False):
+        """One certified scan of at most MAX_K results per query -> (distance, index) numpy arrays."""
+        refine = int(min(64, max(top_k, top_k * max(1, int(refine_factor)))))
         certify = self.recheck is not None and self.path != "stream_f32"
         searcher = self._retriever if self._retriever is not None else store
         # reuse: result arrays are recycled between small calls (the caller builds its records right away)
-        res = searcher.search_host(q, int(top_k), metric=self.metric, path=self.path, refine=refine,
+        res = searcher.search_host(q, top_k, metric=self.metric, path=self.path, refine=refine,
                                    exclude_group=excl, filter_mode=mode, certify=certify,
                                    reuse=reuse and q.shape[0] <= 4)
         dist, idx = res[0], res[1]
         if certify:
             self._recheck(searcher, store, q, excl, dist, idx, res[3], top_k, mode)
-        if preds is not None:
+        return dist, idx
+
+    def _search_deep(self, store, q, top_k: int, where, refine_factor, exclude_group):
+        """top_k above the kernels' MAX_K = 32 results per scan (LanceDB takes any `limit`; the reference's own
+        callers stay below it, src/data/datamodule.py:234,241): the k nearest rows are collected in passes of 32.
+        Every pass scans with the rows already returned labelled as an excluded group (pre-filter in the scan, so
+        a pass returns exactly the next-nearest rows; ties keep the (distance, row) order across passes), one
+        query at a time because the label array is per query. `where` keeps its meaning: a post-filter over the
+        k nearest rows, or — `prefilter=True` — rows failing it are labelled taken before the first pass.
+        Costs one label upload (4 B per row) and one scan per 32 results; it exists for API completeness."""
+        if exclude_group is not None:
+            raise ValueError(f"exclude_group= is limited to top_k <= {MAX_K}; pass the clause as where=")
+        nq, n_rows = q.shape[0], len(self)
+        wheres = [where] * nq if (where is None or isinstance(where, str)) else list(where)
+        if len(wheres) != nq:
+            raise ValueError("need one where clause per query")
+        preds = []
+        for w in wheres:
+            hit = None if w is None else self._where_to_group(w)
+            preds.append(hit[2] if isinstance(hit, tuple) else hit)
+        dist = np.full((nq, top_k), np.inf, dtype=np.float32)
+        idx = np.full((nq, top_k), -1, dtype=np.int64)
+        one = np.ones(1, dtype=np.int32)
+        sharded = self._retriever is not None and self._retriever.world > 1
+        try:
+            for qi in range(nq):
+                taken = np.zeros(n_rows, dtype=np.int32)
+                if self.prefilter and preds[qi] is not None:
+                    taken[~preds[qi].evaluate(self._columns)] = 1
+                got = 0
+                while got < top_k:
+                    k = min(MAX_K, top_k - got)
+                    self._group_col = ("deep", qi, got)
+                    for st in self._stores.values():
+                        part = taken
+                        if sharded:
+                            lo = self._retriever.rank * self._retriever.rows_per_shard
+                            part = taken[lo:lo + len(st)]
+                        st.set_groups(part)
+                    d, i = self._scan(store, q[qi:qi + 1], k, one, "pre", refine_factor)
+                    n = int((i[0] >= 0).sum())
+                    dist[qi, got:got + n], idx[qi, got:got + n] = d[0, :n], i[0, :n]
+                    taken[i[0, :n]] = 1
+                    got += n
+                    if n < k:           # fewer eligible rows than asked for
+                        break
+        finally:
+            self._group_col = None      # the next ordinary call binds its own labelling again
+        if not self.prefilter and any(p is not None for p in preds):
             self._apply_predicates(preds, dist, idx)
-        return dist, idx, single
+        return dist, idx
 
     def _scan_profile(self, store, nq: int, top_k: int) -> tuple[str, int, float]:
         """(scan path AUTO resolves to, length of its candidate lists, margin threshold) for this call shape."""

@@ -197,6 +197,48 @@ def test_general_where_clauses_match_the_oracle(libmrag, table, prefilter):
             _same(o, ora.text_search(q, top_k=12, where=w, select=['id', 'video', 'start_sec']))
 
 
+@pytest.mark.parametrize("prefilter", [False, True])
+def test_top_k_above_the_kernels_32_runs_in_passes_and_matches_the_oracle(libmrag, table, prefilter):
+    """LanceDB takes any `limit` (src/data/rag.py:54 forwards top_k); above 32 results the drop-in collects the k
+    nearest rows in passes of 32: same rows, order and distances as the oracle — with where clauses (post- and
+    pre-filter), duplicate rows across a pass border, a batch, and more results asked for than rows exist."""
+    from motionrag_b200 import RAGDatabase
+    t = dict(table)
+    emb = table["text_embedding"].copy()
+    emb[[40, 41, 42, 43]] = emb[39]                   # five identical rows: ties straddle the 32-result border below
+    t["text_embedding"] = emb
+    db = RAGDatabase(None, None, 'cuda', columns=t, prefilter=prefilter)
+    ora = fs.OracleRAGDatabase(t, prefilter=prefilter)
+    rng = np.random.default_rng(21)
+    sel = ['id', 'video', 'start_sec']
+    for k, w in [(33, None), (50, 'video != "clip_00013.mp4"'), (100, "start_sec >= 2"), (64, "id >= 3000 or start_sec = 0")]:
+        for j in (39, int(rng.integers(0, 6000))):
+            q = (emb[j] + 0.02 * rng.standard_normal(768)).astype(np.float32) * 3
+            got, want = db.text_search(q, top_k=k, where=w, select=sel), ora.text_search(q, top_k=k, where=w, select=sel)
+            _same(got, want)
+            assert len(got) == k if (w is None or prefilter) else len(got) <= k
+    # the duplicates sit inside the first 40 results in ascending row order
+    ids = [r["id"] for r in db.text_search(emb[39] * 2, top_k=40, select=['id'])]
+    assert ids[:5] == [39, 40, 41, 42, 43]
+    # an ordinary call afterwards binds its own labelling again
+    kw = dict(text=emb[7] * 2, top_k=12, where=f'video != "{t["video"][7]}"', select=sel)
+    _same(db.text_search(**kw), ora.text_search(**kw))
+    # batch form
+    qs = (emb[[5, 600, 4242]] * 2).astype(np.float32)
+    for q, o in zip(qs, db.search_batch(qs, top_k=45, where="end_sec <= 4", select=sel)):
+        _same(o, ora.text_search(q, top_k=45, where="end_sec <= 4", select=sel))
+    # more than the table holds
+    small = {c: v[:50] for c, v in t.items()}
+    got = RAGDatabase(None, None, 'cuda', columns=small).text_search(emb[3], top_k=80, select=['id'])
+    _same(got, fs.OracleRAGDatabase(small).text_search(emb[3], top_k=80, select=['id']))
+    assert len(got) == 50
+    # two-stage search with ref_video_num = 20: k0 = 2 * 20 + 3 = 43 text hits feed the image stage (datamodule.py:241)
+    if not prefilter:
+        kw = dict(text=emb[100] * 2, image_embedding=table["image_embedding"][100] * 2, top_k=(43, 20),
+                  where=f'video != "{t["video"][100]}"', select=sel)
+        _same(db.text_image_search(**kw), ora.text_image_search(**kw))
+
+
 @pytest.mark.parametrize("container", ["parquet", "arrow", "fragments"])
 def test_arrow_dump_of_the_reference_table_opens_and_matches_the_oracle(libmrag, table, tmp_path, container):
     """A pyarrow-written table with the schema tools/build_rag_database.py:35-45 produces (FixedSizeList<f32>[768]

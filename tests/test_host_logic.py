@@ -364,3 +364,50 @@ def test_erfc_polynomial_gelu_of_the_gemm_epilogue_is_within_4e7_of_the_exact_ge
     want = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
     assert np.abs(got - want).max() < 4e-7
     assert np.abs(got - want).max() < 2.0 ** -9 * 1e-3      # three orders below a bf16 half-ulp at unit scale
+
+
+@pytest.mark.parametrize("prefilter", [False, True])
+def test_top_k_above_32_is_collected_in_passes_of_32(prefilter):
+    """RAGDatabase._search_deep (host logic; the scans are played by the oracle's flat search standing in for the
+    store): same rows, order and distances as ONE oracle search with the large k, for post- and pre-filter clauses."""
+    from oracle import flat_search as fs
+    db = _db_no_gpu(n=300, dim=16)
+    emb = db._vectors["text_embedding"]
+    emb[[40, 41, 42]] = emb[39]                                      # ties across the first pass border
+    calls = []
+
+    class Store:
+        dim = 16
+        groups = None
+
+        def __len__(self):
+            return 300
+
+        def set_groups(self, g):
+            self.groups = np.array(g, dtype=np.int64)
+
+        def search_host(self, q, k, *, metric, path, refine, exclude_group, filter_mode, certify, reuse=False, list_len=0):
+            assert 1 <= k <= 32 and filter_mode == "pre" and exclude_group.tolist() == [1] and q.shape[0] == 1
+            calls.append(k)
+            d, i = fs.flat_search(emb, q, k, metric, self.groups, np.array([1]), True)
+            return d.astype(np.float32), i.astype(np.int64), None
+
+    db._stores = {"text_embedding": Store()}
+    db.metric, db.path, db.prefilter, db.recheck = "l2", "auto", prefilter, None
+    ora = fs.OracleRAGDatabase({**db._columns, "text_embedding": emb}, prefilter=prefilter)
+    rng = np.random.default_rng(3)
+    for k, w in [(33, None), (70, "start_sec >= 100"), (100, 'video != "v13"'), (64, "id < 20 or id > 250")]:
+        q = (emb[39] + 0.05 * rng.standard_normal(16)).astype(np.float32)
+        calls.clear()
+        dist, idx, single = db._search(q, None, k, w, 30)
+        want = ora.text_search(q, top_k=k, where=w, select=["id"])
+        n = int((idx[0] >= 0).sum())
+        assert single and idx[0, :n].tolist() == [r["id"] for r in want] and (idx[0, n:] == -1).all()
+        np.testing.assert_allclose(dist[0, :n], [r["_distance"] for r in want], rtol=1e-5, atol=1e-6)
+        assert calls == [32] * (k // 32) + ([k % 32] if k % 32 else [])
+        assert db._group_col is None                                 # the next ordinary call re-binds its labelling
+    # more results than rows: passes stop when a scan comes back short
+    dist, idx, _ = db._search(emb[:2], None, 320, None, 30)
+    assert (idx >= 0).sum(-1).tolist() == [300, 300] and sorted(idx[1, :300].tolist()) == list(range(300))
+    with pytest.raises(ValueError, match="exclude_group"):
+        db._search(emb[0], None, 40, None, 30, exclude_group=np.zeros(1, dtype=np.int32))
